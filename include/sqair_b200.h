@@ -1,0 +1,149 @@
+/* sqair_b200 -- C ABI of the B200-native SQAIR Discover/Propagate hot path.
+ *
+ * The reference (akosiorek/sqair @ 474f5d0) is pure Python building a TF1/Sonnet graph; it has no
+ * FFI.  The operator this library replaces is `SequentialAIR.__call__` (sqair/seq.py:69-84: the
+ * `tf.while_loop` over frames whose body is seq.py:181-269) together with the objective of
+ * `Model._build` / `Model.make_target` (sqair/model.py:79-168, sqair/targets.py:38-75).  Each entry
+ * point below names the reference code it stands in for.  The ctypes binding a maintainer of the
+ * reference would add is shown in INTEGRATION.md.
+ *
+ * Conventions: every pointer is a DEVICE pointer owned by the caller unless the name says `host`;
+ * the library never allocates device memory; all work is enqueued on `stream` (a cudaStream_t passed
+ * as void*; NULL = legacy default stream) and is asynchronous.  Functions return 0 on success or a
+ * negative code; `sqair_last_error()` returns a thread-local message for the last failure.
+ * All tensors are fp32, C-contiguous.
+ */
+#ifndef SQAIR_B200_H
+#define SQAIR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { SQAIR_OK = 0, SQAIR_EINVAL = -1, SQAIR_EUNSUPPORTED = -2, SQAIR_ECUDA = -3 };
+enum { SQAIR_PRIOR_RNN = 0, SQAIR_PRIOR_RW = 1, SQAIR_PRIOR_GUIDED = 2 };   /* propagate.py:35-45 */
+enum { SQAIR_DISC_PRIOR_CAT = 0, SQAIR_DISC_PRIOR_GEOM = 1 };               /* sqair_modules.py:205-224 */
+
+/* Model / problem description: the flags of common_model_flags.py:32-56 and
+ * configs/mlp_mnist_model.py:42-52 plus the tensor sizes of the call. */
+typedef struct sqair_cfg {
+    int32_t T;                 /* frames in the sequence                                   */
+    int32_t B;                 /* sequences handled by THIS call (the local shard)          */
+    int32_t K;                 /* k_particles; rows = B*K, row = b*K + k (index.py:106-129) */
+    int32_t n;                 /* n_steps_per_image (object slots)                          */
+    int32_t H, W;              /* canvas size (C = 1)                                       */
+    int32_t G;                 /* glimpse_size                                              */
+    int32_t n_what;            /* n_what                                                    */
+    int32_t n_hidden;          /* 32 * n_units                                              */
+    int32_t prior_type;        /* SQAIR_PRIOR_*                                             */
+    int32_t disc_prior_type;   /* SQAIR_DISC_PRIOR_*                                        */
+    int32_t rec_where_prior;   /* bool                                                      */
+    int32_t masked_glimpse;    /* bool                                                      */
+    float step_success_prob;   /* geom prior only                                           */
+    float prop_prior_step_bias;
+    float output_std, bg_std;  /* std of p(x|z) inside / outside glimpses (modules.py:406-426) */
+    float where_update_scale;  /* core.py:258-260 (non-trainable)                           */
+    float min_std;             /* modules.py:72 (non-trainable)                             */
+    float where_mean[4], where_std[4];   /* disc where prior when rec_where_prior == 0      */
+} sqair_cfg;
+
+typedef struct sqair_sizes {
+    int64_t param_count;       /* trainable scalars, canonical (TF variable order) layout   */
+    int64_t packed_floats;     /* floats of the kernel-side parameter buffer                */
+    int64_t eps_where_floats, eps_what_floats, u_pres_floats;   /* noise tensors            */
+    int32_t rows;              /* B*K                                                       */
+    int32_t rows_per_cta;      /* rows each thread block carries through the sequence       */
+    int32_t n_ctas;
+    int32_t smem_bytes;        /* dynamic shared memory per thread block                    */
+    int32_t n_layers;          /* dense layers in the per-frame schedule                    */
+} sqair_sizes;
+
+/* One trainable variable of the reference (names as printed by notebooks/play.ipynb:239-362). */
+typedef struct sqair_param_desc {
+    char name[160];
+    int32_t ndim;
+    int32_t shape[3];
+    int64_t offset;            /* into the canonical flat buffer (tight, variable order)    */
+    int64_t packed_offset;     /* into the kernel-side buffer (16-byte aligned)             */
+} sqair_param_desc;
+
+/* The 38 per-frame outputs of SequentialAIR (seq.py:121-177), each [T, rows, ...].  NULL = skip. */
+typedef struct sqair_outputs {
+    float *what, *what_loc, *what_scale;          /* [T,rows,n,n_what]                       */
+    float *where, *where_loc, *where_scale;       /* [T,rows,n,4]                            */
+    float *presence_prob, *presence, *presence_logit;   /* [T,rows,n]                        */
+    float *obj_id;                                /* [T,rows,n]                              */
+    float *step_log_prob;                         /* [T,rows]                                */
+    float *canvas;                                /* [T,rows,H,W]                            */
+    float *glimpse;                               /* [T,rows,n,G,G]                          */
+    float *disc_what_log_prob, *disc_where_log_prob, *disc_what_prior_log_prob, *disc_where_prior_log_prob; /* [T,rows,n] */
+    float *disc_log_prob, *disc_prior_log_prob;   /* [T,rows]                                */
+    float *disc_prob;                             /* [T,rows,n+1]                            */
+    float *prop_what_log_prob, *prop_where_log_prob, *prop_what_prior_log_prob, *prop_where_prior_log_prob; /* [T,rows,n] */
+    float *prop_log_prob, *prop_prior_log_prob;   /* [T,rows]                                */
+    float *prop_prob;                             /* [T,rows,n]                              */
+    float *discrete_log_prob;                     /* [T,rows]                                */
+    float *num_prop_steps_per_sample, *num_disc_steps_per_sample, *num_steps_per_sample;   /* [T,rows] */
+    float *prop_pres, *disc_pres;                 /* [T,rows,n]                              */
+    float *data_ll_per_sample, *kl_per_sample, *log_q_z_given_x_per_sample, *log_p_z_per_sample,
+          *log_weights_per_timestep;              /* [T,rows]                                */
+} sqair_outputs;
+
+/* Scalars produced by sqair_objective (model.py:88-103,150-158; targets.py:38-75; ops.py:52-59). */
+enum { SQAIR_OBJ_ELBO_VAE = 0, SQAIR_OBJ_ELBO_IWAE = 1, SQAIR_OBJ_ESS = 2, SQAIR_OBJ_VIMCO_TARGET = 3,
+       SQAIR_OBJ_IWAE_TARGET = 4, SQAIR_OBJ_N = 8 };
+
+const char* sqair_last_error(void);
+int sqair_version(void);
+
+/* Sizes implied by a configuration; also validates it (replaces the graph-build shape logic of
+ * seq.py:86-179 and the variable creation of configs/mlp_mnist_model.py:74-150). */
+int sqair_query_sizes(const sqair_cfg* cfg, sqair_sizes* out);
+
+/* Table of the reference's trainable variables in canonical order.  `descs` may be NULL to query
+ * the count; otherwise *n holds the capacity on entry and the count on return. */
+int sqair_param_layout(const sqair_cfg* cfg, sqair_param_desc* descs, int32_t* n);
+
+/* canonical flat parameters -> kernel-side (aligned) buffer. */
+int sqair_pack_params(const sqair_cfg* cfg, const float* params, float* packed, void* stream);
+
+/* Counter-based draws for every noise site of the path (core.py:143,218,227,
+ * 330,356): Philox4x32-10 keyed by `seed`, counter (row_offset + row, frame, slot, block), so a
+ * shard of rows reproduces exactly the draws of the unsharded run.
+ * eps_where [T,rows,2n,4], eps_what [T,rows,2n,n_what], u_pres [T,rows,2n]. */
+int sqair_fill_noise(const sqair_cfg* cfg, uint64_t seed, int32_t row_offset,
+                     float* eps_where, float* eps_what, float* u_pres, void* stream);
+
+/* SequentialAIR.__call__ (seq.py:69-84): the whole T-frame Discover/Propagate recursion in one
+ * persistent kernel.  obs is [T,B,H,W] (NOT tiled: the K particles of a sequence share its frame,
+ * replacing index.tile_input_for_iwae, index.py:106-129). */
+int sqair_forward(const sqair_cfg* cfg, const float* packed_params, const float* obs,
+                  const float* eps_where, const float* eps_what, const float* u_pres,
+                  const sqair_outputs* out, void* stream);
+
+/* Model._build / make_target reductions over particles (model.py:88-103,150-158).
+ * log_w_t, disc_lp_t: [T, B*K] per-frame log weights / discrete log-probs.  Outputs (nullable):
+ * log_weights [B,K], elbo_iwae_per_example [B], importance_weights [B,K], scalars [SQAIR_OBJ_N]. */
+int sqair_objective(const float* log_w_t, const float* disc_lp_t, int32_t T, int32_t B, int32_t K,
+                    float* log_weights, float* elbo_iwae_per_example, float* importance_weights,
+                    float* scalars, void* stream);
+
+/* Per-op entry points (unit parity / roofline of the bandwidth-shaped pieces).
+ * sqair_stn_glimpse: SpatialTransformer forward (modules.py:165-172,204-218): img [N,H,W],
+ *   where-logits [N,4] -> glimpse [N,G,G].
+ * sqair_canvas_ll: AIRDecoder._decode/_add_mean_image + pixel likelihood (modules.py:435-467,
+ *   seq.py:272-273): glimpse [N,n,G,G], where [N,n,4], presence [N,n], mean_img [H,W], img [N,H,W]
+ *   -> canvas [N,H,W], data_ll [N]. */
+int sqair_stn_glimpse(const float* img, const float* where, float* glimpse,
+                      int32_t N, int32_t H, int32_t W, int32_t G, void* stream);
+int sqair_canvas_ll(const float* glimpse, const float* where, const float* presence, const float* mean_img,
+                    const float* img, float* canvas, float* data_ll,
+                    int32_t N, int32_t n, int32_t H, int32_t W, int32_t G, float output_std, float bg_std,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQAIR_B200_H */

@@ -1,0 +1,447 @@
+// sqair_api.cu -- CUDA kernels (sm_100a) and the C ABI of include/sqair_b200.h.
+//
+// The hot path is ONE persistent kernel per call: `sqair_sequence_kernel<R>` runs the whole
+// T-frame Discover/Propagate recursion for R rows per thread block with all recurrent state in
+// shared memory (sqair_device.cuh).  Small auxiliary kernels: parameter packing, counter-based
+// noise, the particle objective, and stand-alone entry points for the two bandwidth-shaped ops
+// (glimpse sampler, canvas compose + likelihood).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string>
+
+#include "sqair_device.cuh"
+
+using namespace sq;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    return fail(SQAIR_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CUDA_TRY(x)                                  \
+    do {                                             \
+        cudaError_t e_ = (x);                        \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #x); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// persistent sequence kernel
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(NT) sqair_sequence_kernel(const __grid_constant__ Plan plan,
+                                                            const __grid_constant__ Job job) {
+    extern __shared__ __align__(16) float smem[];
+    Ctx c{(int)threadIdx.x, (int)blockDim.x, (int)(threadIdx.x & 31), 32, (int)(threadIdx.x >> 5),
+          (int)(blockDim.x >> 5), smem};
+    Block<R> blk(c, plan, job, (int)blockIdx.x * R);
+    blk.run();
+}
+
+static const int kRowChoices[] = {1, 2, 3, 4, 5, 8};
+static const int kSmemLimit = 232448;    // 227 KB opt-in shared memory per block on sm_100
+
+template <int R>
+static int launch_sequence(const Plan& plan, const Job& job, cudaStream_t st) {
+    const int smem_bytes = plan.sm.total * (int)sizeof(float);
+    CUDA_TRY(cudaFuncSetAttribute(sqair_sequence_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    const int nblk = (plan.rows + R - 1) / R;
+    sqair_sequence_kernel<R><<<nblk, NT, smem_bytes, st>>>(plan, job);
+    CUDA_TRY(cudaGetLastError());
+    return SQAIR_OK;
+}
+
+// Rows per block R.  More rows per block = fewer re-reads of the weights from L2 but fewer blocks;
+// default: the largest supported R that fits shared memory and still yields >= 64 blocks, else R = 1.
+// SQAIR_ROWS_PER_CTA overrides (used by the tuning sweeps in bench.py).
+static int choose_rows(const sqair_cfg& c, const std::vector<ParamEntry>& tab, Plan& plan, std::string& err) {
+    const int rows = c.B * c.K;
+    int forced = 0;
+    if (const char* e = getenv("SQAIR_ROWS_PER_CTA")) forced = atoi(e);
+    int best = 0;
+    for (int R : kRowChoices) {
+        if (forced && R != forced) continue;
+        Plan p;
+        std::string e2 = build_plan(c, R, p, tab);
+        if (!e2.empty()) { err = e2; return 0; }
+        if (p.sm.total * (int)sizeof(float) > kSmemLimit) continue;
+        const int nblk = (rows + R - 1) / R;
+        if (best == 0 || forced || nblk >= 64) { best = R; plan = p; }
+    }
+    if (best == 0) err = forced ? "SQAIR_ROWS_PER_CTA value unsupported or does not fit shared memory"
+                                : "configuration does not fit shared memory";
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// auxiliary kernels
+// ---------------------------------------------------------------------------------------------
+struct PackTab {
+    int n;
+    int src[128], dst[128], cnt[128];
+};
+
+__global__ void pack_kernel(const __grid_constant__ PackTab tab, const float* __restrict__ src, float* __restrict__ dst,
+                            int total) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int lo = 0, hi = tab.n - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (tab.src[mid] <= i) lo = mid; else hi = mid - 1;
+        }
+        dst[tab.dst[lo] + (i - tab.src[lo])] = src[i];
+    }
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter = (row, frame, slot, block), key = seed.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+    const float u1 = ((float)(a >> 8) + 1.0f) * 5.9604644775390625e-8f;    // (0, 1]
+    const float r = sqrtf(-2.0f * logf(u1));
+    const float th = 6.283185307179586f * u01(b);
+    z0 = r * cosf(th);
+    z1 = r * sinf(th);
+}
+
+__global__ void noise_kernel(int T, int rows, int n2, int nw, uint32_t k0, uint32_t k1, int row_offset,
+                             float* __restrict__ eps_where, float* __restrict__ eps_what, float* __restrict__ u_pres) {
+    const int nblk = (nw + 3) / 4;          // what blocks; block 0 = where, block nblk+1 = presence
+    const long long total = (long long)T * rows * n2 * (nblk + 2);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i % (nblk + 2));
+        const long long site = i / (nblk + 2);            // (t, row, slot)
+        const int s = (int)(site % n2);
+        const int row = (int)((site / n2) % rows);
+        const int t = (int)(site / ((long long)n2 * rows));
+        uint32_t x[4];
+        if (j == nblk + 1) {
+            philox4x32_10((uint32_t)(row + row_offset), (uint32_t)t, (uint32_t)s, 63u, k0, k1, x);
+            u_pres[site] = u01(x[0]);
+        } else {
+            philox4x32_10((uint32_t)(row + row_offset), (uint32_t)t, (uint32_t)s, (uint32_t)j, k0, k1, x);
+            float z[4];
+            box_muller(x[0], x[1], z[0], z[1]);
+            box_muller(x[2], x[3], z[2], z[3]);
+            if (j == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) eps_where[site * 4 + q] = z[q];
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int d = (j - 1) * 4 + q;
+                    if (d < nw) eps_what[site * nw + d] = z[q];
+                }
+            }
+        }
+    }
+}
+
+// Particle reductions (model.py:88-103,150-158; targets.py:38-75; ops.py:52-59).  One block; thread b
+// owns sample b (K is small), then a block reduction for the batch means.
+__global__ void objective_kernel(const float* __restrict__ lw_t, const float* __restrict__ lp_t, int T, int B, int K,
+                                 float* __restrict__ log_weights, float* __restrict__ iwae_pe,
+                                 float* __restrict__ imp_w, float* __restrict__ scalars) {
+    __shared__ float red[4][32];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};      // sum lw, sum iwae, sum ess, sum vimco proxy
+    const float logK = logf((float)K);
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float S = 0.f, mx = -INFINITY;
+        for (int k = 0; k < K; ++k) {
+            float a = 0.f;
+            for (int t = 0; t < T; ++t) a += lw_t[(size_t)t * B * K + b * K + k];
+            if (log_weights) log_weights[b * K + k] = a;
+            S += a;
+            mx = fmaxf(mx, a);
+        }
+        // second pass re-sums from global (K*T small) to avoid a K-sized local array
+        float se = 0.f;
+        for (int k = 0; k < K; ++k) {
+            float a = 0.f;
+            for (int t = 0; t < T; ++t) a += lw_t[(size_t)t * B * K + b * K + k];
+            se += expf(a - mx);
+        }
+        const float lse = mx + logf(se);
+        const float iw = lse - logK;                                        // targets.py:38-43
+        if (iwae_pe) iwae_pe[b] = iw;
+        float sw = 0.f, sw2 = 0.f, proxy = 0.f;
+        for (int j = 0; j < K; ++j) {
+            float lwj = 0.f, lpj = 0.f;
+            for (int t = 0; t < T; ++t) {
+                lwj += lw_t[(size_t)t * B * K + b * K + j];
+                if (lp_t) lpj += lp_t[(size_t)t * B * K + b * K + j];
+            }
+            const float w = expf(lwj - lse);                                // softmax, model.py:100
+            if (imp_w) imp_w[b * K + j] = w;
+            sw += w;
+            sw2 += w * w;
+            // VIMCO control variate (targets.py:46-59): logsumexp over i of (i == j ? mean_{i != j} lw : lw_i) - log K
+            const float abo = (S - lwj) / ((float)K - 1.f);
+            float m2 = abo;
+            for (int i = 0; i < K; ++i) {
+                if (i == j) continue;
+                float a = 0.f;
+                for (int t = 0; t < T; ++t) a += lw_t[(size_t)t * B * K + b * K + i];
+                m2 = fmaxf(m2, a);
+            }
+            float s2 = expf(abo - m2);
+            for (int i = 0; i < K; ++i) {
+                if (i == j) continue;
+                float a = 0.f;
+                for (int t = 0; t < T; ++t) a += lw_t[(size_t)t * B * K + b * K + i];
+                s2 += expf(a - m2);
+            }
+            const float cv = m2 + logf(s2) - logK;
+            proxy += -iw - (lwj - cv) * lpj;                                // targets.py:62-75
+        }
+        acc[0] += S;
+        acc[1] += iw;
+        acc[2] += sw * sw / sw2;                                            // ops.py:52-59
+        acc[3] += proxy;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float v = warp_sum(acc[q]);
+        if (lane == 0) red[q][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && scalars) {
+        float tot[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int q = 0; q < 4; ++q)
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot[q] += red[q][w];
+        for (int q = 0; q < SQAIR_OBJ_N; ++q) scalars[q] = 0.f;
+        scalars[SQAIR_OBJ_ELBO_VAE] = tot[0] / (float)(B * K);
+        scalars[SQAIR_OBJ_ELBO_IWAE] = tot[1] / (float)B;
+        scalars[SQAIR_OBJ_ESS] = tot[2] / (float)B;
+        scalars[SQAIR_OBJ_VIMCO_TARGET] = tot[3] / (float)(B * K) / (float)T;   // model.py:158
+        scalars[SQAIR_OBJ_IWAE_TARGET] = -(tot[1] / (float)B) / (float)T;
+    }
+}
+
+// SpatialTransformer forward (modules.py:165-172,204-218): one thread per glimpse texel.
+__global__ void stn_glimpse_kernel(const float* __restrict__ img, const float* __restrict__ where,
+                                   float* __restrict__ glimpse, int N, int H, int W, int G) {
+    const long long total = (long long)N * G * G;
+    const float hw = 0.5f * (float)(W - 1), hh = 0.5f * (float)(H - 1);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int gx = (int)(i % G), gy = (int)((i / G) % G);
+        const int nidx = (int)(i / ((long long)G * G));
+        const float* wl = where + (size_t)nidx * 4;
+        const float sx = fmaxf(sigmoidf_(__ldg(wl)), 1e-4f), sy = fmaxf(sigmoidf_(__ldg(wl + 1)), 1e-4f);
+        const float tx = tanhf(__ldg(wl + 2)), ty = tanhf(__ldg(wl + 3));
+        const float x = hw * (sx * lin11(gx, G) + tx) + hw;
+        const float y = hh * (sy * lin11(gy, G) + ty) + hh;
+        const float* im = img + (size_t)nidx * H * W;
+        glimpse[i] = bilinear_zero_pad(x, y, W, H, [&](int ix, int iy) { return __ldg(im + iy * W + ix); });
+    }
+}
+
+// AIRDecoder._decode/_add_mean_image + Normal(canvas, std).log_prob(img) (modules.py:435-467; seq.py:272-273).
+// One block per image; the n decoded glimpses are staged in shared memory.
+__global__ void canvas_ll_kernel(const float* __restrict__ glimpse, const float* __restrict__ where,
+                                 const float* __restrict__ presence, const float* __restrict__ mean_img,
+                                 const float* __restrict__ img, float* __restrict__ canvas, float* __restrict__ data_ll,
+                                 int n, int H, int W, int G, float output_std, float bg_std) {
+    extern __shared__ float sg[];              // [n][G*G] then coords [n][5]
+    const int b = blockIdx.x, g = G * G;
+    float* cc = sg + n * g;
+    for (int i = threadIdx.x; i < n * g; i += blockDim.x) sg[i] = glimpse[(size_t)b * n * g + i];
+    for (int s = threadIdx.x; s < n; s += blockDim.x) {
+        const float* wl = where + ((size_t)b * n + s) * 4;
+        cc[s * 5 + 0] = fmaxf(sigmoidf_(wl[0]), 1e-4f);
+        cc[s * 5 + 1] = fmaxf(sigmoidf_(wl[1]), 1e-4f);
+        cc[s * 5 + 2] = tanhf(wl[2]);
+        cc[s * 5 + 3] = tanhf(wl[3]);
+        cc[s * 5 + 4] = presence[(size_t)b * n + s];
+    }
+    __syncthreads();
+    const float hg = 0.5f * (float)(G - 1);
+    const float sf0 = sqrtf(output_std), sb0 = sqrtf(bg_std);
+    const float sf = sf0 * sf0, sb = sb0 * sb0;
+    float ll = 0.f;
+    for (int px = threadIdx.x; px < H * W; px += blockDim.x) {
+        const int iy = px / W, ix = px % W;
+        const float u = lin11(ix, W), v = lin11(iy, H);
+        float cv = 0.f, nz = 0.f;
+        for (int s = 0; s < n; ++s) {
+            const float pres = cc[s * 5 + 4];
+            if (pres == 0.f) continue;
+            const float xg = hg * ((u - cc[s * 5 + 2]) / cc[s * 5 + 0]) + hg;
+            const float yg = hg * ((v - cc[s * 5 + 3]) / cc[s * 5 + 1]) + hg;
+            const float* gl = sg + s * g;
+            cv += pres * bilinear_zero_pad(xg, yg, G, G, [&](int gx, int gy) { return gl[gy * G + gx]; });
+            nz += pres * bilinear_zero_pad(xg, yg, G, G, [&](int, int) { return 1.f; });
+        }
+        const float mask = sigmoidf_(-10.f + nz * 20.f);
+        cv += __ldg(mean_img + px) * mask;
+        const float std = mask * sf + (1.f - mask) * sb;
+        ll += normal_lp(__ldg(img + (size_t)b * H * W + px), cv, std);
+        canvas[(size_t)b * H * W + px] = cv;
+    }
+    __shared__ float red[32];
+    ll = warp_sum(ll);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ll;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += red[w];
+        data_ll[b] = a;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* sqair_last_error(void) { return g_err.c_str(); }
+int sqair_version(void) { return 100; }
+
+int sqair_query_sizes(const sqair_cfg* cfg, sqair_sizes* out) {
+    if (!cfg || !out) return fail(SQAIR_EINVAL, "null argument");
+    std::string e = validate_cfg(*cfg);
+    if (!e.empty()) return fail(SQAIR_EINVAL, e);
+    auto tab = param_table(*cfg);
+    Plan plan;
+    int R = choose_rows(*cfg, tab, plan, e);
+    if (R == 0) return fail(SQAIR_EUNSUPPORTED, e);
+    const int64_t rows = (int64_t)cfg->B * cfg->K, sites = (int64_t)cfg->T * rows * 2 * cfg->n;
+    out->param_count = tab.back().offset + tab.back().count;
+    out->packed_floats = packed_floats(tab);
+    out->eps_where_floats = sites * 4;
+    out->eps_what_floats = sites * cfg->n_what;
+    out->u_pres_floats = sites;
+    out->rows = (int32_t)rows;
+    out->rows_per_cta = R;
+    out->n_ctas = (int32_t)((rows + R - 1) / R);
+    out->smem_bytes = plan.sm.total * (int)sizeof(float);
+    out->n_layers = L_COUNT;
+    return SQAIR_OK;
+}
+
+int sqair_param_layout(const sqair_cfg* cfg, sqair_param_desc* descs, int32_t* n) {
+    if (!cfg || !n) return fail(SQAIR_EINVAL, "null argument");
+    std::string e = validate_cfg(*cfg);
+    if (!e.empty()) return fail(SQAIR_EINVAL, e);
+    auto tab = param_table(*cfg);
+    if (!descs) { *n = (int32_t)tab.size(); return SQAIR_OK; }
+    if (*n < (int32_t)tab.size()) return fail(SQAIR_EINVAL, "descriptor array too small");
+    for (size_t i = 0; i < tab.size(); ++i) {
+        sqair_param_desc& d = descs[i];
+        memset(&d, 0, sizeof(d));
+        snprintf(d.name, sizeof(d.name), "%s", tab[i].name.c_str());
+        d.ndim = tab[i].ndim;
+        for (int k = 0; k < 3; ++k) d.shape[k] = tab[i].shape[k];
+        d.offset = tab[i].offset;
+        d.packed_offset = tab[i].packed_offset;
+    }
+    *n = (int32_t)tab.size();
+    return SQAIR_OK;
+}
+
+int sqair_pack_params(const sqair_cfg* cfg, const float* params, float* packed, void* stream) {
+    if (!cfg || !params || !packed) return fail(SQAIR_EINVAL, "null argument");
+    std::string e = validate_cfg(*cfg);
+    if (!e.empty()) return fail(SQAIR_EINVAL, e);
+    auto tab = param_table(*cfg);
+    if (tab.size() > 128) return fail(SQAIR_EUNSUPPORTED, "too many variables");
+    PackTab pt;
+    memset(&pt, 0, sizeof(pt));
+    pt.n = (int)tab.size();
+    for (size_t i = 0; i < tab.size(); ++i) {
+        pt.src[i] = (int)tab[i].offset; pt.dst[i] = (int)tab[i].packed_offset; pt.cnt[i] = (int)tab[i].count;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int total = (int)(tab.back().offset + tab.back().count);
+    CUDA_TRY(cudaMemsetAsync(packed, 0, packed_floats(tab) * sizeof(float), st));
+    pack_kernel<<<592, 256, 0, st>>>(pt, params, packed, total);
+    CUDA_TRY(cudaGetLastError());
+    return SQAIR_OK;
+}
+
+int sqair_fill_noise(const sqair_cfg* cfg, uint64_t seed, int32_t row_offset, float* eps_where, float* eps_what,
+                     float* u_pres, void* stream) {
+    if (!cfg || !eps_where || !eps_what || !u_pres) return fail(SQAIR_EINVAL, "null argument");
+    std::string e = validate_cfg(*cfg);
+    if (!e.empty()) return fail(SQAIR_EINVAL, e);
+    const int rows = cfg->B * cfg->K;
+    noise_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(cfg->T, rows, 2 * cfg->n, cfg->n_what, (uint32_t)(seed & 0xffffffffu),
+                                                        (uint32_t)(seed >> 32), row_offset, eps_where, eps_what, u_pres);
+    CUDA_TRY(cudaGetLastError());
+    return SQAIR_OK;
+}
+
+int sqair_forward(const sqair_cfg* cfg, const float* packed_params, const float* obs, const float* eps_where,
+                  const float* eps_what, const float* u_pres, const sqair_outputs* out, void* stream) {
+    if (!cfg || !packed_params || !obs || !eps_where || !eps_what || !u_pres || !out)
+        return fail(SQAIR_EINVAL, "null argument");
+    std::string e = validate_cfg(*cfg);
+    if (!e.empty()) return fail(SQAIR_EINVAL, e);
+    auto tab = param_table(*cfg);
+    Plan plan;
+    const int R = choose_rows(*cfg, tab, plan, e);
+    if (R == 0) return fail(SQAIR_EUNSUPPORTED, e);
+    Job job{packed_params, obs, eps_where, eps_what, u_pres, *out};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (R) {
+        case 1: return launch_sequence<1>(plan, job, st);
+        case 2: return launch_sequence<2>(plan, job, st);
+        case 3: return launch_sequence<3>(plan, job, st);
+        case 4: return launch_sequence<4>(plan, job, st);
+        case 5: return launch_sequence<5>(plan, job, st);
+        case 8: return launch_sequence<8>(plan, job, st);
+    }
+    return fail(SQAIR_EUNSUPPORTED, "unsupported rows per block");
+}
+
+int sqair_objective(const float* log_w_t, const float* disc_lp_t, int32_t T, int32_t B, int32_t K, float* log_weights,
+                    float* elbo_iwae_per_example, float* importance_weights, float* scalars, void* stream) {
+    if (!log_w_t || T < 1 || B < 1 || K < 1) return fail(SQAIR_EINVAL, "bad argument");
+    objective_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(log_w_t, disc_lp_t, T, B, K, log_weights, elbo_iwae_per_example,
+                                                           importance_weights, scalars);
+    CUDA_TRY(cudaGetLastError());
+    return SQAIR_OK;
+}
+
+int sqair_stn_glimpse(const float* img, const float* where, float* glimpse, int32_t N, int32_t H, int32_t W, int32_t G,
+                      void* stream) {
+    if (!img || !where || !glimpse || N < 1 || H < 2 || W < 2 || G < 2) return fail(SQAIR_EINVAL, "bad argument");
+    const long long total = (long long)N * G * G;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    stn_glimpse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(img, where, glimpse, N, H, W, G);
+    CUDA_TRY(cudaGetLastError());
+    return SQAIR_OK;
+}
+
+int sqair_canvas_ll(const float* glimpse, const float* where, const float* presence, const float* mean_img,
+                    const float* img, float* canvas, float* data_ll, int32_t N, int32_t n, int32_t H, int32_t W,
+                    int32_t G, float output_std, float bg_std, void* stream) {
+    if (!glimpse || !where || !presence || !mean_img || !img || !canvas || !data_ll || N < 1 || n < 1)
+        return fail(SQAIR_EINVAL, "bad argument");
+    const int smem = (n * G * G + n * 5) * (int)sizeof(float);
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(canvas_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    canvas_ll_kernel<<<N, 256, smem, (cudaStream_t)stream>>>(glimpse, where, presence, mean_img, img, canvas, data_ll, n, H,
+                                                             W, G, output_std, bg_std);
+    CUDA_TRY(cudaGetLastError());
+    return SQAIR_OK;
+}
+
+}  // extern "C"

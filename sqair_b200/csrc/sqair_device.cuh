@@ -1,0 +1,1007 @@
+// sqair_device.cuh -- the SQAIR per-frame step for one block of R rows.
+//
+// Single source: compiled by nvcc as device code for the persistent sequence kernel
+// (sqair_api.cu) and, with SQAIR_HOST_EMU defined, by g++ as a one-thread-per-block emulation used
+// ONLY by tests/host_emu to debug the kernel logic against the oracle without a GPU.
+//
+// Reference walk (all under /root/reference/sqair): seq.py:181-276 (frame body) ->
+// sqair_modules.py:446-582 (SQAIRTimestep) -> sqair_modules.py:250-329 + propagate.py:68-184 +
+// core.py:280-359 (propagation) -> sqair_modules.py:368-385 (latent summary) ->
+// sqair_modules.py:94-229 + core.py:164-227 (discovery) -> modules.py:548-607, prior.py:61-102
+// (discovery priors / number-of-steps posterior) -> index.py:132-221 (slot compaction, ids) ->
+// modules.py:435-467 (decoder, canvas) -> seq.py:271-276 (log weights).
+#pragma once
+#include <math.h>
+#include "sqair_core.h"
+
+#ifdef SQAIR_HOST_EMU
+#define SQ_DEV inline
+#define SQ_DEVNI inline
+#define SQ_LDG(p) (*(p))
+#define SQ_RESTRICT
+#else
+#define SQ_DEV __device__ __forceinline__
+#define SQ_DEVNI __device__ __noinline__
+#define SQ_LDG(p) __ldg(p)
+#define SQ_RESTRICT __restrict__
+#endif
+
+namespace sq {
+
+struct Ctx {
+    int tid, nthreads, lane, nlanes, warp, nwarps;
+    float* sm;
+    SQ_DEV void sync() const {
+#ifndef SQAIR_HOST_EMU
+        __syncthreads();
+#endif
+    }
+};
+
+SQ_DEV float warp_sum(float v) {
+#ifndef SQAIR_HOST_EMU
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+    return v;
+}
+
+// ---- scalar math (fp32, accurate libm variants: parity needs fp32-faithful logits) -----------
+SQ_DEV float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+SQ_DEV float eluf_(float x) { return x > 0.f ? x : expm1f(x); }
+SQ_DEV float softplusf_(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+SQ_DEV float actf(int act, float v) {
+    switch (act) {
+        case ACT_ELU: return eluf_(v);
+        case ACT_SIGMOID: return sigmoidf_(v);
+        case ACT_TANH: return tanhf(v);
+        case ACT_SOFTPLUS: return softplusf_(v);
+        default: return v;
+    }
+}
+#define SQ_LOG_2PI 1.8378770664093453f
+// tfd.Normal.log_prob
+SQ_DEV float normal_lp(float x, float loc, float scale) {
+    float z = (x - loc) / scale;
+    return -0.5f * z * z - logf(scale) - 0.5f * SQ_LOG_2PI;
+}
+// tfd.Bernoulli(logits).log_prob(x) = -sigmoid_cross_entropy_with_logits(labels=x, logits)
+SQ_DEV float bernoulli_lp(float x, float l) {
+    return -(fmaxf(l, 0.f) - l * x + log1pf(expf(-fabsf(l))));
+}
+
+// tf.contrib.resampler bilinear sample with zero padding.  `F(ix, iy)` fetches
+// an in-range texel.
+template <class Fetch>
+SQ_DEV float bilinear_zero_pad(float x, float y, int w, int h, Fetch fetch) {
+    if (!(x > -1.f && y > -1.f && x < (float)w && y < (float)h)) return 0.f;
+    float fx = floorf(x), fy = floorf(y);
+    float cx = fx + 1.f, cy = fy + 1.f;
+    float dx = cx - x, dy = cy - y;
+    int ifx = (int)fx, ify = (int)fy, icx = ifx + 1, icy = ify + 1;
+    bool fx_ok = ifx >= 0 && ifx <= w - 1, cx_ok = icx >= 0 && icx <= w - 1;
+    bool fy_ok = ify >= 0 && ify <= h - 1, cy_ok = icy >= 0 && icy <= h - 1;
+    float v00 = (fx_ok && fy_ok) ? fetch(ifx, ify) : 0.f;
+    float v11 = (cx_ok && cy_ok) ? fetch(icx, icy) : 0.f;
+    float v01 = (fx_ok && cy_ok) ? fetch(ifx, icy) : 0.f;
+    float v10 = (cx_ok && fy_ok) ? fetch(icx, ify) : 0.f;
+    return dx * dy * v00 + (1.f - dx) * (1.f - dy) * v11 + dx * (1.f - dy) * v01 + (1.f - dx) * dy * v10;
+}
+// i-th point of linspace(-1, 1, n) (symmetric evaluation, as torch/numpy do)
+SQ_DEV float lin11(int i, int n) {
+    float step = 2.f / (float)(n - 1);
+    return (i < n / 2) ? (-1.f + step * (float)i) : (1.f - step * (float)(n - 1 - i));
+}
+
+// Everything a block needs for one call.
+struct Job {
+    const float* prm;        // packed parameters
+    const float* obs;        // [T][B][P]
+    const float* eps_where;  // [T][rows][2n][4]
+    const float* eps_what;   // [T][rows][2n][nw]
+    const float* u_pres;     // [T][rows][2n]
+    sqair_outputs out;
+};
+
+SQ_DEV void dense_map(const Layer& L, int nthreads, int& G, int& Gp, int& ks) {
+    G = 0;
+    for (int b = 0; b < L.nblk; ++b) G += (L.blk[b].N + 3) >> 2;
+    Gp = (G + 7) & ~7;
+    ks = nthreads / Gp;
+    if (ks > MAX_KS) ks = MAX_KS;
+    if (ks < 1) ks = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense layer (snt.Linear / Nonlinear, neural.py:34-47; VanillaRNN / GRU gate pre-activations):
+//   out[col][r] = act( sum_seg sum_k W_seg[k][col] * x_seg[k][r] + b[col] (+ b2[col]) ) * scale + add
+// Thread tile: 4 adjacent columns x R rows; the K range of every segment is split into `ks`
+// slices whose partial sums are combined through shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int R>
+SQ_DEV void dense_accum(const Ctx& c, const Plan& P, const float* SQ_RESTRICT prm, const Layer& L, int slot,
+                        int b, int col, int sl, int ks, const float* const* imgrow, float (&acc)[4][R]) {
+    const Blk& B = L.blk[b];
+    const int ldw = B.ldw;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[j][r] = 0.f;
+    for (int si = 0; si < L.nseg; ++si) {
+        const Seg& S = L.seg[si];
+        const int kc = (S.K + ks - 1) / ks;
+        const int k0 = sl * kc;
+        int k1 = k0 + kc;
+        if (k1 > S.K) k1 = S.K;
+        if (k0 >= k1) continue;
+        const int wbase = S.w_off[b] + col;
+        const float* SQ_RESTRICT w = prm + wbase + (size_t)k0 * ldw;
+        const bool vec = ((ldw & 3) == 0) && ((wbase & 3) == 0);
+        if (S.kind == SEG_SMEM) {
+            const float* x = c.sm + S.x_off + slot * S.x_sstride + k0 * S.ld;
+            const int ld = S.ld;
+            if (vec) {
+                int k = k0;
+                for (; k + 4 <= k1; k += 4) {
+                    float4 w0 = SQ_LDG(reinterpret_cast<const float4*>(w));
+                    float4 w1 = SQ_LDG(reinterpret_cast<const float4*>(w + ldw));
+                    float4 w2 = SQ_LDG(reinterpret_cast<const float4*>(w + 2 * ldw));
+                    float4 w3 = SQ_LDG(reinterpret_cast<const float4*>(w + 3 * ldw));
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        float x0 = x[r], x1 = x[ld + r], x2 = x[2 * ld + r], x3 = x[3 * ld + r];
+                        acc[0][r] += w0.x * x0; acc[1][r] += w0.y * x0; acc[2][r] += w0.z * x0; acc[3][r] += w0.w * x0;
+                        acc[0][r] += w1.x * x1; acc[1][r] += w1.y * x1; acc[2][r] += w1.z * x1; acc[3][r] += w1.w * x1;
+                        acc[0][r] += w2.x * x2; acc[1][r] += w2.y * x2; acc[2][r] += w2.z * x2; acc[3][r] += w2.w * x2;
+                        acc[0][r] += w3.x * x3; acc[1][r] += w3.y * x3; acc[2][r] += w3.z * x3; acc[3][r] += w3.w * x3;
+                    }
+                    w += 4 * ldw;
+                    x += 4 * ld;
+                }
+                for (; k < k1; ++k) {
+                    float4 w0 = SQ_LDG(reinterpret_cast<const float4*>(w));
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        float x0 = x[r];
+                        acc[0][r] += w0.x * x0; acc[1][r] += w0.y * x0; acc[2][r] += w0.z * x0; acc[3][r] += w0.w * x0;
+                    }
+                    w += ldw;
+                    x += ld;
+                }
+            } else {
+                const int nv = (B.N - col) < 4 ? (B.N - col) : 4;
+                for (int k = k0; k < k1; ++k) {
+                    float wv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) wv[j] = (j < nv) ? SQ_LDG(w + j) : 0.f;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        float x0 = x[r];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[j][r] += wv[j] * x0;
+                    }
+                    w += ldw;
+                    x += ld;
+                }
+            }
+        } else {   // SEG_IMAGE: x[k][r] = frame pixel k of the image of row r (global, read-only)
+            int k = k0;
+            if (vec) {
+                for (; k + 2 <= k1; k += 2) {
+                    float4 w0 = SQ_LDG(reinterpret_cast<const float4*>(w));
+                    float4 w1 = SQ_LDG(reinterpret_cast<const float4*>(w + ldw));
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        float x0 = SQ_LDG(imgrow[r] + k), x1 = SQ_LDG(imgrow[r] + k + 1);
+                        acc[0][r] += w0.x * x0; acc[1][r] += w0.y * x0; acc[2][r] += w0.z * x0; acc[3][r] += w0.w * x0;
+                        acc[0][r] += w1.x * x1; acc[1][r] += w1.y * x1; acc[2][r] += w1.z * x1; acc[3][r] += w1.w * x1;
+                    }
+                    w += 2 * ldw;
+                }
+            }
+            const int nv = (B.N - col) < 4 ? (B.N - col) : 4;
+            for (; k < k1; ++k) {
+                float wv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) wv[j] = (j < nv) ? SQ_LDG(w + j) : 0.f;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float x0 = SQ_LDG(imgrow[r] + k);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j][r] += wv[j] * x0;
+                }
+                w += ldw;
+            }
+        }
+    }
+}
+
+template <int R>
+SQ_DEV void dense_epilogue(const Ctx& c, const float* SQ_RESTRICT prm, const Layer& L, int slot, int b, int col,
+                           float (&acc)[4][R]) {
+    const Blk& B = L.blk[b];
+    const float pscale = B.scale_p_off >= 0 ? SQ_LDG(prm + B.scale_p_off) : 1.f;
+    float* out = c.sm + B.out_off + slot * B.out_sstride;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int cc = col + j;
+        if (cc < B.N) {
+            float bias = B.b_off >= 0 ? SQ_LDG(prm + B.b_off + cc) : 0.f;
+            if (B.b2_off >= 0) bias += SQ_LDG(prm + B.b2_off + cc);
+            const bool hi = cc >= B.split;
+            const int act = hi ? B.act_hi : B.act;
+            const float sc = hi ? B.scale_hi : B.scale, ad = hi ? B.add_hi : B.add;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float v = actf(act, acc[j][r] + bias) * sc + ad;
+                out[cc * B.out_ld + r] = v * pscale;
+            }
+        }
+    }
+}
+
+template <int R>
+SQ_DEVNI void dense(const Ctx& c, const Plan& P, const float* SQ_RESTRICT prm, int layer_id, int slot,
+                    const float* const* imgrow) {
+    const Layer& L = P.L[layer_id];
+    int G, Gp, ks;
+    dense_map(L, c.nthreads, G, Gp, ks);
+    float acc[4][R];
+    if (ks == 1) {
+        for (int g = c.tid; g < G; g += c.nthreads) {
+            int b = 0, cg = g;
+            while (cg >= ((L.blk[b].N + 3) >> 2)) { cg -= (L.blk[b].N + 3) >> 2; ++b; }
+            dense_accum<R>(c, P, prm, L, slot, b, cg * 4, 0, 1, imgrow, acc);
+            dense_epilogue<R>(c, prm, L, slot, b, cg * 4, acc);
+        }
+    } else {
+        const int g = c.tid % Gp, sl = c.tid / Gp;
+        const bool active = g < G && sl < ks;
+        int b = 0, cg = g;
+        if (active) {
+            while (cg >= ((L.blk[b].N + 3) >> 2)) { cg -= (L.blk[b].N + 3) >> 2; ++b; }
+            dense_accum<R>(c, P, prm, L, slot, b, cg * 4, sl, ks, imgrow, acc);
+            if (sl > 0) {
+                float* red = c.sm + P.sm.Red + ((sl - 1) * Gp + g) * 4 * R;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) red[j * R + r] = acc[j][r];
+            }
+        }
+        c.sync();
+        if (active && sl == 0) {
+            for (int s2 = 1; s2 < ks; ++s2) {
+                const float* red = c.sm + P.sm.Red + ((s2 - 1) * Gp + g) * 4 * R;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc[j][r] += red[j * R + r];
+            }
+            dense_epilogue<R>(c, prm, L, slot, b, cg * 4, acc);
+        }
+    }
+    c.sync();
+}
+
+// ---------------------------------------------------------------------------------------------
+// The per-block state machine
+// ---------------------------------------------------------------------------------------------
+template <int R>
+struct Block {
+    const Ctx& c;
+    const Plan& P;
+    const Job& J;
+    int row0;                       // first global row of this block
+    const float* imgrow[R];         // frame of each row for the current t
+    int grow[R];                    // global row (clamped) of each local row
+    bool valid[R];
+
+    SQ_DEV Block(const Ctx& c_, const Plan& P_, const Job& J_, int row0_) : c(c_), P(P_), J(J_), row0(row0_) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int gr = row0 + r;
+            valid[r] = gr < P.rows;
+            grow[r] = valid[r] ? gr : P.rows - 1;
+            imgrow[r] = nullptr;
+        }
+    }
+    // accessors ------------------------------------------------------------------------------
+    SQ_DEV float* sm() const { return c.sm; }
+    SQ_DEV int LDS() const { return P.NS * R; }
+    SQ_DEV int LDE() const { return (P.NS + 1) * R; }
+    SQ_DEV float& Z(int f, int s, int r) const { return c.sm[P.sm.Z + f * LDS() + s * R + r]; }
+    SQ_DEV float& rec(int base, int e, int f, int r) const { return c.sm[base + f * LDE() + e * R + r]; }
+    SQ_DEV float& pri(int f, int s, int r) const { return c.sm[P.sm.Pri + f * LDS() + s * R + r]; }
+    SQ_DEV float& lp(int k, int s, int r) const { return c.sm[P.sm.Lp + k * LDS() + s * R + r]; }
+    SQ_DEV float& rowacc(int k, int r) const { return c.sm[P.sm.RowAcc + k * R + r]; }
+    SQ_DEV float prm(int off) const { return SQ_LDG(J.prm + off); }
+    SQ_DEV void lin(int id, int slot = 0) const { dense<R>(c, P, J.prm, id, slot, imgrow); }
+    SQ_DEV size_t nidx(int t, int r, int slot2) const {      // noise index of (t, row, slot in [0,2n))
+        return ((size_t)t * P.rows + grow[r]) * (2 * P.NS) + slot2;
+    }
+    enum { RA_QPRES = 0, RA_PPRES = 1, RA_NPROP = 2, RA_NDISC = 3, RA_QNUM = 4, RA_PNUM = 5, RA_LL = 6 };
+    enum { LP_PQWHAT = 0, LP_PQWHERE = 1, LP_PPWHAT = 2, LP_PPWHERE = 3, LP_PROB = 4,
+           LP_DQWHAT = 5, LP_DQWHERE = 6, LP_DPWHAT = 7, LP_DPWHERE = 8 };
+
+    // ------------------------------------------------------------------------------------------
+    // sequence start: seq.py:86-104 (initial z = 0, ids = -1, trainable initial GRU states)
+    // ------------------------------------------------------------------------------------------
+    SQ_DEV void init_sequence() const {
+        const Smem& m = P.sm;
+        const int nh = P.nh, nw = P.nw, NS = P.NS;
+        for (int i = c.tid; i < (nw + 6) * LDS(); i += c.nthreads) c.sm[m.Z + i] = 0.f;
+        for (int i = c.tid; i < LDS(); i += c.nthreads) c.sm[m.Ids + i] = -1.f;
+        for (int i = c.tid; i < R; i += c.nthreads) c.sm[m.LastId + i] = -1.f;
+        for (int i = c.tid; i < nh * LDS(); i += c.nthreads) {
+            int f = i / LDS();
+            c.sm[m.Tst + i] = prm(P.po.temporal_h0 + f);
+            c.sm[m.Pst + i] = prm(P.po.prior_h0 + f);
+        }
+        // entry 0 of the slot records = RNN-core initial state (core.py:132-139,153,238)
+        for (int i = c.tid; i < (nw + 5) * R; i += c.nthreads) {
+            int f = i / R, r = i % R;
+            rec(m.PropOut, 0, f, r) = 0.f;
+            rec(m.DiscOut, 0, f, r) = (f == P.rec.pres) ? 1.f : 0.f;
+        }
+        if (P.cfg.rec_where_prior)
+            for (int i = c.tid; i < 4 * R; i += c.nthreads) c.sm[m.RnInit + i] = prm(P.po.rn_init_state + i / R);
+        (void)NS;
+        c.sync();
+    }
+
+    // forward spatial transformer (modules.py:165-172,204-218) at Coords -> Glm (* Mask)
+    SQ_DEV void extract_glimpse(bool use_mask) const {
+        const Smem& m = P.sm;
+        const int G = P.cfg.G, W = P.cfg.W, H = P.cfg.H;
+        const float hw = 0.5f * (float)(W - 1), hh = 0.5f * (float)(H - 1);
+        for (int i = c.tid; i < P.g * R; i += c.nthreads) {
+            const int r = i % R, j = i / R;
+            const int gy = j / G, gx = j % G;
+            const float sx = c.sm[m.Coords + 0 * R + r], sy = c.sm[m.Coords + 1 * R + r];
+            const float tx = c.sm[m.Coords + 2 * R + r], ty = c.sm[m.Coords + 3 * R + r];
+            const float x = hw * (sx * lin11(gx, G) + tx) + hw;
+            const float y = hh * (sy * lin11(gy, G) + ty) + hh;
+            const float* img = imgrow[0];
+#pragma unroll
+            for (int q = 1; q < R; ++q) if (r == q) img = imgrow[q];
+            float v = bilinear_zero_pad(x, y, W, H, [&](int ix, int iy) { return SQ_LDG(img + iy * W + ix); });
+            if (use_mask) v *= c.sm[m.Mask + i];
+            c.sm[m.Glm + i] = v;
+        }
+        c.sync();
+    }
+    // to_coords (modules.py:220-227) + clip_preserve(scale, 1e-4) (modules.py:206)
+    SQ_DEV void set_coords(float w0, float w1, float w2, float w3, int r) const {
+        const Smem& m = P.sm;
+        c.sm[m.Coords + 0 * R + r] = fmaxf(sigmoidf_(w0), 1e-4f);
+        c.sm[m.Coords + 1 * R + r] = fmaxf(sigmoidf_(w1), 1e-4f);
+        c.sm[m.Coords + 2 * R + r] = tanhf(w2);
+        c.sm[m.Coords + 3 * R + r] = tanhf(w3);
+    }
+    SQ_DEV void encode_glimpse(int last_layer) const {
+        lin(L_ENC1); lin(L_ENC2); lin(last_layer);
+    }
+    // snt.GRU gate algebra (Appendix B) around the two dense calls: Gr <- r*h, then state update.
+    SQ_DEV void gru_mul_r(int state_off, int s) const {
+        const Smem& m = P.sm;
+        for (int i = c.tid; i < P.nh * R; i += c.nthreads) {
+            int f = i / R, r = i % R;
+            c.sm[m.Gr + i] *= c.sm[state_off + f * LDS() + s * R + r];
+        }
+        c.sync();
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // propagation prior for slot s (propagate.py:68-98,123-158); updates Pst in place
+    // ------------------------------------------------------------------------------------------
+    SQ_DEV void prop_prior(int s) const {
+        const Smem& m = P.sm;
+        const int nh = P.nh, nw = P.nw;
+        lin(L_PGRU_ZR, s);
+        gru_mul_r(m.Pst, s);
+        lin(L_PGRU_C, s);
+        for (int i = c.tid; i < nh * R; i += c.nthreads) {
+            int f = i / R, r = i % R;
+            float& h = c.sm[m.Pst + f * LDS() + s * R + r];
+            float z = c.sm[m.Gz + i];
+            h = (1.f - z) * h + z * c.sm[m.Gc + i];
+        }
+        c.sync();
+        lin(L_PLIN, s);
+        // stats post-processing: rows 0 logit | 1..4 where_loc | 5..4+nw what_loc | where_scale(4) | what_scale(nw)
+        const int nstat = 2 * (4 + nw) + 1;
+        for (int i = c.tid; i < nstat * R; i += c.nthreads) {
+            int f = i / R, r = i % R;
+            float v = pri(f, s, r);
+            const float ptm1 = Z(nw + 4, s, r);
+            if (f == 0) {
+                v += P.cfg.prop_prior_step_bias;
+                v = ptm1 * v + (ptm1 - 1.f) * 88.f;
+                if (P.cfg.prior_type != SQAIR_PRIOR_RNN) v = Z(nw + 5, s, r) + 0.1f * v;
+            } else if (f <= 4 + nw) {
+                // locs: where_loc (4) then what_loc (nw); Z rows: what 0..nw-1, where nw..nw+3
+                const int zf = (f <= 4) ? (nw + f - 1) : (f - 5);
+                if (P.cfg.prior_type == SQAIR_PRIOR_RW) v = Z(zf, s, r);
+                else if (P.cfg.prior_type == SQAIR_PRIOR_GUIDED) v = Z(zf, s, r) + 0.1f * v;
+            } else {
+                v = softplusf_(v) + 1e-2f;
+            }
+            pri(f, s, r) = v;
+        }
+        c.sync();
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // one propagation slot (core.py:280-359) + its log-prob terms (sqair_modules.py:281-326)
+    // ------------------------------------------------------------------------------------------
+    SQ_DEV void prop_slot(int t, int s) const {
+        const Smem& m = P.sm;
+        const RecF& F = P.rec;
+        const int nh = P.nh, nw = P.nw, e = s + 1;
+        const bool masked = P.cfg.masked_glimpse != 0;
+        prop_prior(s);
+        // where_bias MLP and glimpse mask MLP on the slot's temporal state (core.py:291; modules.py:350-356)
+        lin(L_WBMK1, s);
+        lin(L_WB2);
+        if (masked) lin(L_MK2);
+        for (int r = c.tid; r < R; r += c.nthreads)
+            set_coords(Z(nw + 0, s, r) + c.sm[m.Wb + 0 * R + r], Z(nw + 1, s, r) + c.sm[m.Wb + 1 * R + r],
+                       Z(nw + 2, s, r) + c.sm[m.Wb + 2 * R + r], Z(nw + 3, s, r) + c.sm[m.Wb + 3 * R + r], r);
+        c.sync();
+        extract_glimpse(masked);
+        encode_glimpse(L_ENC3_LOC);                               // -> Loc1 (core.py:292-293)
+        lin(L_PRNN, s);                                           // core.py:295-302 -> Hrnn[1]
+        lin(L_PT1, s); lin(L_PT2); lin(L_PT3);                    // core.py:323-324 -> Tp
+        // where ~ MVN_TriL(where_tm1 + us*loc, L) (core.py:326-330; modules.py:535-545)
+        for (int r = c.tid; r < R; r += c.nthreads) {
+            float loc[4], sc[4], eps[4], L[4][4], wh[4];
+            const float so = prm(P.po.p_scale_offset);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                loc[i] = Z(nw + i, s, r) + P.cfg.where_update_scale * c.sm[m.Tp + i * R + r];
+                sc[i] = softplusf_(c.sm[m.Tp + (4 + i) * R + r] + so - 1.f) + 1e-2f;
+                eps[i] = J.eps_where[nidx(t, r, s) * 4 + i];
+            }
+            tril_from_scale(sc, L);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float a = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (j <= i) a += L[i][j] * eps[j];
+                wh[i] = loc[i] + a;
+                rec(m.PropOut, e, F.where + i, r) = wh[i];
+                rec(m.PropOut, e, F.where_loc + i, r) = loc[i];
+                rec(m.PropOut, e, F.where_scale + i, r) = sc[i];
+            }
+            set_coords(wh[0], wh[1], wh[2], wh[3], r);
+        }
+        c.sync();
+        extract_glimpse(masked);
+        encode_glimpse(L_ENC3);                                   // -> Enc = (loc2, scale2) (core.py:336-337)
+        // temporal GRU (core.py:339-340); new state left in Gc, Tst updated at the end of the slot
+        lin(L_TGRU_ZR, s);
+        gru_mul_r(m.Tst, s);
+        lin(L_TGRU_C, s);
+        for (int i = c.tid; i < nh * R; i += c.nthreads) {
+            int f = i / R, r = i % R;
+            float h = c.sm[m.Tst + f * LDS() + s * R + r], z = c.sm[m.Gz + i];
+            c.sm[m.Gc + i] = (1.f - z) * h + z * c.sm[m.Gc + i];
+        }
+        c.sync();
+        lin(L_PHEADS);                                            // core.py:343-349 -> Tg, Gt
+        for (int i = c.tid; i < nw * R; i += c.nthreads) {        // core.py:351-357
+            int j = i / R, r = i % R;
+            float fg = c.sm[m.Gt + i], ig = c.sm[m.Gt + nw * R + i], tg = c.sm[m.Gt + 2 * nw * R + i];
+            float loc2 = c.sm[m.Enc + i], sc2 = c.sm[m.Enc + nw * R + i];
+            float loct = c.sm[m.Tg + i], sct = c.sm[m.Tg + nw * R + i];
+            float wl = fg * Z(j, s, r) + (1.f - ig) * loc2 + (1.f - tg) * loct;
+            float ws = (1.f - ig) * sc2 + (1.f - tg) * sct;
+            float what = wl + ws * J.eps_what[nidx(t, r, s) * nw + j];
+            rec(m.PropOut, e, F.what + j, r) = what;
+            rec(m.PropOut, e, F.what_loc + j, r) = wl;
+            rec(m.PropOut, e, F.what_scale + j, r) = ws;
+        }
+        c.sync();
+        lin(L_PST1, s); lin(L_PST2);                              // modules.py:506-513
+        for (int r = c.tid; r < R; r += c.nthreads) {             // core.py:141-144
+            const float ptm1 = Z(nw + 4, s, r);
+            float logit = ptm1 * c.sm[m.Lg + r] + (ptm1 - 1.f) * 88.f;
+            float prob = sigmoidf_(logit);
+            float pres = (J.u_pres[nidx(t, r, s)] < prob ? 1.f : 0.f) * ptm1;
+            rec(m.PropOut, e, F.logit, r) = logit;
+            rec(m.PropOut, e, F.prob, r) = prob;
+            rec(m.PropOut, e, F.pres, r) = pres;
+        }
+        c.sync();
+        // log-probs under q and p (sqair_modules.py:290-317): one warp per row, lanes over dims
+        for (int r = c.warp; r < R; r += c.nwarps) {
+            float qw = 0.f, pw = 0.f;
+            for (int j = c.lane; j < nw; j += c.nlanes) {
+                float x = rec(m.PropOut, e, F.what + j, r);
+                qw += normal_lp(x, rec(m.PropOut, e, F.what_loc + j, r), rec(m.PropOut, e, F.what_scale + j, r));
+                pw += normal_lp(x, pri(5 + j, s, r), pri(9 + nw + j, s, r));
+            }
+            qw = warp_sum(qw);
+            pw = warp_sum(pw);
+            if (c.lane == 0) {
+                float x[4], loc[4], sc[4], L[4][4], y[4];
+                float pwh = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    x[i] = rec(m.PropOut, e, F.where + i, r);
+                    loc[i] = rec(m.PropOut, e, F.where_loc + i, r);
+                    sc[i] = rec(m.PropOut, e, F.where_scale + i, r);
+                    pwh += normal_lp(x[i], pri(1 + i, s, r), pri(5 + nw + i, s, r));
+                }
+                tril_from_scale(sc, L);
+                float qwh = -2.f * SQ_LOG_2PI, ss = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {               // forward substitution L y = x - loc
+                    float a = x[i] - loc[i];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (j < i) a -= L[i][j] * y[j];
+                    y[i] = a / L[i][i];
+                    ss += y[i] * y[i];
+                    qwh -= logf(fabsf(L[i][i]));
+                }
+                qwh += -0.5f * ss;
+                const float ptm1 = Z(nw + 4, s, r), pres = rec(m.PropOut, e, F.pres, r);
+                const float qp = bernoulli_lp(pres, rec(m.PropOut, e, F.logit, r));
+                const float pp = bernoulli_lp(pres, pri(0, s, r));
+                const float mk = ptm1 * pres;
+                lp(LP_PQWHAT, s, r) = qw * mk;
+                lp(LP_PQWHERE, s, r) = qwh * mk;
+                lp(LP_PPWHAT, s, r) = pw * mk;
+                lp(LP_PPWHERE, s, r) = pwh * mk;
+                lp(LP_PROB, s, r) = expf(qp) * ptm1;
+                rowacc(RA_QPRES, r) += qp * ptm1;
+                rowacc(RA_PPRES, r) += pp * ptm1;
+                rowacc(RA_NPROP, r) += pres;
+            }
+        }
+        // commit the slot: temporal state, RNN hidden
+        for (int i = c.tid; i < nh * R; i += c.nthreads) {
+            int f = i / R, r = i % R;
+            c.sm[m.Tst + f * LDS() + s * R + r] = c.sm[m.Gc + i];
+            c.sm[m.Hrnn + i] = c.sm[m.Hrnn + nh * R + i];
+        }
+        c.sync();
+    }
+
+    // L = fill_triangular(cholesky_scale) * scale[:, None] + diag(scale) (modules.py:535-545).
+    // TF fill_triangular order for a 10-vector x: row0 [x4], row1 [x8 x9], row2 [x7 x6 x5], row3 [x3 x2 x1 x0].
+    SQ_DEV void tril_from_scale(const float (&sc)[4], float (&L)[4][4]) const {
+        const int co = P.po.cholesky;
+        const int idx[4][4] = {{4, -1, -1, -1}, {8, 9, -1, -1}, {7, 6, 5, -1}, {3, 2, 1, 0}};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v = 0.f;
+                if (j <= i) v = prm(co + idx[i][j]) * sc[i];
+                if (i == j) v += sc[i];
+                L[i][j] = v;
+            }
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // one discovery slot (core.py:192-227) + posterior / N(0,1) prior terms (sqair_modules.py:177-186)
+    // ------------------------------------------------------------------------------------------
+    SQ_DEV void disc_slot(int t, int s) const {
+        const Smem& m = P.sm;
+        const RecF& F = P.rec;
+        const int nh = P.nh, nw = P.nw, e = s + 1, ns2 = P.NS + s;
+        lin(L_DRNN, s);
+        lin(L_DT1); lin(L_DT2); lin(L_DT3);
+        for (int r = c.tid; r < R; r += c.nthreads) {             // core.py:220-227
+            const float so = prm(P.po.d_scale_offset);
+            float wh[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float loc = c.sm[m.Tp + i * R + r];
+                float sc = softplusf_(c.sm[m.Tp + (4 + i) * R + r] + so) + 1e-2f;
+                wh[i] = loc + sc * J.eps_where[nidx(t, r, ns2) * 4 + i];
+                rec(m.DiscOut, e, F.where + i, r) = wh[i];
+                rec(m.DiscOut, e, F.where_loc + i, r) = loc;
+                rec(m.DiscOut, e, F.where_scale + i, r) = sc;
+            }
+            set_coords(wh[0], wh[1], wh[2], wh[3], r);
+        }
+        c.sync();
+        extract_glimpse(false);                                   // discovery passes no mask (core.py:217)
+        encode_glimpse(L_ENC3);
+        for (int i = c.tid; i < nw * R; i += c.nthreads) {        // core.py:216-218
+            int j = i / R, r = i % R;
+            float wl = c.sm[m.Enc + i], ws = c.sm[m.Enc + nw * R + i];
+            rec(m.DiscOut, e, F.what + j, r) = wl + ws * J.eps_what[nidx(t, r, ns2) * nw + j];
+            rec(m.DiscOut, e, F.what_loc + j, r) = wl;
+            rec(m.DiscOut, e, F.what_scale + j, r) = ws;
+        }
+        c.sync();
+        lin(L_DST1, s); lin(L_DST2);
+        for (int r = c.tid; r < R; r += c.nthreads) {
+            const float pkm1 = rec(m.DiscOut, s, F.pres, r);      // entry 0 holds the initial 1 (core.py:153)
+            float logit = pkm1 * c.sm[m.Lg + r] + (pkm1 - 1.f) * 88.f;
+            float prob = sigmoidf_(logit);
+            float pres = (J.u_pres[nidx(t, r, ns2)] < prob ? 1.f : 0.f) * pkm1;
+            rec(m.DiscOut, e, F.logit, r) = logit;
+            rec(m.DiscOut, e, F.prob, r) = prob;
+            rec(m.DiscOut, e, F.pres, r) = pres;
+        }
+        c.sync();
+        for (int r = c.warp; r < R; r += c.nwarps) {
+            float qw = 0.f, pw = 0.f;
+            for (int j = c.lane; j < nw; j += c.nlanes) {
+                float x = rec(m.DiscOut, e, F.what + j, r);
+                qw += normal_lp(x, rec(m.DiscOut, e, F.what_loc + j, r), rec(m.DiscOut, e, F.what_scale + j, r));
+                pw += normal_lp(x, 0.f, 1.f);
+            }
+            qw = warp_sum(qw);
+            pw = warp_sum(pw);
+            if (c.lane == 0) {
+                float qwh = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    qwh += normal_lp(rec(m.DiscOut, e, F.where + i, r), rec(m.DiscOut, e, F.where_loc + i, r),
+                                     rec(m.DiscOut, e, F.where_scale + i, r));
+                const float pres = rec(m.DiscOut, e, F.pres, r);
+                lp(LP_DQWHAT, s, r) = qw * pres;
+                lp(LP_DQWHERE, s, r) = qwh * pres;
+                lp(LP_DPWHAT, s, r) = pw * pres;
+                rowacc(RA_NDISC, r) += pres;
+            }
+        }
+        for (int i = c.tid; i < nh * R; i += c.nthreads) c.sm[m.Hrnn + i] = c.sm[m.Hrnn + nh * R + i];
+        c.sync();
+    }
+
+    // discovery priors and the number-of-steps posterior (sqair_modules.py:149-226; modules.py:548-607;
+    // prior.py:61-102)
+    SQ_DEV void disc_priors(int t) const {
+        const Smem& m = P.sm;
+        const RecF& F = P.rec;
+        const int NS = P.NS;
+        if (P.cfg.rec_where_prior) {
+            // previous-sample inputs of the autoregressive prior: init_sample, then where_{s-1}
+            for (int i = c.tid; i < 4 * LDS(); i += c.nthreads) {
+                int f = i / LDS(), s = (i / R) % NS, r = i % R;
+                c.sm[m.RnPrev0 + i] = (s == 0) ? prm(P.po.rn_init_sample + f) : rec(m.DiscOut, s, F.where + f, r);
+            }
+            c.sync();
+            lin(L_RN1);
+            for (int s = 0; s < NS; ++s) {
+                lin(L_RN2, s); lin(L_RN3);
+                for (int r = c.tid; r < R; r += c.nthreads) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        a += normal_lp(rec(m.DiscOut, s + 1, F.where + i, r), c.sm[m.Rns + i * R + r],
+                                       c.sm[m.Rns + (4 + i) * R + r]);
+                    lp(LP_DPWHERE, s, r) = a * rec(m.DiscOut, s + 1, F.pres, r);
+                }
+                c.sync();
+            }
+        } else {
+            for (int i = c.tid; i < LDS(); i += c.nthreads) {
+                int s = i / R, r = i % R;
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    a += normal_lp(rec(m.DiscOut, s + 1, F.where + k, r), P.cfg.where_mean[k], P.cfg.where_std[k]);
+                lp(LP_DPWHERE, s, r) = a * rec(m.DiscOut, s + 1, F.pres, r);
+            }
+            c.sync();
+        }
+        if (P.cfg.disc_prior_type == SQAIR_DISC_PRIOR_CAT) { lin(L_SP1); lin(L_SP2); }
+        for (int r = c.tid; r < R; r += c.nthreads) {
+            const int num = (int)rowacc(RA_NDISC, r);
+            // p(N): Categorical(elu(bias + (t>0) tbias + MLP(E[n_prop]))) (sqair_modules.py:208-221)
+            float pnum;
+            if (P.cfg.disc_prior_type == SQAIR_DISC_PRIOR_CAT) {
+                float lg[MAX_SLOTS + 1], mx = -INFINITY;
+                for (int k = 0; k <= NS; ++k) {
+                    float v = prm(P.po.step_prior_bias + k) + (t == 0 ? 0.f : 1.f) * prm(P.po.step_prior_tbias + k);
+                    v = eluf_(v + c.sm[m.Spl + k * R + r]);
+                    lg[k] = v;
+                    mx = fmaxf(mx, v);
+                }
+                float se = 0.f, sel = 0.f;
+                for (int k = 0; k <= NS; ++k) { se += expf(lg[k] - mx); if (k == num) sel = lg[k]; }
+                pnum = sel - mx - logf(se);
+            } else {                                              // tfd.Geometric(probs = 1 - success)
+                const float pr = 1.f - P.cfg.step_success_prob;
+                pnum = (float)num * log1pf(-pr) + logf(pr);
+            }
+            // q(N): modified geometric from the Bernoulli chain, float64 (prior.py:61-67,95-102)
+            double pp[MAX_SLOTS], mod[MAX_SLOTS + 1], cum = 1.0, tot = 0.0;
+            for (int k = 0; k < NS; ++k) pp[k] = (double)rec(m.DiscOut, k + 1, F.prob, r);
+            for (int k = 0; k < NS; ++k) {
+                mod[k] = (1.0 - pp[k]) * cum;
+                cum *= pp[k];
+                tot += mod[k];
+            }
+            mod[NS] = cum;
+            tot += cum;
+            float qsel = 0.f;
+            for (int k = 0; k <= NS; ++k) {
+                float v = (float)(mod[k] / tot);
+                c.sm[m.Spl + k * R + r] = v;                      // Spl now holds disc_prob
+                if (k == num) qsel = v;
+            }
+            rowacc(RA_QNUM, r) = logf(fminf(fmaxf(qsel, 1e-16f), 1.f));
+            rowacc(RA_PNUM, r) = pnum;
+        }
+        c.sync();
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // slot compaction + object ids (sqair_modules.py:514-582; index.py:132-221)
+    // ------------------------------------------------------------------------------------------
+    SQ_DEV void choose_latents(int t) const {
+        const Smem& m = P.sm;
+        const RecF& F = P.rec;
+        const int NS = P.NS, nw = P.nw, nh = P.nh;
+        const sqair_outputs& o = J.out;
+        for (int r = c.tid; r < R; r += c.nthreads) {
+            // stable partition of the 2n candidates, present first
+            int order[2 * MAX_SLOTS], cnt = 0;
+            for (int k = 0; k < 2 * NS; ++k) {
+                float p = k < NS ? rec(m.PropOut, k + 1, F.pres, r) : rec(m.DiscOut, k - NS + 1, F.pres, r);
+                if (p != 0.f) order[cnt++] = k;
+            }
+            for (int k = 0; k < 2 * NS; ++k) {
+                float p = k < NS ? rec(m.PropOut, k + 1, F.pres, r) : rec(m.DiscOut, k - NS + 1, F.pres, r);
+                if (p == 0.f) order[cnt++] = k;
+            }
+            // ids (index.py:198-221)
+            float ids[2 * MAX_SLOTS];
+            float last = c.sm[m.LastId + r], inc = 0.f;
+            for (int k = 0; k < NS; ++k) {
+                float pp = rec(m.PropOut, k + 1, F.pres, r);
+                ids[k] = c.sm[m.Ids + k * R + r] * pp - (1.f - pp);
+            }
+            for (int k = 0; k < NS; ++k) {
+                float dp = rec(m.DiscOut, k + 1, F.pres, r);
+                inc += dp;
+                ids[NS + k] = (inc + last) * dp - (1.f - dp);
+            }
+            c.sm[m.LastId + r] = last + inc;
+            float nsteps = 0.f;
+            for (int j = 0; j < NS; ++j) {
+                c.sm[m.Perm + j * R + r] = (float)order[j];
+                c.sm[m.Ids + j * R + r] = ids[order[j]];
+                int k = order[j];
+                nsteps += k < NS ? rec(m.PropOut, k + 1, F.pres, r) : rec(m.DiscOut, k - NS + 1, F.pres, r);
+            }
+            rowacc(7, r) = nsteps;
+        }
+        c.sync();
+        // new z_t and the 9 compacted heads
+        const size_t trow = (size_t)t * P.rows;
+        for (int i = c.tid; i < F.size * LDS(); i += c.nthreads) {
+            const int r = i % R, j = (i / R) % NS, f = i / LDS();
+            const int k = (int)c.sm[m.Perm + j * R + r];
+            const float v = k < NS ? rec(m.PropOut, k + 1, f, r) : rec(m.DiscOut, k - NS + 1, f, r);
+            float* dst = nullptr;
+            int ff = 0, width = 1;
+            if (f < F.where) { Z(f, j, r) = v; dst = o.what; ff = f; width = nw; }
+            else if (f < F.pres) { Z(f, j, r) = v; dst = o.where; ff = f - F.where; width = 4; }
+            else if (f == F.pres) { Z(nw + 4, j, r) = v; dst = o.presence; }
+            else if (f < F.what_scale) { dst = o.what_loc; ff = f - F.what_loc; width = nw; }
+            else if (f < F.where_loc) { dst = o.what_scale; ff = f - F.what_scale; width = nw; }
+            else if (f < F.where_scale) { dst = o.where_loc; ff = f - F.where_loc; width = 4; }
+            else if (f < F.prob) { dst = o.where_scale; ff = f - F.where_scale; width = 4; }
+            else if (f == F.prob) { dst = o.presence_prob; }
+            else { Z(nw + 5, j, r) = v; dst = o.presence_logit; }
+            if (dst && valid_row(r)) dst[((trow + grow_of(r)) * NS + j) * width + ff] = v;
+        }
+        // GRU states travel with their slots; discovered objects start from the trainable initial states
+        for (int i = c.tid; i < nh * R; i += c.nthreads) {
+            const int f = i / R, r = i % R;
+            float tv[MAX_SLOTS], pv[MAX_SLOTS];
+            const float t0 = prm(P.po.temporal_h0 + f), p0 = prm(P.po.prior_h0 + f);
+            for (int j = 0; j < NS; ++j) {
+                const int k = (int)c.sm[m.Perm + j * R + r];
+                tv[j] = k < NS ? c.sm[m.Tst + f * LDS() + k * R + r] : t0;
+                pv[j] = k < NS ? c.sm[m.Pst + f * LDS() + k * R + r] : p0;
+            }
+            for (int j = 0; j < NS; ++j) {
+                c.sm[m.Tst + f * LDS() + j * R + r] = tv[j];
+                c.sm[m.Pst + f * LDS() + j * R + r] = pv[j];
+            }
+        }
+        c.sync();
+    }
+    SQ_DEV bool valid_row(int r) const {
+        bool v = valid[0];
+#pragma unroll
+        for (int q = 1; q < R; ++q) if (r == q) v = valid[q];
+        return v;
+    }
+    SQ_DEV int grow_of(int r) const {
+        int v = grow[0];
+#pragma unroll
+        for (int q = 1; q < R; ++q) if (r == q) v = grow[q];
+        return v;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // decoder + canvas + pixel likelihood (modules.py:435-467; seq.py:271-273)
+    // ------------------------------------------------------------------------------------------
+    SQ_DEV void decode_and_score(int t) const {
+        const Smem& m = P.sm;
+        const int NS = P.NS, nw = P.nw, G = P.cfg.G, W = P.cfg.W, H = P.cfg.H, g = P.g, PX = P.P;
+        const sqair_outputs& o = J.out;
+        const size_t trow = (size_t)t * P.rows;
+        for (int s = 0; s < NS; ++s) { lin(L_DEC1, s); lin(L_DEC2); lin(L_DEC3, s); }
+        if (o.glimpse)
+            for (int i = c.tid; i < R * NS * g; i += c.nthreads) {
+                const int px = i % g, s = (i / g) % NS, r = i / (g * NS);
+                if (valid_row(r)) o.glimpse[((trow + grow_of(r)) * NS + s) * g + px] = c.sm[m.Dgl + px * LDS() + s * R + r];
+            }
+        // inverse-transformer coordinates of every slot (Pri is dead by now and reused as a table)
+        float* cc = c.sm + m.Pri;    // [4][NS][R]
+        for (int i = c.tid; i < LDS(); i += c.nthreads) {
+            const int s = i / R, r = i % R;
+            cc[0 * LDS() + i] = fmaxf(sigmoidf_(Z(nw + 0, s, r)), 1e-4f);
+            cc[1 * LDS() + i] = fmaxf(sigmoidf_(Z(nw + 1, s, r)), 1e-4f);
+            cc[2 * LDS() + i] = tanhf(Z(nw + 2, s, r));
+            cc[3 * LDS() + i] = tanhf(Z(nw + 3, s, r));
+        }
+        c.sync();
+        const float hg = 0.5f * (float)(G - 1);
+        // p(x|z) stds as the reference builds them: (sqrt(std))^2 (modules.py:419-422)
+        const float sf0 = sqrtf(P.cfg.output_std), sb0 = sqrtf(P.cfg.bg_std);
+        const float sf = sf0 * sf0, sb = sb0 * sb0;
+        float ll[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) ll[r] = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            for (int px = c.tid; px < PX; px += c.nthreads) {
+                const int iy = px / W, ix = px % W;
+                const float u = lin11(ix, W), v = lin11(iy, H);
+                float canvas = 0.f, nz = 0.f;
+                for (int s = 0; s < NS; ++s) {
+                    const float pres = Z(nw + 4, s, r);
+                    if (pres == 0.f) continue;
+                    const float sx = cc[0 * LDS() + s * R + r], sy = cc[1 * LDS() + s * R + r];
+                    const float tx = cc[2 * LDS() + s * R + r], ty = cc[3 * LDS() + s * R + r];
+                    const float xg = hg * ((u - tx) / sx) + hg;
+                    const float yg = hg * ((v - ty) / sy) + hg;
+                    const float* gl = c.sm + m.Dgl + s * R + r;
+                    const int lds = LDS();
+                    canvas += pres * bilinear_zero_pad(xg, yg, G, G, [&](int gx, int gy) { return gl[(gy * G + gx) * lds]; });
+                    nz += pres * bilinear_zero_pad(xg, yg, G, G, [&](int, int) { return 1.f; });
+                }
+                const float mask = sigmoidf_(-10.f + nz * 20.f);                    // modules.py:462
+                canvas += prm(P.po.mean_img + px) * mask;                           // modules.py:465
+                const float std = mask * sf + (1.f - mask) * sb;                    // modules.py:453
+                ll[r] += normal_lp(SQ_LDG(imgrow[r] + px), canvas, std);
+                if (o.canvas && valid[r]) o.canvas[(trow + grow[r]) * PX + px] = canvas;
+            }
+        }
+        // block reduction of the R partial sums
+        float* red = c.sm + m.Red;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float v = warp_sum(ll[r]);
+            if (c.lane == 0) red[c.warp * R + r] = v;
+        }
+        c.sync();
+        for (int r = c.tid; r < R; r += c.nthreads) {
+            float a = 0.f;
+            for (int w = 0; w < c.nwarps; ++w) a += red[w * R + r];
+            rowacc(RA_LL, r) = a;
+        }
+        c.sync();
+    }
+
+    // per-frame scalars and the remaining outputs (seq.py:215-257,271-276; sqair_modules.py:473-488)
+    SQ_DEV void write_frame_outputs(int t) const {
+        const Smem& m = P.sm;
+        const RecF& F = P.rec;
+        const int NS = P.NS;
+        const sqair_outputs& o = J.out;
+        const size_t trow = (size_t)t * P.rows;
+        for (int i = c.tid; i < LDS(); i += c.nthreads) {
+            const int s = i / R, r = i % R;
+            if (!valid_row(r)) continue;
+            const size_t b = (trow + grow_of(r)) * NS + s;
+            if (o.obj_id) o.obj_id[b] = c.sm[m.Ids + s * R + r];
+            if (o.disc_what_log_prob) o.disc_what_log_prob[b] = lp(LP_DQWHAT, s, r);
+            if (o.disc_where_log_prob) o.disc_where_log_prob[b] = lp(LP_DQWHERE, s, r);
+            if (o.disc_what_prior_log_prob) o.disc_what_prior_log_prob[b] = lp(LP_DPWHAT, s, r);
+            if (o.disc_where_prior_log_prob) o.disc_where_prior_log_prob[b] = lp(LP_DPWHERE, s, r);
+            if (o.prop_what_log_prob) o.prop_what_log_prob[b] = lp(LP_PQWHAT, s, r);
+            if (o.prop_where_log_prob) o.prop_where_log_prob[b] = lp(LP_PQWHERE, s, r);
+            if (o.prop_what_prior_log_prob) o.prop_what_prior_log_prob[b] = lp(LP_PPWHAT, s, r);
+            if (o.prop_where_prior_log_prob) o.prop_where_prior_log_prob[b] = lp(LP_PPWHERE, s, r);
+            if (o.prop_prob) o.prop_prob[b] = lp(LP_PROB, s, r);
+            if (o.prop_pres) o.prop_pres[b] = rec(m.PropOut, s + 1, F.pres, r);
+            if (o.disc_pres) o.disc_pres[b] = rec(m.DiscOut, s + 1, F.pres, r);
+        }
+        if (o.disc_prob)
+            for (int i = c.tid; i < (NS + 1) * R; i += c.nthreads) {
+                const int k = i / R, r = i % R;
+                if (valid_row(r)) o.disc_prob[(trow + grow_of(r)) * (NS + 1) + k] = c.sm[m.Spl + i];
+            }
+        for (int r = c.tid; r < R; r += c.nthreads) {
+            if (!valid_row(r)) continue;
+            // q, p in the reference's summation order: sum_s(what_s + where_s) + discrete term, disc + prop
+            float pq = 0.f, pp = 0.f, dq = 0.f, dp = 0.f;
+            for (int s = 0; s < NS; ++s) {
+                pq += lp(LP_PQWHAT, s, r) + lp(LP_PQWHERE, s, r);
+                pp += lp(LP_PPWHAT, s, r) + lp(LP_PPWHERE, s, r);
+                dq += lp(LP_DQWHAT, s, r) + lp(LP_DQWHERE, s, r);
+                dp += lp(LP_DPWHAT, s, r) + lp(LP_DPWHERE, s, r);
+            }
+            const float prop_lp = rowacc(RA_QPRES, r), prop_plp = rowacc(RA_PPRES, r);
+            const float qnum = rowacc(RA_QNUM, r), pnum = rowacc(RA_PNUM, r);
+            const float q = (dq + qnum) + (pq + prop_lp);
+            const float p = (dp + pnum) + (pp + prop_plp);
+            const float ll = rowacc(RA_LL, r), kl = q - p;
+            const size_t b = trow + grow_of(r);
+            if (o.step_log_prob) o.step_log_prob[b] = prop_lp + qnum;
+            if (o.discrete_log_prob) o.discrete_log_prob[b] = prop_lp + qnum;
+            if (o.disc_log_prob) o.disc_log_prob[b] = qnum;
+            if (o.disc_prior_log_prob) o.disc_prior_log_prob[b] = pnum;
+            if (o.prop_log_prob) o.prop_log_prob[b] = prop_lp;
+            if (o.prop_prior_log_prob) o.prop_prior_log_prob[b] = prop_plp;
+            if (o.num_prop_steps_per_sample) o.num_prop_steps_per_sample[b] = rowacc(RA_NPROP, r);
+            if (o.num_disc_steps_per_sample) o.num_disc_steps_per_sample[b] = rowacc(RA_NDISC, r);
+            if (o.num_steps_per_sample) o.num_steps_per_sample[b] = rowacc(7, r);
+            if (o.data_ll_per_sample) o.data_ll_per_sample[b] = ll;
+            if (o.kl_per_sample) o.kl_per_sample[b] = kl;
+            if (o.log_q_z_given_x_per_sample) o.log_q_z_given_x_per_sample[b] = q;
+            if (o.log_p_z_per_sample) o.log_p_z_per_sample[b] = p;
+            if (o.log_weights_per_timestep) o.log_weights_per_timestep[b] = ll - kl;
+        }
+        c.sync();
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // one frame (seq.py:181-269 / sqair_modules.py:446-512)
+    // ------------------------------------------------------------------------------------------
+    SQ_DEV void frame(int t) {
+        const Smem& m = P.sm;
+        const int NS = P.NS, nh = P.nh;
+#pragma unroll
+        for (int r = 0; r < R; ++r) imgrow[r] = J.obs + ((size_t)t * P.cfg.B + grow[r] / P.cfg.K) * P.P;
+        for (int i = c.tid; i < 16 * R; i += c.nthreads) c.sm[m.RowAcc + i] = 0.f;
+        for (int i = c.tid; i < nh * R; i += c.nthreads) {
+            c.sm[m.Hrnn + i] = prm(P.po.prop_h0 + i / R);          // propagate.py:170 / core.py:130
+            c.sm[m.DIn + nh * R + i] = 0.f;                         // conditioning accumulator
+        }
+        c.sync();
+        for (int s = 0; s < NS; ++s) prop_slot(t, s);
+        // latent summary: sum_s pres_s * MLP([what_s, where_s]) (sqair_modules.py:368-385,501)
+        for (int s = 0; s < NS; ++s) {
+            lin(L_LAT1, s); lin(L_LAT2);
+            for (int i = c.tid; i < nh * R; i += c.nthreads)
+                c.sm[m.DIn + nh * R + i] += c.sm[m.A1 + i] * rec(m.PropOut, s + 1, P.rec.pres, i % R);
+            c.sync();
+        }
+        for (int r = c.tid; r < R; r += c.nthreads) {               // sqair_modules.py:505-507
+            float a = 0.f;
+            for (int s = 0; s < NS; ++s) a += (sigmoidf_(pri(0, s, r)) - 0.5f) / (float)NS;
+            c.sm[m.Exp + r] = a;
+        }
+        lin(L_IMG1); lin(L_IMG2);                                    // core.py:165, hoisted out of the slot loop
+        for (int i = c.tid; i < nh * R; i += c.nthreads) c.sm[m.Hrnn + i] = prm(P.po.disc_h0 + i / R);
+        c.sync();
+        for (int s = 0; s < NS; ++s) disc_slot(t, s);
+        disc_priors(t);
+        choose_latents(t);
+        decode_and_score(t);
+        write_frame_outputs(t);
+    }
+
+    SQ_DEV void run() {
+        init_sequence();
+        for (int t = 0; t < P.cfg.T; ++t) frame(t);
+    }
+};
+
+}  // namespace sq

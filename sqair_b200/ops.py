@@ -1,0 +1,119 @@
+"""Thin torch-facing wrappers over the C ABI (include/sqair_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream; every computation below is a
+call into libsqair_b200.so on the caller's current stream.  There is no fallback: tensors must be
+CUDA tensors and the library must be built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _capi
+from ._capi import SqairCfg, SqairOutputs, OUTPUT_NAMES, check, make_cfg, output_shapes, query_sizes, param_layout
+
+
+def _ptr(t: torch.Tensor):
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError('sqair_b200 expects contiguous float32 CUDA tensors (no CPU fallback exists)')
+
+
+def pack_params(cfg: SqairCfg, flat: torch.Tensor) -> torch.Tensor:
+    """Canonical flat parameter vector (TF variable order) -> kernel-side buffer."""
+    _need_cuda(flat)
+    sizes = query_sizes(cfg)
+    if flat.numel() != sizes.param_count:
+        raise ValueError('expected %d parameters, got %d' % (sizes.param_count, flat.numel()))
+    packed = torch.empty(sizes.packed_floats, dtype=torch.float32, device=flat.device)
+    check(_capi.lib().sqair_pack_params(C.byref(cfg), _ptr(flat), _ptr(packed), _stream()))
+    return packed
+
+
+def alloc_noise(cfg: SqairCfg, device):
+    rows, n2 = cfg.B * cfg.K, 2 * cfg.n
+    return dict(eps_where=torch.empty(cfg.T, rows, n2, 4, dtype=torch.float32, device=device),
+                eps_what=torch.empty(cfg.T, rows, n2, cfg.n_what, dtype=torch.float32, device=device),
+                u_pres=torch.empty(cfg.T, rows, n2, dtype=torch.float32, device=device))
+
+
+def fill_noise(cfg: SqairCfg, seed: int, row_offset: int = 0, noise=None, device=None):
+    """Counter-based draws for every noise site; `row_offset` = global index of this shard's row 0."""
+    if noise is None:
+        noise = alloc_noise(cfg, device or torch.device('cuda', torch.cuda.current_device()))
+    _need_cuda(noise['eps_where'], noise['eps_what'], noise['u_pres'])
+    check(_capi.lib().sqair_fill_noise(C.byref(cfg), C.c_uint64(seed & (2 ** 64 - 1)), int(row_offset),
+                                       _ptr(noise['eps_where']), _ptr(noise['eps_what']), _ptr(noise['u_pres']),
+                                       _stream()))
+    return noise
+
+
+def alloc_outputs(cfg: SqairCfg, device, names=None):
+    shapes = output_shapes(cfg)
+    return {k: torch.empty(shapes[k], dtype=torch.float32, device=device) for k in (names or OUTPUT_NAMES)}
+
+
+def forward(cfg: SqairCfg, packed: torch.Tensor, obs: torch.Tensor, noise: dict, outputs: dict = None, names=None):
+    """SequentialAIR over a [T,B,H,W] batch (seq.py:69-84); returns {name: [T, B*K, ...] tensor}."""
+    _need_cuda(packed, obs, noise['eps_where'], noise['eps_what'], noise['u_pres'])
+    if tuple(obs.shape) != (cfg.T, cfg.B, cfg.H, cfg.W):
+        raise ValueError('obs must be [T,B,H,W] = %s, got %s' % ((cfg.T, cfg.B, cfg.H, cfg.W), tuple(obs.shape)))
+    rows, n2 = cfg.B * cfg.K, 2 * cfg.n
+    if tuple(noise['eps_where'].shape) != (cfg.T, rows, n2, 4) or \
+            tuple(noise['eps_what'].shape) != (cfg.T, rows, n2, cfg.n_what) or \
+            tuple(noise['u_pres'].shape) != (cfg.T, rows, n2):
+        raise ValueError('noise tensors have the wrong shape for this configuration')
+    if outputs is None:
+        outputs = alloc_outputs(cfg, obs.device, names)
+    so = SqairOutputs()
+    for k, v in outputs.items():
+        _need_cuda(v)
+        setattr(so, k, v.data_ptr())
+    check(_capi.lib().sqair_forward(C.byref(cfg), _ptr(packed), _ptr(obs), _ptr(noise['eps_where']),
+                                    _ptr(noise['eps_what']), _ptr(noise['u_pres']), C.byref(so), _stream()))
+    return outputs
+
+
+def objective(log_w_t: torch.Tensor, disc_lp_t: torch.Tensor, B: int, K: int):
+    """Particle reductions of Model._build / make_target (model.py:88-103,150-158)."""
+    _need_cuda(log_w_t, disc_lp_t)
+    T = log_w_t.shape[0]
+    dev = log_w_t.device
+    lw = torch.empty(B, K, dtype=torch.float32, device=dev)
+    pe = torch.empty(B, dtype=torch.float32, device=dev)
+    iw = torch.empty(B, K, dtype=torch.float32, device=dev)
+    sc = torch.empty(_capi.OBJ_N, dtype=torch.float32, device=dev)
+    check(_capi.lib().sqair_objective(_ptr(log_w_t), _ptr(disc_lp_t), T, B, K, _ptr(lw), _ptr(pe), _ptr(iw), _ptr(sc),
+                                      _stream()))
+    return dict(log_weights=lw, elbo_iwae_per_example=pe, importance_weights=iw, scalars=sc)
+
+
+def stn_glimpse(img: torch.Tensor, where: torch.Tensor, G: int) -> torch.Tensor:
+    """SpatialTransformer forward at where-logits (modules.py:165-172,204-227): [N,H,W],[N,4] -> [N,G,G]."""
+    _need_cuda(img, where)
+    N, H, W = img.shape
+    out = torch.empty(N, G, G, dtype=torch.float32, device=img.device)
+    check(_capi.lib().sqair_stn_glimpse(_ptr(img), _ptr(where), _ptr(out), N, H, W, G, _stream()))
+    return out
+
+
+def canvas_ll(glimpse, where, presence, mean_img, img, output_std=0.3, bg_std=None):
+    """AIRDecoder canvas composition + pixel log-likelihood (modules.py:435-467; seq.py:272-273)."""
+    _need_cuda(glimpse, where, presence, mean_img, img)
+    N, n, G, _ = glimpse.shape
+    H, W = img.shape[1:]
+    canvas = torch.empty(N, H, W, dtype=torch.float32, device=img.device)
+    ll = torch.empty(N, dtype=torch.float32, device=img.device)
+    check(_capi.lib().sqair_canvas_ll(_ptr(glimpse), _ptr(where), _ptr(presence), _ptr(mean_img), _ptr(img),
+                                      _ptr(canvas), _ptr(ll), N, n, H, W, G, float(output_std),
+                                      float(output_std if bg_std is None else bg_std), _stream()))
+    return canvas, ll

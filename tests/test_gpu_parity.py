@@ -1,0 +1,176 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerance: 1e-4 relative (+1e-4 absolute near zero) on every real-valued output, bit-exact on the
+integer-valued ones (presence, object ids, step counts) -- BASELINE.json north_star.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import sqair_testlib as TL
+from oracle import sqair_oracle as O
+from oracle import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu():
+    if not torch.cuda.is_available():
+        pytest.fail('no CUDA device: the gpu-marked tests need a B200')
+    from sqair_b200 import ops
+    return ops, torch.device('cuda:0')
+
+
+def run_cuda(cfg, imgs, params, noise, rows_per_cta=None):
+    ops, dev = _gpu()
+    ccfg = TL.capi_cfg(cfg)
+    old = os.environ.pop('SQAIR_ROWS_PER_CTA', None)
+    if rows_per_cta:
+        os.environ['SQAIR_ROWS_PER_CTA'] = str(rows_per_cta)
+    try:
+        flat = O.flatten_params(params, cfg).to(dev)
+        packed = ops.pack_params(ccfg, flat)
+        nz = {k: torch.from_numpy(v).to(dev) for k, v in noise.items()}
+        out = ops.forward(ccfg, packed, torch.from_numpy(imgs).to(dev), nz)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop('SQAIR_ROWS_PER_CTA', None)
+        if old is not None:
+            os.environ['SQAIR_ROWS_PER_CTA'] = old
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+CASES = {
+    'c1_T3_B4_K1_n2': dict(T=3, B=4, K=1, n=2),                       # BASELINE configs[0]
+    'small_c2_T4_B3_K5_n4': dict(T=4, B=3, K=5, n=4),                 # configs[1] shape, fewer sequences
+    'n3_K2': dict(T=3, B=3, K=2, n=3),
+    'rw_prior': dict(T=3, B=2, K=2, n=2, prior_type='rw'),
+    'guided_geom': dict(T=3, B=2, K=2, n=2, prior_type='guided', disc_prior_type='geom'),
+    'no_rec_no_mask': dict(T=3, B=2, K=1, n=2, rec_where_prior=False, masked_glimpse=False),
+    'c4_like_64px_n6': dict(T=2, B=2, K=2, n=6, H=64, W=64),
+}
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_forward_parity(name):
+    cfg = O.Cfg(**CASES[name])
+    imgs, params, noise = TL.make_inputs(cfg)
+    want, _ = TL.run_oracle(cfg, imgs, params, noise)
+    got = run_cuda(cfg, imgs, params, noise)
+    bad = TL.compare_outputs(got, want)
+    assert not bad, '\n'.join(bad)
+
+
+@pytest.mark.parametrize('R', [1, 2, 3, 4, 5, 8])
+def test_rows_per_block_variants(R):
+    """Every instantiation of the persistent kernel, including row counts that do not divide."""
+    cfg = O.Cfg(T=3, B=3, K=3, n=3)
+    imgs, params, noise = TL.make_inputs(cfg)
+    want, _ = TL.run_oracle(cfg, imgs, params, noise)
+    got = run_cuda(cfg, imgs, params, noise, rows_per_cta=R)
+    bad = TL.compare_outputs(got, want)
+    assert not bad, '\n'.join(bad)
+
+
+def test_full_size_c2_parity():
+    """BASELINE configs[1]: T=10, B=32, K=5, n=4, 50x50 (the oracle needs a few seconds)."""
+    cfg = O.Cfg(T=10, B=32, K=5, n=4)
+    imgs, params, noise = TL.make_inputs(cfg)
+    want, obj = TL.run_oracle(cfg, imgs, params, noise)
+    got = run_cuda(cfg, imgs, params, noise)
+    bad = TL.compare_outputs(got, want)
+    assert not bad, '\n'.join(bad)
+    assert 0.05 < want['presence'].mean() < 0.95     # both branches exercised
+
+
+def test_device_noise_matches_numpy_philox():
+    ops, dev = _gpu()
+    cfg = O.Cfg(T=3, B=4, K=2, n=3)
+    ccfg = TL.capi_cfg(cfg)
+    for off in (0, 5):
+        nz = ops.fill_noise(ccfg, seed=0x1234567890abcdef, row_offset=off, device=dev)
+        torch.cuda.synchronize()
+        ref = S.philox_noise(cfg.T, cfg.rows, cfg.n, cfg.nw, 0x1234567890abcdef, row_offset=off)
+        assert np.array_equal(nz['u_pres'].cpu().numpy(), ref['u_pres'])              # uniforms are exact
+        np.testing.assert_allclose(nz['eps_where'].cpu().numpy(), ref['eps_where'], rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(nz['eps_what'].cpu().numpy(), ref['eps_what'], rtol=1e-4, atol=2e-5)
+
+
+def test_sharded_rows_reproduce_unsharded_run():
+    """Multi-GPU invariant: sequences are independent, so running two shards of the batch
+    with row_offset-keyed noise must reproduce the single-call result exactly."""
+    ops, dev = _gpu()
+    cfg = O.Cfg(T=3, B=4, K=3, n=2)
+    imgs, params, _ = TL.make_inputs(cfg)
+    ccfg = TL.capi_cfg(cfg)
+    flat = O.flatten_params(params, cfg).to(dev)
+    packed = ops.pack_params(ccfg, flat)
+    obs = torch.from_numpy(imgs).to(dev)
+    full = ops.forward(ccfg, packed, obs, ops.fill_noise(ccfg, 99, 0, device=dev))
+    half = O.Cfg(T=3, B=2, K=3, n=2)
+    hcfg = TL.capi_cfg(half)
+    parts = []
+    for s in range(2):
+        o = obs[:, 2 * s:2 * s + 2].contiguous()
+        parts.append(ops.forward(hcfg, packed, o, ops.fill_noise(hcfg, 99, s * half.rows, device=dev)))
+    torch.cuda.synchronize()
+    for k in full:
+        cat = torch.cat([p[k] for p in parts], 1)
+        assert torch.equal(cat, full[k]), k
+
+
+def test_stn_glimpse_op():
+    ops, dev = _gpu()
+    rng = np.random.default_rng(0)
+    N, H, W, G = 37, 50, 50, 20
+    img = rng.random((N, H, W), dtype=np.float32)
+    where = (rng.standard_normal((N, 4)) * 1.5).astype(np.float32)
+    got = ops.stn_glimpse(torch.from_numpy(img).to(dev), torch.from_numpy(where).to(dev), G).cpu().numpy()
+    want = O.stn_forward(torch.from_numpy(img), O.to_coords(torch.from_numpy(where)), G).numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
+    # identity transform copies the image when G == H (invariant)
+    ident = np.tile(np.array([[20., 20., 0., 0.]], dtype=np.float32), (N, 1))
+    got = ops.stn_glimpse(torch.from_numpy(img).to(dev), torch.from_numpy(ident).to(dev), H).cpu().numpy()
+    np.testing.assert_allclose(got, img, rtol=0, atol=1e-5)
+
+
+def test_canvas_ll_op():
+    ops, dev = _gpu()
+    rng = np.random.default_rng(1)
+    N, n, H, W, G = 9, 4, 50, 50, 20
+    cfg = O.Cfg(T=1, B=N, K=1, n=n)
+    p = O.init_params(cfg, 3, mean_img=rng.random((H, W)) * 0.2)
+    what = torch.from_numpy(rng.standard_normal((N, n, cfg.nw)).astype(np.float32))
+    where = torch.from_numpy((rng.standard_normal((N, n, 4))).astype(np.float32))
+    pres = torch.from_numpy((rng.random((N, n, 1)) < 0.6).astype(np.float32))
+    img = torch.from_numpy(rng.random((N, H, W), dtype=np.float32))
+    canvas, std, glimpse = O.air_decoder(p, cfg, what, where, pres)
+    want_ll = O.normal_log_prob(img, canvas, std).sum((1, 2)).numpy()
+    got_canvas, got_ll = ops.canvas_ll(glimpse.contiguous().to(dev), where.to(dev), pres[..., 0].contiguous().to(dev),
+                                       p['decoder/air_decoder/Variable'][..., 0].contiguous().to(dev), img.to(dev))
+    np.testing.assert_allclose(got_canvas.cpu().numpy(), canvas.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(got_ll.cpu().numpy(), want_ll, rtol=1e-4, atol=1e-3)
+
+
+def test_objective_op():
+    ops, dev = _gpu()
+    from sqair_b200 import _capi
+    rng = np.random.default_rng(2)
+    T, B, K = 10, 32, 5
+    lw_t = (rng.standard_normal((T, B * K)) * 3 + 50).astype(np.float32)
+    lp_t = (rng.standard_normal((T, B * K))).astype(np.float32)
+    got = ops.objective(torch.from_numpy(lw_t).to(dev), torch.from_numpy(lp_t).to(dev), B, K)
+    lw = torch.from_numpy(lw_t).sum(0).reshape(B, K)
+    lp = torch.from_numpy(lp_t).sum(0).reshape(B, K)
+    np.testing.assert_allclose(got['log_weights'].cpu().numpy(), lw.numpy(), rtol=1e-5)
+    np.testing.assert_allclose(got['elbo_iwae_per_example'].cpu().numpy(), O.iwae(lw).numpy(), rtol=1e-5)
+    np.testing.assert_allclose(got['importance_weights'].cpu().numpy(), torch.softmax(lw, -1).numpy(),
+                               rtol=1e-4, atol=1e-6)
+    sc = got['scalars'].cpu().numpy()
+    np.testing.assert_allclose(sc[_capi.OBJ_ELBO_VAE], lw.mean().item(), rtol=1e-5)
+    np.testing.assert_allclose(sc[_capi.OBJ_ELBO_IWAE], O.iwae(lw).mean().item(), rtol=1e-5)
+    np.testing.assert_allclose(sc[_capi.OBJ_ESS], O.ess(torch.softmax(lw, -1)).mean().item(), rtol=1e-4)
+    np.testing.assert_allclose(sc[_capi.OBJ_VIMCO_TARGET], (O.vimco(lw, lp, O.iwae(lw)) / T).item(), rtol=1e-4)
+    np.testing.assert_allclose(sc[_capi.OBJ_IWAE_TARGET], (-O.iwae(lw).mean() / T).item(), rtol=1e-5)
