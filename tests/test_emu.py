@@ -1,0 +1,28 @@
+"""CPU check of the kernel program itself: sqair_device.cuh compiled for the host (one sequential
+"thread" per block, tests/host_emu) must reproduce the oracle.  This validates indexing, slot
+bookkeeping, the layer/packing tables and every formula of the device code without a GPU; the
+`-m gpu` tests then validate the real kernel."""
+import pytest
+
+import sqair_testlib as TL
+from oracle import sqair_oracle as O
+
+CASES = [
+    (dict(T=3, B=4, K=1, n=2), 2),
+    (dict(T=3, B=3, K=2, n=3), 4),
+    (dict(T=2, B=2, K=5, n=4), 5),
+    (dict(T=3, B=2, K=2, n=2, prior_type='rw'), 1),
+    (dict(T=3, B=2, K=2, n=2, prior_type='guided', disc_prior_type='geom'), 3),
+    (dict(T=2, B=2, K=1, n=2, rec_where_prior=False, masked_glimpse=False), 2),
+    (dict(T=2, B=2, K=2, n=6, H=64, W=64), 4),
+]
+
+
+@pytest.mark.parametrize('kw,R', CASES)
+def test_emulated_kernel_matches_oracle(kw, R):
+    cfg = O.Cfg(**kw)
+    imgs, params, noise = TL.make_inputs(cfg)
+    want, _ = TL.run_oracle(cfg, imgs, params, noise)
+    got = TL.run_emu(cfg, imgs, params, noise, R)
+    bad = TL.compare_outputs(got, want)
+    assert not bad, '\n'.join(bad)

@@ -66,7 +66,7 @@ def test_forward_parity(name):
 @pytest.mark.parametrize('R', [1, 2, 3, 4, 5, 8])
 def test_rows_per_block_variants(R):
     """Every instantiation of the persistent kernel, including row counts that do not divide."""
-    cfg = O.Cfg(T=3, B=3, K=3, n=3)
+    cfg = O.Cfg(T=3, B=3, K=3, n=2)
     imgs, params, noise = TL.make_inputs(cfg)
     want, _ = TL.run_oracle(cfg, imgs, params, noise)
     got = run_cuda(cfg, imgs, params, noise, rows_per_cta=R)
