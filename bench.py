@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the SQAIR Discover/Propagate hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path over one batch: draw the step's noise, run SequentialAIR over
+T frames for B sequences x K particles, reduce the particle objective (ELBO / IWAE / VIMCO value).
+Workload at every N: BASELINE configs[1] per GPU (T=10, B=32, K=5 IWAE, n=4 objects, 50x50,
+synthetic moving sprites, random-init weights) -- weak scaling: sequences are independent, each
+rank owns B=32 of them, no data-path collective.
+
+`value`  : frames/s with inputs resident in HBM (CUDA events around each step, L2 flushed between).
+`e2e`    : same metric through the public plugin API (`sqair_b200.model.Model`-level call chain) with the
+           step's frames coming from pinned HOST memory and the ELBO scalars + log-weights read back.
+`--impl reference` : the reference's own CPU path.  TF1/Sonnet cannot be installed here, so this
+           arm times the oracle (the torch-CPU restatement of the reference graph, kind "port") on
+           all host cores, same config / metric.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(T=10, B=32, K=5, n=4, H=50, W=50)
+WORKLOAD_NAME = 'configs[1]: multi-MNIST-like 50x50, seq_len=10, 4 objects, batch=32, K=5 IWAE (per GPU)'
+METRIC = 'frames/sec (seq_len=10, K=5 IWAE, 4 obj, 50x50)'
+
+
+def algorithmic_bytes(w, params):
+    """forward HBM bytes per particle-frame (fp32) x particle-frames + parameters once."""
+    n, nw, P, g, K = w['n'], 50, w['H'] * w['W'], 400, w['K']
+    per_pf = 4 * P / K + 4 * P + 4 * n * g + 4 * n * (3 * nw + 12 + 4) + 4 * (14 * n + (n + 1) + 12) + 4 * 2 * n * (nw + 5)
+    return per_pf * w['B'] * w['K'] * w['T'] + 4 * params
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))), 'measured'
+    except Exception:
+        return dict(hbm_gbs=6650.0, bf16_tflops=1590.0), 'fallback'
+
+
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ''
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def run_reference(args):
+    """CPU arm: the oracle (port of the reference graph) on all host cores; rank 0 only."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import sqair_testlib as TL
+    from oracle import sqair_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = dict(WORKLOAD)
+    # bounded sample: shrink the batch if one full step would take too long on this host
+    cfg = O.Cfg(T=w['T'], B=4, K=w['K'], n=w['n'], H=w['H'], W=w['W'])
+    imgs, params, noise = TL.make_inputs(cfg, jitter=0.0)
+    t0 = time.perf_counter(); TL.run_oracle(cfg, imgs, params, noise); probe = time.perf_counter() - t0
+    B = w['B']
+    while B > 4 and probe * (B / 4.0) * (args.steps + args.warmup) > 240.0:
+        B //= 2
+    cfg = O.Cfg(T=w['T'], B=B, K=w['K'], n=w['n'], H=w['H'], W=w['W'])
+    imgs, params, noise = TL.make_inputs(cfg, jitter=0.0)
+    for _ in range(args.warmup):
+        TL.run_oracle(cfg, imgs, params, noise)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        TL.run_oracle(cfg, imgs, params, noise)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = B * w['T'] / dt
+    sample = '%d steps of %d sequences x K=%d x T=%d (torch-CPU fp32 oracle, %d threads)' % (args.steps, B, w['K'], w['T'], cores)
+    line = dict(impl='reference', metric=METRIC, value=value, unit='frames/s', n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=dt * 1e3 * (w['B'] / B), higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload=WORKLOAD_NAME, **w),
+                cpu_baseline=dict(value=value, unit='frames/s', cores=cores, kind='port', sample=sample),
+                e2e=dict(value=value, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0,
+                note='reference TF1/Sonnet cannot run here (Python 2 / TF 1.6); this is its op-for-op torch-CPU restatement')
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample():
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import sqair_testlib as TL
+    from oracle import sqair_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = WORKLOAD
+    cfg = O.Cfg(T=w['T'], B=8, K=w['K'], n=w['n'], H=w['H'], W=w['W'])
+    imgs, params, noise = TL.make_inputs(cfg, jitter=0.0)
+    TL.run_oracle(cfg, imgs, params, noise)
+    steps, t0 = 0, time.perf_counter()
+    while steps < 3 or (time.perf_counter() - t0 < 10.0 and steps < 20):
+        TL.run_oracle(cfg, imgs, params, noise)
+        steps += 1
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=cfg.B * cfg.T / dt, unit='frames/s', cores=cores, kind='port',
+                sample='%d steps of 8 sequences x K=5 x T=10 of the same workload, torch-CPU fp32 oracle' % steps)
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from sqair_b200 import _capi, ops
+    from sqair_b200.model import load_synthetic_model
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    w = WORKLOAD
+    model = load_synthetic_model(device=dev, rank=rank, **w)          # public plugin API (mirrors configs/mlp_mnist_model.load)
+    cfg = model.cfg
+    sizes = _capi.query_sizes(cfg)
+    obs_host = model.synthetic_obs_host()                               # pinned [T,B,H,W]
+    obs_dev = obs_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step_device(i):
+        return model.step(obs_dev, seed=1000 + i)                       # noise + sequence kernel + objective
+
+    def step_e2e(i):
+        res = model.step(obs_host.to(dev, non_blocking=True), seed=1000 + i)
+        return res['scalars'].cpu(), res['log_weights'].cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_device(i)
+        step_e2e(i)
+    barrier()
+
+    # ---- device-resident timing: CUDA events around every step, L2 flushed between steps
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        model.step(obs_dev, seed=2000 + i, kernel_events=kev[i])
+        ev[i][1].record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    # ---- end-to-end timing: pinned host frames in, scalars + log-weights out, every step
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+
+    times = torch.tensor([total_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, kern_ms = [float(x) for x in times.cpu()]
+    frames = w['B'] * w['T'] * world * args.steps
+    value = frames / (total_ms * 1e-3)
+    if rank == 0:
+        peaks, which = measured_peaks()
+        alg = algorithmic_bytes(w, sizes.param_count)
+        achieved = alg / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'latest_traffic.json')))['dram_bytes_per_launch']
+        except Exception:
+            pass
+        line = dict(metric=METRIC, value=value, unit='frames/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=total_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='f32', data='synthetic',
+                    config=dict(workload=WORKLOAD_NAME, l2='flushed between timed steps (256 MiB memset)',
+                                rows_per_cta=sizes.rows_per_cta, n_ctas=sizes.n_ctas, smem_bytes=sizes.smem_bytes, **w),
+                    clocks=clocks,
+                    e2e=dict(value=frames / (e2e_ms * 1e-3), unit='frames/s',
+                             h2d_bytes_per_step=int(obs_host.numel() * 4),
+                             d2h_bytes_per_step=int(4 * (_capi.OBJ_N + w['B'] * w['K']))),
+                    gpu_launches=3 * args.steps,
+                    roofline=dict(bound='hbm', achieved=achieved, peak=peaks['hbm_gbs'], unit='GB/s',
+                                  frac=achieved / peaks['hbm_gbs'], traffic=traffic, peak_source=which,
+                                  kernel='sqair_sequence_kernel', kernel_ms=kern_ms, algorithmic_bytes=alg,
+                                  note='latency-bound dependent chain of small dense layers; see DESIGN.md'),
+                    elbo_iwae=float(model.last_scalars[1]))
+        line['cpu_baseline'] = cpu_baseline_sample() if world == 1 else None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,91 @@
+"""Parameter store: the reference's trainable variables by TF name (notebooks/play.ipynb:239-362)
+in one flat fp32 device buffer (canonical order = `sqair_param_layout`) plus its packed kernel-side copy."""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _capi, ops
+
+
+def table(cfg):
+    """OrderedDict name -> (shape, offset) in canonical order."""
+    return OrderedDict((n, (s, o)) for n, s, o, _ in _capi.param_layout(cfg))
+
+
+def initial_values(cfg, seed=42, spec=None):
+    """Sonnet-style initialisation: w ~ TruncNormal(0, 1/sqrt(fan_in)) (+-2 sigma), b = 0,
+    GRU matrices glorot-uniform, trainable initial states 0, plus the reference's constant initialisers taken
+    from `spec` (steps biases, scale offsets, output_scale, gate / mask biases, where-prior readout bias,
+    step_prior_timestep_bias = [10, 0, ...], mean image)."""
+    spec = spec or {}
+    rng = np.random.default_rng(seed)
+    tab = table(cfg)
+    total = sum(int(np.prod(s)) for s, _ in tab.values())
+    flat = np.zeros(total, dtype=np.float32)
+
+    def view(name):
+        s, o = tab[name]
+        return flat[o:o + int(np.prod(s))].reshape(s) if len(s) else flat[o:o + 1]
+
+    for name, (shape, off) in tab.items():
+        base = name.rsplit('/', 1)[-1]
+        if base in ('wz', 'wr', 'wh', 'uz', 'ur', 'uh'):
+            lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+            view(name)[...] = rng.uniform(-lim, lim, shape)
+        elif base == 'w' and 'initial_state' not in name:
+            v = rng.standard_normal(shape)
+            bad = np.abs(v) > 2.
+            while bad.any():
+                v[bad] = rng.standard_normal(int(bad.sum()))
+                bad = np.abs(v) > 2.
+            view(name)[...] = v / math.sqrt(shape[0])
+    DC, PC = 'discovery/discovery_core/', 'propagation/propagation_core/'
+    RN = 'discovery/discover/recurrent_normal_impl/'
+    view('decoder/air_decoder/decoder/output_scale')[...] = spec.get('output_scale', .25)
+    view(DC + 'stochastic_transform_param/scale_offset')[...] = spec.get('disc_scale_offset', -3.)
+    view(PC + 'stochastic_transform_param/scale_offset')[...] = spec.get('prop_scale_offset', -3.)
+    view(DC + 'steps_predictor/mlp/linear_1/b')[...] = spec.get('disc_step_bias', 1.)
+    view(PC + 'steps_predictor/mlp/linear_1/b')[...] = spec.get('prop_step_bias', 5.)
+    view(PC + 'what/linear/b')[...] = 1.                                            # remember_bias, core.py:345
+    if cfg.masked_glimpse:
+        view(DC + 'air_encoder/mlp/linear_1/b')[...] = 1.                            # modules.py:324
+    if cfg.rec_where_prior:
+        view(RN + 'linear/b')[...] = np.asarray(list(spec.get('where_mean', (-2., -2., 0., 0.))) +
+                                                list(spec.get('where_std', (1., 1., 1., 1.))))
+        lim = math.sqrt(6.0 / 5.0)
+        view(RN + 'init_sample')[...] = rng.uniform(-lim, lim, (1, 4))               # tf.get_variable default: glorot uniform
+    view('model/sequential_air/while/sqair_timestep/discover/step_prior_timestep_bias')[0] = 10.
+    lim = math.sqrt(6.0 / 10.0)
+    view(PC + 'affine_diag_normal/cholesky_scale')[...] = rng.uniform(-lim, lim, (10,))
+    if spec.get('mean_img') is not None:
+        view('decoder/air_decoder/Variable')[...] = np.asarray(spec['mean_img'], dtype=np.float32).reshape(cfg.H, cfg.W, 1)
+    return flat
+
+
+class ParamStore(object):
+    def __init__(self, cfg, device, seed=42, spec=None):
+        self.cfg, self.device = cfg, device
+        self.table = table(cfg)
+        self.flat = torch.from_numpy(initial_values(cfg, seed, spec)).to(device)
+        self._packed, self._version, self._packed_version = None, 0, -1
+
+    def state_dict(self):
+        return OrderedDict((n, self.flat[o:o + int(np.prod(s))].reshape(s)) for n, (s, o) in self.table.items())
+
+    def load_state_dict(self, sd):
+        for n, (s, o) in self.table.items():
+            self.flat[o:o + int(np.prod(s))].copy_(torch.as_tensor(sd[n], dtype=torch.float32).reshape(-1))
+        self._version += 1
+
+    def load_flat(self, flat):
+        self.flat.copy_(torch.as_tensor(flat, dtype=torch.float32).reshape(-1))
+        self._version += 1
+
+    def packed(self):
+        """Kernel-side copy, re-packed only after the parameters changed."""
+        if self._packed_version != self._version:
+            self._packed = ops.pack_params(self.cfg, self.flat)
+            self._packed_version = self._version
+        return self._packed

@@ -1,0 +1,104 @@
+"""SequentialAIR: the operator this package accelerates (reference: sqair/seq.py:41-279).
+
+The reference unrolls SQAIRTimestep in a `tf.while_loop` writing 38 TensorArrays; here the same
+recursion is ONE persistent CUDA kernel launch (`sqair_forward`) per call.  The constructor keeps the
+reference signature and validates that the wired modules form the architecture the fused kernel
+implements (the reference's MNIST config and its flag-level variants)."""
+import torch
+
+from . import _capi, ops
+from .params import ParamStore
+from .sqair_modules import SQAIRTimestep
+
+
+class AttrDict(dict):
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+class SequentialAIR(object):
+    def __init__(self, max_steps, glimpse_size, discover, propagate, time_cell, decoder,
+                 sample_from_prior=False, generate_after=-1):
+        if sample_from_prior or generate_after > 0:
+            raise NotImplementedError('sampling from the prior / conditional generation (seq.py:198-203) is '
+                                      'outside the fused inference path of this build')
+        self._max_steps, self._glimpse_size, self._decoder = max_steps, tuple(glimpse_size), decoder
+        self._sqair = SQAIRTimestep(self._max_steps, discover, propagate, time_cell)
+        self._discover, self._propagate = discover, propagate
+        self._spec = self._read_architecture()
+        self._stores = {}
+
+    # ---- architecture -> kernel configuration ----------------------------------------------------
+    def _read_architecture(self):
+        d, p = self._discover._cell, self._propagate._ssm._cell
+        nh = d._n_hidden
+        def need(cond, what):
+            if not cond:
+                raise NotImplementedError('fused SQAIR kernel: unsupported architecture: ' + what)
+        need(d._cell.kind == 'VanillaRNN' and p._cell.kind == 'VanillaRNN', 'transition must be VanillaRNN')
+        need(p._temporal_cell.kind == 'GRU' and self._propagate._prior._cell.kind == 'GRU',
+             'time_transition / prior_transition must be GRU')
+        need(p._n_hidden == nh and p._temporal_cell.hidden_size == nh and self._propagate._prior._cell.hidden_size == nh,
+             'all recurrent cores must share one width')
+        need(p._glimpse_encoder is d._glimpse_encoder, 'propagation must share discovery\'s glimpse encoder')
+        enc = d._glimpse_encoder
+        need(enc.glimpse_encoder.n_hidden == [nh, nh] and d._input_encoder.n_hidden == [nh, nh], 'encoders must be [nh, nh]')
+        for te in (d._transform_estimator, p._transform_estimator):
+            need(te.n_hidden == [nh, nh], 'transform estimators must be [nh, nh]')
+        for sp in (d._steps_predictor, p._steps_predictor):
+            need(sp.n_hidden == [nh // 2], 'steps predictors must be [nh/2]')
+        dec = self._decoder.glimpse_decoder
+        need(dec.n_hidden == [nh, nh] and tuple(dec.output_size) == self._glimpse_size, 'decoder must be [nh, nh] -> glimpse')
+        need(self._glimpse_size[0] == self._glimpse_size[1], 'square glimpses only')
+        return dict(n_hidden=nh, n_what=d.n_what, masked_glimpse=enc.masked_glimpse,
+                    prior_type=self._propagate._prior.name, prop_prior_step_bias=self._propagate._prior._prop_logit_bias,
+                    disc_prior_type=self._discover._disc_prior_type, rec_where_prior=self._discover._rec_where_prior,
+                    step_success_prob=self._discover._init_disc_step_success_prob,
+                    where_mean=self._discover._where_mean, where_std=self._discover._where_std,
+                    where_update_scale=p._where_update_scale, output_std=self._decoder.output_std,
+                    bg_std=self._decoder.bg_std,
+                    init=dict(output_scale=dec.output_scale, disc_scale_offset=d._transform_estimator.scale_offset,
+                              prop_scale_offset=p._transform_estimator.scale_offset,
+                              disc_step_bias=d._steps_predictor.steps_bias, prop_step_bias=p._steps_predictor.steps_bias,
+                              where_mean=self._discover._where_mean, where_std=self._discover._where_std,
+                              mean_img=self._decoder.mean_img))
+
+    def make_cfg(self, T, B, K, H, W):
+        s = self._spec
+        return _capi.make_cfg(T, B, K, self._max_steps, H, W, self._glimpse_size[0], s['n_what'], s['n_hidden'],
+                              s['prior_type'], s['disc_prior_type'], s['rec_where_prior'], s['masked_glimpse'],
+                              s['step_success_prob'], s['prop_prior_step_bias'], s['output_std'], s['bg_std'],
+                              s['where_update_scale'], 1e-2, s['where_mean'], s['where_std'])
+
+    def param_store(self, H, W, device, seed=42):
+        """Variables depend on the canvas size only; one store per (H, W, device)."""
+        key = (H, W, str(device))
+        if key not in self._stores:
+            self._stores[key] = ParamStore(self.make_cfg(1, 1, 1, H, W), device, seed, self._spec['init'])
+        return self._stores[key]
+
+    # ---- the operator ------------------------------------------------------------------------------
+    def __call__(self, obs, coords=None, sample_from_prior=False, k_particles=1, noise=None, seed=0,
+                 row_offset=0, outputs=None, kernel_events=None):
+        """obs: [T,B,H,W] or [T,B,H,W,1] float32 CUDA tensor.  With k_particles = K > 1 the K particles of a
+        sequence share its frames (virtual `tile_input_for_iwae`); outputs are [T, B*K, ...] as in the reference.
+        `noise` (eps_where / eps_what / u_pres tensors) fixes every random draw; otherwise they are generated
+        on the device from `seed` with rows keyed by `row_offset + row`."""
+        if sample_from_prior:
+            raise NotImplementedError('sample_from_prior')
+        if obs.dim() == 5:
+            if obs.shape[-1] != 1:
+                raise NotImplementedError('multi-channel frames')
+            obs = obs[..., 0]
+        obs = obs.contiguous()
+        T, B, H, W = obs.shape
+        cfg = self.make_cfg(T, B, k_particles, H, W)
+        store = self.param_store(H, W, obs.device)
+        if noise is None:
+            noise = ops.fill_noise(cfg, seed, row_offset, device=obs.device)
+        if kernel_events is not None:
+            kernel_events[0].record()
+        out = ops.forward(cfg, store.packed(), obs, noise, outputs)
+        if kernel_events is not None:
+            kernel_events[1].record()
+        return AttrDict(out)
