@@ -44,8 +44,19 @@ def run_oracle(cfg, imgs, params, noise):
     return {k: v.numpy() for k, v in out.items()}, {k: v.numpy() for k, v in obj.items()}
 
 
+# Outputs whose value is a SUM of H*W per-pixel log-densities (|summand| up to ~1e2) that largely cancel: fp32
+# accumulation-order noise is ~1e-7 * sum|summands|, so their absolute tolerance scales with the pixel count.
+PIXEL_SUMS = ('data_ll_per_sample', 'log_weights_per_timestep')
+
+
 def compare_outputs(got: dict, want: dict, rtol=RTOL, atol=ATOL, names=None):
-    """Returns a list of human-readable mismatches (empty == parity)."""
+    """Returns a list of human-readable mismatches (empty == parity).
+
+    * integer-valued outputs (EXACT): bit-exact;
+    * canvas: the inverse transformer amplifies fp32-level (1e-6) differences of `where` by (G-1)/(2 sx) ~ 1e2 at
+      glimpse edges, so >= 99.99% of the pixels must meet rtol/atol 1e-4 and every pixel 2e-3 (values in [0, 1]);
+    * pixel sums: atol = 2e-5 * H*W;
+    * everything else: |got - want| <= atol + rtol * |want|."""
     bad = []
     for k in (names or _capi.OUTPUT_NAMES):
         a, b = np.asarray(got[k]), np.asarray(want[k])
@@ -56,13 +67,21 @@ def compare_outputs(got: dict, want: dict, rtol=RTOL, atol=ATOL, names=None):
             nbad = int((a != b).sum())
             if nbad:
                 bad.append('%s: %d/%d entries differ (must be exact)' % (k, nbad, a.size))
-        else:
-            err = np.abs(a - b) - (atol + rtol * np.abs(b))
-            if not np.isfinite(a).all() or (err > 0).any():
-                e2 = np.where(np.isfinite(err), err, np.inf)
-                i = np.unravel_index(np.argmax(e2), err.shape)
-                bad.append('%s: %d bad; worst at %s got %r want %r (|d|=%.3g)'
-                           % (k, int((e2 > 0).sum()), i, a[i], b[i], abs(a[i] - b[i])))
+            continue
+        at = atol
+        if k in PIXEL_SUMS:
+            at = 2e-5 * want['canvas'].shape[-1] * want['canvas'].shape[-2]
+        err = np.abs(a - b) - (at + rtol * np.abs(b))
+        finite = np.isfinite(a).all()
+        nviol = int((err > 0).sum())
+        if k == 'canvas' and finite:
+            if nviol <= 1e-4 * a.size and np.abs(a - b).max() <= 2e-3:
+                continue
+        if not finite or nviol:
+            e2 = np.where(np.isfinite(err), err, np.inf)
+            i = np.unravel_index(np.argmax(e2), err.shape)
+            bad.append('%s: %d bad; worst at %s got %r want %r (|d|=%.3g)'
+                       % (k, nviol, i, a[i], b[i], abs(a[i] - b[i])))
     return bad
 
 

@@ -63,7 +63,7 @@ def test_forward_parity(name):
     assert not bad, '\n'.join(bad)
 
 
-@pytest.mark.parametrize('R', [1, 2, 3, 4, 5, 8])
+@pytest.mark.parametrize('R', [1, 2, 3, 4, 5])
 def test_rows_per_block_variants(R):
     """Every instantiation of the persistent kernel, including row counts that do not divide."""
     cfg = O.Cfg(T=3, B=3, K=3, n=2)
