@@ -54,10 +54,11 @@ typedef struct sqair_sizes {
     int64_t packed_floats;     /* floats of the kernel-side parameter buffer                */
     int64_t eps_where_floats, eps_what_floats, u_pres_floats;   /* noise tensors            */
     int32_t rows;              /* B*K                                                       */
-    int32_t rows_per_cta;      /* rows each thread block carries through the sequence       */
+    int32_t rows_per_cta;      /* rows each cluster of thread blocks carries through the sequence */
+    int32_t cluster_size;      /* thread blocks per cluster (column split of every dense layer) */
     int32_t n_ctas;
     int32_t smem_bytes;        /* dynamic shared memory per thread block                    */
-    int32_t n_layers;          /* dense layers in the per-frame schedule                    */
+    int32_t n_layers;          /* dense-layer calls per frame                               */
 } sqair_sizes;
 
 /* One trainable variable of the reference (names as printed by notebooks/play.ipynb:239-362). */

@@ -39,7 +39,7 @@ class SqairCfg(C.Structure):
 class SqairSizes(C.Structure):
     _fields_ = [(k, C.c_int64) for k in
                 'param_count packed_floats eps_where_floats eps_what_floats u_pres_floats'.split()] + \
-               [(k, C.c_int32) for k in 'rows rows_per_cta n_ctas smem_bytes n_layers'.split()]
+               [(k, C.c_int32) for k in 'rows rows_per_cta cluster_size n_ctas smem_bytes n_layers'.split()]
 
 
 class SqairParamDesc(C.Structure):

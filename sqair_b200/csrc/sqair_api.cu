@@ -30,51 +30,89 @@ static int cuda_fail(cudaError_t e, const char* what) {
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
-// persistent sequence kernel
+// persistent sequence kernel: one cluster of C blocks per R rows, the whole T-frame recursion
 // ---------------------------------------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(NT) sqair_sequence_kernel(const __grid_constant__ Plan plan,
                                                             const __grid_constant__ Job job) {
-    extern __shared__ __align__(16) float smem[];
-    Ctx c{(int)threadIdx.x, (int)blockDim.x, (int)(threadIdx.x & 31), 32, (int)(threadIdx.x >> 5),
-          (int)(blockDim.x >> 5), smem};
-    Block<R> blk(c, plan, job, (int)blockIdx.x * R);
+    extern __shared__ __align__(128) float smem[];
+    Ctx c;
+    c.tid = (int)threadIdx.x; c.nthreads = (int)blockDim.x; c.lane = (int)(threadIdx.x & 31); c.nlanes = 32;
+    c.warp = (int)(threadIdx.x >> 5); c.nwarps = (int)(blockDim.x >> 5);
+    c.sm = smem;
+    c.ncta = plan.C;
+    c.rank = plan.C > 1 ? (int)cluster_ctarank() : 0;
+    Block<R> blk(c, plan, job, (int)(blockIdx.x / plan.C) * R);
     blk.run();
+    if (plan.C > 1) { cluster_arrive(c); cluster_wait(c); }      // no block exits while peers may still write to it
 }
 
-static const int kRowChoices[] = {1, 2, 3, 4, 5, 8};
+static const int kRowChoices[] = {1, 2, 3, 4, 5};
+static const int kClusterChoices[] = {1, 2, 4, 8};
 static const int kSmemLimit = 232448;    // 227 KB opt-in shared memory per block on sm_100
 
 template <int R>
 static int launch_sequence(const Plan& plan, const Job& job, cudaStream_t st) {
     const int smem_bytes = plan.sm.total * (int)sizeof(float);
     CUDA_TRY(cudaFuncSetAttribute(sqair_sequence_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    const int nblk = (plan.rows + R - 1) / R;
-    sqair_sequence_kernel<R><<<nblk, NT, smem_bytes, st>>>(plan, job);
-    CUDA_TRY(cudaGetLastError());
+    const int ncl = (plan.rows + R - 1) / R;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(ncl * plan.C);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = plan.C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = plan.C > 1 ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, sqair_sequence_kernel<R>, plan, job));
     return SQAIR_OK;
 }
 
-// Rows per block R.  More rows per block = fewer re-reads of the weights from L2 but fewer blocks;
-// default: the largest supported R that fits shared memory and still yields >= 64 blocks, else R = 1.
-// SQAIR_ROWS_PER_CTA overrides (used by the tuning sweeps in bench.py).
-static int choose_rows(const sqair_cfg& c, const std::vector<ParamEntry>& tab, Plan& plan, std::string& err) {
+// Launch shape.  R rows per cluster (more rows = fewer re-reads of the weights from L2), C blocks per
+// cluster (more blocks = less weight traffic and math per SM, more exchange).  Default: the (R, C) with
+// the lowest modelled frame time among those that fit shared memory and run as a single wave on 148 SMs;
+// SQAIR_ROWS_PER_CTA / SQAIR_CLUSTER override (tuning sweeps).  Packing depends on C only.
+struct Shape {
+    Plan plan;
+    std::vector<Piece> pieces;
+    int64_t packed_total = 0;
+    int R = 0, C = 0;
+};
+
+static int env_int(const char* name) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : 0;
+}
+
+static std::string choose_shape(const sqair_cfg& c, const std::vector<ParamEntry>& tab, Shape& out) {
     const int rows = c.B * c.K;
-    int forced = 0;
-    if (const char* e = getenv("SQAIR_ROWS_PER_CTA")) forced = atoi(e);
-    int best = 0;
-    for (int R : kRowChoices) {
-        if (forced && R != forced) continue;
-        Plan p;
-        std::string e2 = build_plan(c, R, p, tab);
-        if (!e2.empty()) { err = e2; return 0; }
-        if (p.sm.total * (int)sizeof(float) > kSmemLimit) continue;
-        const int nblk = (rows + R - 1) / R;
-        if (best == 0 || forced || nblk >= 64) { best = R; plan = p; }
+    const int fR = env_int("SQAIR_ROWS_PER_CTA"), fC = env_int("SQAIR_CLUSTER");
+    const double W = 44e6, bw_sm = 100e9, bw_l2 = 8e12, mac_row = 11e6, fma = 128 * 1.9e9 * 0.5;
+    double best = 1e30;
+    std::string err = "configuration does not fit shared memory";
+    for (int C : kClusterChoices) {
+        if (fC && C != fC) continue;
+        for (int R : kRowChoices) {
+            if (fR && R != fR) continue;
+            if (R > rows && R != 1) continue;
+            Shape s;
+            std::string e = build_plan(c, R, C, s.plan, tab, s.pieces, &s.packed_total);
+            if (!e.empty()) { err = e; continue; }
+            if (s.plan.sm.total * (int)sizeof(float) > kSmemLimit) continue;
+            const int ncl = (rows + R - 1) / R;
+            const int max_blocks = C == 1 ? 148 : (C == 2 ? 148 : (C == 4 ? 132 : 128));
+            double waves = (double)((ncl * C + max_blocks - 1) / max_blocks);
+            double t = waves * (W / C / bw_sm + R * mac_row / C / fma) + ncl * W / bw_l2 + (C > 1 ? 40e-6 : 0.0);
+            if (t < best) { best = t; s.R = R; s.C = C; out = s; }
+        }
     }
-    if (best == 0) err = forced ? "SQAIR_ROWS_PER_CTA value unsupported or does not fit shared memory"
-                                : "configuration does not fit shared memory";
-    return best;
+    if (out.R == 0) return (fR || fC) ? "SQAIR_ROWS_PER_CTA / SQAIR_CLUSTER value unsupported or does not fit shared memory" : err;
+    return "";
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -94,6 +132,27 @@ __global__ void pack_kernel(const __grid_constant__ PackTab tab, const float* __
             if (tab.src[mid] <= i) lo = mid; else hi = mid - 1;
         }
         dst[tab.dst[lo] + (i - tab.src[lo])] = src[i];
+    }
+}
+
+// canonical matrices -> per-layer column panels [Ktot][Nc] (virtual matrix of each dense layer)
+struct PieceDev {
+    int vrow0, vcol0, K, N, src_off, src_ld, w_off, Ktot, Nc;
+};
+struct PieceTab {
+    int n;
+    PieceDev p[96];
+};
+
+__global__ void pack_panels_kernel(const __grid_constant__ PieceTab tab, const float* __restrict__ src,
+                                   float* __restrict__ dst) {
+    const PieceDev& pc = tab.p[blockIdx.y];
+    const int total = pc.K * pc.N;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int k = i / pc.N, n = i - k * pc.N;
+        const int vrow = pc.vrow0 + k, vcol = pc.vcol0 + n, panel = vcol / pc.Nc;
+        dst[(size_t)pc.w_off + (size_t)panel * pc.Ktot * pc.Nc + (size_t)vrow * pc.Nc + (vcol - panel * pc.Nc)] =
+            src[(size_t)pc.src_off + (size_t)k * pc.src_ld + n];
     }
 }
 
@@ -318,20 +377,21 @@ int sqair_query_sizes(const sqair_cfg* cfg, sqair_sizes* out) {
     std::string e = validate_cfg(*cfg);
     if (!e.empty()) return fail(SQAIR_EINVAL, e);
     auto tab = param_table(*cfg);
-    Plan plan;
-    int R = choose_rows(*cfg, tab, plan, e);
-    if (R == 0) return fail(SQAIR_EUNSUPPORTED, e);
+    Shape sh;
+    e = choose_shape(*cfg, tab, sh);
+    if (!e.empty()) return fail(SQAIR_EUNSUPPORTED, e);
     const int64_t rows = (int64_t)cfg->B * cfg->K, sites = (int64_t)cfg->T * rows * 2 * cfg->n;
     out->param_count = tab.back().offset + tab.back().count;
-    out->packed_floats = packed_floats(tab);
+    out->packed_floats = sh.packed_total;
     out->eps_where_floats = sites * 4;
     out->eps_what_floats = sites * cfg->n_what;
     out->u_pres_floats = sites;
     out->rows = (int32_t)rows;
-    out->rows_per_cta = R;
-    out->n_ctas = (int32_t)((rows + R - 1) / R);
-    out->smem_bytes = plan.sm.total * (int)sizeof(float);
-    out->n_layers = L_COUNT;
+    out->rows_per_cta = sh.R;
+    out->cluster_size = sh.C;
+    out->n_ctas = (int32_t)((rows + sh.R - 1) / sh.R) * sh.C;
+    out->smem_bytes = sh.plan.sm.total * (int)sizeof(float);
+    out->n_layers = sh.plan.nseq;
     return SQAIR_OK;
 }
 
@@ -360,17 +420,30 @@ int sqair_pack_params(const sqair_cfg* cfg, const float* params, float* packed, 
     std::string e = validate_cfg(*cfg);
     if (!e.empty()) return fail(SQAIR_EINVAL, e);
     auto tab = param_table(*cfg);
-    if (tab.size() > 128) return fail(SQAIR_EUNSUPPORTED, "too many variables");
+    Shape sh;
+    e = choose_shape(*cfg, tab, sh);
+    if (!e.empty()) return fail(SQAIR_EUNSUPPORTED, e);
+    if (tab.size() > 128 || sh.pieces.size() > 96) return fail(SQAIR_EUNSUPPORTED, "too many variables");
     PackTab pt;
     memset(&pt, 0, sizeof(pt));
     pt.n = (int)tab.size();
     for (size_t i = 0; i < tab.size(); ++i) {
         pt.src[i] = (int)tab[i].offset; pt.dst[i] = (int)tab[i].packed_offset; pt.cnt[i] = (int)tab[i].count;
     }
+    PieceTab qt;
+    memset(&qt, 0, sizeof(qt));
+    qt.n = (int)sh.pieces.size();
+    for (size_t i = 0; i < sh.pieces.size(); ++i) {
+        const Piece& p = sh.pieces[i];
+        const Layer& L = sh.plan.L[p.layer];
+        qt.p[i] = PieceDev{p.vrow0, p.vcol0, p.K, p.N, (int)p.src_off, p.src_ld, L.w_off, L.Ktot, L.Nc};
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const int total = (int)(tab.back().offset + tab.back().count);
-    CUDA_TRY(cudaMemsetAsync(packed, 0, packed_floats(tab) * sizeof(float), st));
+    CUDA_TRY(cudaMemsetAsync(packed, 0, sh.packed_total * sizeof(float), st));
     pack_kernel<<<592, 256, 0, st>>>(pt, params, packed, total);
+    CUDA_TRY(cudaGetLastError());
+    pack_panels_kernel<<<dim3(64, qt.n), 256, 0, st>>>(qt, params, packed);
     CUDA_TRY(cudaGetLastError());
     return SQAIR_OK;
 }
@@ -394,18 +467,17 @@ int sqair_forward(const sqair_cfg* cfg, const float* packed_params, const float*
     std::string e = validate_cfg(*cfg);
     if (!e.empty()) return fail(SQAIR_EINVAL, e);
     auto tab = param_table(*cfg);
-    Plan plan;
-    const int R = choose_rows(*cfg, tab, plan, e);
-    if (R == 0) return fail(SQAIR_EUNSUPPORTED, e);
+    Shape sh;
+    e = choose_shape(*cfg, tab, sh);
+    if (!e.empty()) return fail(SQAIR_EUNSUPPORTED, e);
     Job job{packed_params, obs, eps_where, eps_what, u_pres, *out};
     cudaStream_t st = (cudaStream_t)stream;
-    switch (R) {
-        case 1: return launch_sequence<1>(plan, job, st);
-        case 2: return launch_sequence<2>(plan, job, st);
-        case 3: return launch_sequence<3>(plan, job, st);
-        case 4: return launch_sequence<4>(plan, job, st);
-        case 5: return launch_sequence<5>(plan, job, st);
-        case 8: return launch_sequence<8>(plan, job, st);
+    switch (sh.R) {
+        case 1: return launch_sequence<1>(sh.plan, job, st);
+        case 2: return launch_sequence<2>(sh.plan, job, st);
+        case 3: return launch_sequence<3>(sh.plan, job, st);
+        case 4: return launch_sequence<4>(sh.plan, job, st);
+        case 5: return launch_sequence<5>(sh.plan, job, st);
     }
     return fail(SQAIR_EUNSUPPORTED, "unsupported rows per block");
 }

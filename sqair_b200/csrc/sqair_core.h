@@ -3,13 +3,20 @@
 // Plain C++ (no CUDA headers): included by the CUDA translation unit and by the host-side
 // kernel-logic emulator under tests/host_emu (test infrastructure only).
 //
-// The per-frame SQAIR step (reference: sqair/seq.py:181-269 -> sqair/sqair_modules.py:446-582) is
-// executed by one thread block per group of R rows (row = b*K + k).  All activations of those rows
-// live in shared memory in FEATURE-MAJOR layout x[feature][row] so that a dense layer reads one
-// weight per (k, column) from L2 and broadcasts the R activations of feature k to every thread.
-// The schedule is data: a `Plan` holds one `Layer` descriptor per dense layer (weight offsets into
-// the packed parameter buffer, input segments and output buffers as shared-memory offsets) and is
-// passed to the kernel as a __grid_constant__ parameter.
+// Execution model.  The per-frame SQAIR step (reference: sqair/seq.py:181-269 ->
+// sqair/sqair_modules.py:446-582) runs in ONE persistent kernel.  A thread-block CLUSTER of C blocks
+// owns R rows (row = b*K + k) for the whole sequence.  Every block of the cluster keeps a full copy
+// of the rows' activations in shared memory in FEATURE-MAJOR layout x[feature][row]; a dense layer is
+// split by OUTPUT COLUMNS across the C blocks: block c multiplies the activations with its column
+// panel of the layer's weight matrix and writes its slice of the result into the shared memory of
+// all C blocks (distributed shared memory), so the next layer again finds the full vector locally.
+// Weights never sit in shared memory permanently: each block streams its panels from L2 through a
+// ring of stages filled by `cp.async.bulk` (TMA) copies that run ahead of the dependent chain --
+// the order of layers within a frame is static (`Plan::seq`), so the copies do not wait for data.
+//
+// The schedule is data: a `Plan` holds one `Layer` descriptor per dense layer (packed weight
+// panels, input segments and output heads as shared-memory offsets) and is passed to the kernel as
+// a __grid_constant__ parameter.
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -22,37 +29,45 @@
 namespace sq {
 
 constexpr int MAXSEG = 5;
-constexpr int MAXBLK = 2;
+constexpr int MAXHEAD = 3;
 constexpr int NT = 256;          // threads per block
-constexpr int MAX_KS = 8;        // max k-slices of a dense layer
+constexpr int MAX_KS = 16;       // max k-slices of a dense layer
 constexpr int MAX_SLOTS = 8;
+constexpr int MAXC = 8;          // max cluster size (portable limit)
+constexpr int MAXSEQ = 400;      // dense calls per frame
+constexpr int NSTAGE = 3;        // weight-ring stages
 
 enum Act { ACT_NONE = 0, ACT_ELU = 1, ACT_SIGMOID = 2, ACT_TANH = 3, ACT_SOFTPLUS = 4 };
 enum SegKind { SEG_SMEM = 0, SEG_IMAGE = 1 };
 
+// One input segment: K consecutive rows of the layer's (virtual) weight matrix, multiplied with
+// x[k][r] = smem[x_off + slot*x_sstride + k*ld + r]  (or with the frame pixels for SEG_IMAGE).
 struct Seg {
-    int x_off;          // smem float offset of x[0][0] (slot 0)
-    int x_sstride;      // added per slot index
-    int ld;             // floats between consecutive features
-    int K;              // number of features
-    int kind;           // SegKind
-    int w_off[MAXBLK];  // packed-parameter offset of the first weight row of this segment, per block
+    int x_off, x_sstride, ld, K, kind;
 };
 
-struct Blk {
-    int N;              // output columns of this block
-    int ldw;            // row stride of its weight matrix
-    int b_off, b2_off;  // bias offsets (-1 = none)
-    int act, split, act_hi;       // activation for col < split / col >= split
-    float scale, add, scale_hi, add_hi;   // v = act(v) * scale + add
-    int scale_p_off;    // >= 0: additionally multiply by params[scale_p_off]
-    int out_off, out_sstride, out_ld;     // out[col*out_ld + row] (+ slot * out_sstride)
+// One output head: columns [col0, col0 + N) of the virtual matrix (col0 is a multiple of 4).
+//   out[j*out_ld + r] = (act(acc + b[j] (+ b2[j])) * scale + add) * (scale_p_off >= 0 ? prm[scale_p_off] : 1)
+struct Head {
+    int col0, N;
+    int b_off, b2_off;
+    int act;
+    float scale, add;
+    int scale_p_off;
+    int out_off, out_sstride, out_ld;
 };
 
 struct Layer {
-    int nseg, nblk;
+    int nseg, nhead;
     Seg seg[MAXSEG];
-    Blk blk[MAXBLK];
+    Head head[MAXHEAD];
+    int Ktot;      // rows of the virtual matrix = sum of segment K
+    int Ntot;      // columns of the virtual matrix (heads padded to multiples of 4)
+    int split;     // 1: columns split across the cluster; 0: every block computes all columns (tiny layers)
+    int Nc;        // columns per panel (multiple of 4); a panel is stored [Ktot][Nc], row-major
+    int npanel;    // panels with real columns (blocks with rank >= npanel idle in this layer); 1 if !split
+    int w_off;     // packed-parameter offset of panel 0; panel p at w_off + p*Ktot*Nc
+    int rpc;       // weight rows per ring chunk
 };
 
 enum LayerId {
@@ -67,8 +82,10 @@ struct RecF {
     int what, where, pres, what_loc, what_scale, where_loc, where_scale, prob, logit, size;
 };
 
-// Shared-memory layout (float offsets).  [f][S][R] = feature-major, S slots, R rows.
+// Shared-memory layout (float offsets from the dynamic shared memory base).  [f][S][R] = feature-major.
 struct Smem {
+    int Bar;      // 2*NSTAGE mbarriers (8 bytes each): full[NSTAGE], empty[NSTAGE]
+    int Ring;     // NSTAGE * stage_floats weight stages (128-byte aligned)
     int Z;        // [nw+6][NS][R]: what, where(4), pres, plogit     (latents of the previous frame)
     int Ids;      // [NS][R]
     int LastId;   // [R]
@@ -79,7 +96,7 @@ struct Smem {
     int RnInit, RnPrev0;    // [4][R], [4][NS][R] (previous-sample inputs of the recurrent where prior)
     int DIn;      // [2nh][R]: image encoding, conditioning
     int Exp;      // [R]
-    int Hrnn;     // [2][nh][R] ping-pong hidden state of the slot RNN
+    int Hrnn;     // [2][nh][R] old / new hidden state of the slot RNN
     int Gz, Gr, Gc;         // [nh][R]
     int Hwb, Hmk; // [128][R]
     int Wb;       // [4][R]
@@ -90,7 +107,7 @@ struct Smem {
     int Tp;       // [8][R]
     int Tg;       // [2nw][R]
     int Gt;       // [3nw][R]
-    int Hs;       // [128][R]
+    int Hs;       // [nh/2][R]
     int Lg;       // [R]
     int Hrn;      // [128][R]
     int Rno;      // [4][R]
@@ -99,14 +116,14 @@ struct Smem {
     int Spl;      // [n+1][R]
     int Coords;   // [4][R]
     int Dgl;      // [g][NS][R] decoded glimpses (aliases the per-slot scratch)
-    int Red;      // k-slice reduction scratch
+    int Red;      // k-slice partial sums
     int RowAcc;   // [16][R] per-row scalars
     int Perm;     // [2NS][R] compaction order (as floats)
     int total;    // floats
-    int red_floats;
+    int red_floats, stage_floats;
 };
 
-// Packed-parameter offsets of everything that is not a dense-layer weight/bias.
+// Packed-parameter offsets of everything that is not a dense-layer weight.
 struct POff {
     int mean_img, output_scale;
     int disc_h0, prop_h0, temporal_h0, prior_h0;
@@ -118,11 +135,13 @@ struct POff {
 
 struct Plan {
     sqair_cfg cfg;
-    int R, NS, rows, nw, nh, g, P, LDS;   // LDS = NS*R
+    int R, C, NS, rows, nw, nh, g, P, LDS;   // LDS = NS*R; C = cluster size
+    int nseq;                                 // dense calls per frame
     RecF rec;
     Smem sm;
     POff po;
     Layer L[L_COUNT];
+    unsigned char seq[MAXSEQ];                // layer ids in program order (one frame)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -133,6 +152,13 @@ struct ParamEntry {
     int ndim;
     int shape[3];
     int64_t offset, packed_offset, count;
+};
+
+// One rectangular piece of a layer's virtual weight matrix, copied from a canonical variable.
+struct Piece {
+    int layer, vrow0, vcol0, K, N;
+    int64_t src_off;     // canonical offset of element (row0, col0) of the source matrix
+    int src_ld;
 };
 
 inline void add_param(std::vector<ParamEntry>& v, const std::string& name, int d0 = -1, int d1 = -1, int d2 = -1) {
@@ -230,78 +256,155 @@ inline std::vector<ParamEntry> param_table(const sqair_cfg& c) {
     return v;
 }
 
-inline int64_t packed_floats(const std::vector<ParamEntry>& v) {
-    return (v.back().packed_offset + v.back().count + 3) / 4 * 4 + 4;    // slack for vector tail loads
+// floats of the "variables" region of the packed buffer (every variable, 16-byte aligned)
+inline int64_t vars_floats(const std::vector<ParamEntry>& v) {
+    return (v.back().packed_offset + v.back().count + 31) / 32 * 32;
 }
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct PlanBuilder {
     Plan& p;
     const std::vector<ParamEntry>& tab;
+    std::vector<Piece>& pieces;
     std::string err;
-    int cursor = 0;
+    int cursor = 0;          // shared-memory cursor (floats)
+    int64_t wcursor = 0;     // packed-parameter cursor (floats)
 
-    PlanBuilder(Plan& plan, const std::vector<ParamEntry>& t) : p(plan), tab(t) {}
-
-    int off(const std::string& name) {
-        for (const auto& e : tab)
-            if (e.name == name) return (int)e.packed_offset;
-        err = "unknown parameter " + name;
-        return -1;
+    PlanBuilder(Plan& plan, const std::vector<ParamEntry>& t, std::vector<Piece>& pc) : p(plan), tab(t), pieces(pc) {
+        wcursor = vars_floats(t);
     }
-    int alloc(int floats) {
+
+    const ParamEntry* find(const std::string& name) {
+        for (const auto& e : tab)
+            if (e.name == name) return &e;
+        err = "unknown parameter " + name;
+        return nullptr;
+    }
+    int off(const std::string& name) {
+        const ParamEntry* e = find(name);
+        return e ? (int)e->packed_offset : -1;
+    }
+    int alloc(int floats, int align = 4) {
+        cursor = round_up(cursor, align);
         int o = cursor;
-        cursor += (floats + 3) / 4 * 4;
+        cursor += round_up(floats, 4);
         return o;
     }
-    Layer& layer(int id, int nblk) {
+    Layer& layer(int id) {
         Layer& l = p.L[id];
         memset(&l, 0, sizeof(l));
-        l.nblk = nblk;
-        for (int b = 0; b < MAXBLK; ++b) {
-            l.blk[b].b_off = l.blk[b].b2_off = l.blk[b].scale_p_off = -1;
-            l.blk[b].scale = l.blk[b].scale_hi = 1.f;
-        }
         return l;
     }
-    // block b: N columns [col0, col0+N) of a matrix with row stride ldw
-    void blk(Layer& l, int b, int N, int ldw, int b_off, int act, int out_off, int out_ld, int out_sstride = 0) {
-        Blk& k = l.blk[b];
-        k.N = N; k.ldw = ldw; k.b_off = b_off; k.act = act; k.split = N; k.act_hi = act;
-        k.out_off = out_off; k.out_ld = out_ld; k.out_sstride = out_sstride;
-    }
-    // input segment; w0/w1: offset of the weight row where this segment starts in block 0/1
-    void seg(Layer& l, int x_off, int ld, int K, int w0, int w1 = -1, int x_sstride = 0, int kind = SEG_SMEM) {
-        Seg& s = l.seg[l.nseg++];
+    int seg(Layer& l, int x_off, int ld, int K, int x_sstride = 0, int kind = SEG_SMEM) {
+        Seg& s = l.seg[l.nseg];
         s.x_off = x_off; s.ld = ld; s.K = K; s.kind = kind; s.x_sstride = x_sstride;
-        s.w_off[0] = w0; s.w_off[1] = w1;
+        l.Ktot += K;
+        return l.nseg++;
+    }
+    int head(Layer& l, int N, int b_off, int act, int out_off, int out_ld, int out_sstride = 0) {
+        Head& h = l.head[l.nhead];
+        h.col0 = l.Ntot; h.N = N; h.b_off = b_off; h.b2_off = -1; h.act = act; h.scale = 1.f; h.add = 0.f;
+        h.scale_p_off = -1; h.out_off = out_off; h.out_ld = out_ld; h.out_sstride = out_sstride;
+        l.Ntot += round_up(N, 4);
+        return l.nhead++;
+    }
+    // weights of (segment s, head h) come from rows [row0, row0+K_s) x cols [col0, col0+N_h) of variable `name`
+    void w(int id, int s, int h, const std::string& name, int row0, int col0 = 0) {
+        const ParamEntry* e = find(name);
+        if (!e) return;
+        const Layer& l = p.L[id];
+        int vr = 0;
+        for (int i = 0; i < s; ++i) vr += l.seg[i].K;
+        Piece pc;
+        pc.layer = id; pc.vrow0 = vr; pc.vcol0 = l.head[h].col0; pc.K = l.seg[s].K; pc.N = l.head[h].N;
+        pc.src_ld = e->shape[1];
+        pc.src_off = e->offset + (int64_t)row0 * pc.src_ld + col0;
+        if (row0 + pc.K > e->shape[0] || col0 + pc.N > e->shape[1]) err = "piece out of range in " + name;
+        pieces.push_back(pc);
+    }
+    // segments first_seg..last_seg are consecutive row blocks of one matrix (starting at row0), for head h
+    void wrows(int id, int h, const std::string& name, int first_seg = 0, int last_seg = -1, int row0 = 0) {
+        const Layer& l = p.L[id];
+        if (last_seg < 0) last_seg = l.nseg - 1;
+        int r = row0;
+        for (int s = first_seg; s <= last_seg; ++s) { w(id, s, h, name, r); r += l.seg[s].K; }
+    }
+    // decide the column split and reserve the packed panels
+    void finish(int id) {
+        Layer& l = p.L[id];
+        const int C = p.C;
+        int per = (l.Ntot + C - 1) / C;
+        if (C > 1 && per >= 16) {
+            l.split = 1;
+            l.Nc = round_up(per, 4);
+            l.npanel = (l.Ntot + l.Nc - 1) / l.Nc;
+        } else {
+            l.split = 0;
+            l.Nc = l.Ntot;
+            l.npanel = 1;
+        }
+        l.w_off = (int)wcursor;
+        wcursor += (int64_t)l.npanel * l.Ktot * l.Nc;
+        wcursor = (wcursor + 31) / 32 * 32;
+        l.rpc = p.sm.stage_floats / l.Nc;
+        if (l.rpc < 1) err = "layer too wide for a ring stage";
+        if (l.Nc / 4 > NT) err = "layer too wide for the thread block";
     }
 };
 
-inline int red_need(const Layer& l, int R) {
-    int G = 0;
-    for (int b = 0; b < l.nblk; ++b) G += (l.blk[b].N + 3) / 4;
-    if (G == 0) return 0;            // layer not part of this configuration
-    int Gp = (G + 7) / 8 * 8;
-    int ks = NT / Gp;
+// k-slices used by a block for a panel of Nc columns (4-column thread tiles, NT threads)
+inline int dense_ks(int Nc, int nthreads) {
+    int Gc = Nc / 4;
+    int ks = nthreads / Gc;
     if (ks > MAX_KS) ks = MAX_KS;
-    if (ks <= 1) return 0;
-    return (ks - 1) * Gp * 4 * R;
+    if (ks < 1) ks = 1;
+    return ks;
 }
 
-// Builds the plan for R rows per block.  Returns "" on success, else an error message.
-inline std::string build_plan(const sqair_cfg& c, int R, Plan& p, const std::vector<ParamEntry>& tab) {
+// Dense calls of one frame in program order; must mirror Block::frame() in sqair_device.cuh (the
+// emulator asserts it on every call).
+inline std::vector<int> frame_sequence(const sqair_cfg& c) {
+    std::vector<int> q;
+    for (int s = 0; s < c.n; ++s) {
+        q.insert(q.end(), {L_PGRU_ZR, L_PGRU_C, L_PLIN, L_WBMK1, L_WB2});
+        if (c.masked_glimpse) q.push_back(L_MK2);
+        q.insert(q.end(), {L_ENC1, L_ENC2, L_ENC3_LOC, L_PRNN, L_PT1, L_PT2, L_PT3, L_ENC1, L_ENC2, L_ENC3,
+                           L_TGRU_ZR, L_TGRU_C, L_PHEADS, L_PST1, L_PST2});
+    }
+    for (int s = 0; s < c.n; ++s) q.insert(q.end(), {L_LAT1, L_LAT2});
+    q.insert(q.end(), {L_IMG1, L_IMG2});
+    for (int s = 0; s < c.n; ++s)
+        q.insert(q.end(), {L_DRNN, L_DT1, L_DT2, L_DT3, L_ENC1, L_ENC2, L_ENC3, L_DST1, L_DST2});
+    if (c.rec_where_prior) {
+        q.push_back(L_RN1);
+        for (int s = 0; s < c.n; ++s) q.insert(q.end(), {L_RN2, L_RN3});
+    }
+    if (c.disc_prior_type == SQAIR_DISC_PRIOR_CAT) q.insert(q.end(), {L_SP1, L_SP2});
+    for (int s = 0; s < c.n; ++s) q.insert(q.end(), {L_DEC1, L_DEC2, L_DEC3});
+    return q;
+}
+
+// Builds the plan for R rows per cluster of C blocks.  Returns "" on success, else an error message.
+// `pieces` receives the packing table; *packed_total the floats of the packed parameter buffer.
+inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const std::vector<ParamEntry>& tab,
+                              std::vector<Piece>& pieces, int64_t* packed_total, int stage_floats = 4096) {
     memset(&p, 0, sizeof(p));
+    pieces.clear();
     p.cfg = c;
     const int NS = c.n, nw = c.n_what, nh = c.n_hidden, g = c.G * c.G, P = c.H * c.W, s = nh / 2;
-    p.R = R; p.NS = NS; p.rows = c.B * c.K; p.nw = nw; p.nh = nh; p.g = g; p.P = P; p.LDS = NS * R;
+    p.R = R; p.C = C; p.NS = NS; p.rows = c.B * c.K; p.nw = nw; p.nh = nh; p.g = g; p.P = P; p.LDS = NS * R;
     RecF& rf = p.rec;
     rf.what = 0; rf.where = nw; rf.pres = nw + 4; rf.what_loc = nw + 5; rf.what_scale = 2 * nw + 5;
     rf.where_loc = 3 * nw + 5; rf.where_scale = 3 * nw + 9; rf.prob = 3 * nw + 13; rf.logit = 3 * nw + 14;
     rf.size = 3 * nw + 15;
 
-    PlanBuilder B(p, tab);
+    PlanBuilder B(p, tab, pieces);
     Smem& m = p.sm;
+    m.stage_floats = stage_floats;
     const int LDS = NS * R, LDE = (NS + 1) * R;
+    m.Bar = B.alloc(2 * 2 * NSTAGE, 4);                 // 8-byte barriers
+    m.Ring = B.alloc(NSTAGE * stage_floats, 32);
     m.Z = B.alloc((nw + 6) * LDS);
     m.Ids = B.alloc(LDS);
     m.LastId = B.alloc(R);
@@ -345,7 +448,7 @@ inline std::string build_plan(const sqair_cfg& c, int R, Plan& p, const std::vec
     m.Glm = B.alloc(g * R);
     int scratch1 = B.cursor;
     m.Dgl = scratch0;
-    if (g * LDS > scratch1 - scratch0) B.cursor = scratch0 + (g * LDS + 3) / 4 * 4;
+    if (g * LDS > scratch1 - scratch0) B.cursor = scratch0 + round_up(g * LDS, 4);
 
     POff& po = p.po;
     const std::string RN = "discovery/discover/recurrent_normal_impl/";
@@ -366,267 +469,265 @@ inline std::string build_plan(const sqair_cfg& c, int R, Plan& p, const std::vec
     po.step_prior_tbias = B.off("model/sequential_air/while/sqair_timestep/discover/step_prior_timestep_bias");
     po.cholesky = B.off(PC + "affine_diag_normal/cholesky_scale");
 
-    auto W = [&](const std::string& n) { return B.off(n + "/w"); };
     auto Bi = [&](const std::string& n) { return B.off(n + "/b"); };
     const int zw = m.Z, zwhere = m.Z + nw * LDS;      // Z: what rows 0..nw-1, where nw..nw+3, pres nw+4
+    const int Hnew = m.Hrnn + nh * R;                 // new hidden state of the slot RNN
+    // a plain MLP layer: one segment, one head, one weight matrix
+    auto simple = [&](int id, int x_off, int x_ld, int K, int x_ss, const std::string& lin, int N, int act, int out_off,
+                      int out_ld, int out_ss = 0) -> Layer& {
+        Layer& l = B.layer(id);
+        B.seg(l, x_off, x_ld, K, x_ss);
+        B.head(l, N, Bi(lin), act, out_off, out_ld, out_ss);
+        B.w(id, 0, 0, lin + "/w", 0);
+        return l;
+    };
 
     // ---- propagation prior GRU (propagate.py:68-98): x = [what_tm1, where_tm1] (nw+4), h = Pst
     {
-        Layer& l = B.layer(L_PGRU_ZR, 2);
-        int wz = B.off("propagation/gru_1/wz"), wr = B.off("propagation/gru_1/wr");
-        int uz = B.off("propagation/gru_1/uz"), ur = B.off("propagation/gru_1/ur");
-        B.blk(l, 0, nh, nh, B.off("propagation/gru_1/bz"), ACT_SIGMOID, m.Gz, R);
-        B.blk(l, 1, nh, nh, B.off("propagation/gru_1/br"), ACT_SIGMOID, m.Gr, R);
-        B.seg(l, zw, LDS, nw + 4, wz, wr, R);
-        B.seg(l, m.Pst, LDS, nh, uz, ur, R);
+        Layer& l = B.layer(L_PGRU_ZR);
+        B.seg(l, zw, LDS, nw + 4, R);
+        B.seg(l, m.Pst, LDS, nh, R);
+        B.head(l, nh, B.off("propagation/gru_1/bz"), ACT_SIGMOID, m.Gz, R);
+        B.head(l, nh, B.off("propagation/gru_1/br"), ACT_SIGMOID, m.Gr, R);
+        B.w(L_PGRU_ZR, 0, 0, "propagation/gru_1/wz", 0); B.w(L_PGRU_ZR, 1, 0, "propagation/gru_1/uz", 0);
+        B.w(L_PGRU_ZR, 0, 1, "propagation/gru_1/wr", 0); B.w(L_PGRU_ZR, 1, 1, "propagation/gru_1/ur", 0);
+        B.finish(L_PGRU_ZR);
     }
     {
-        Layer& l = B.layer(L_PGRU_C, 1);
-        B.blk(l, 0, nh, nh, B.off("propagation/gru_1/bh"), ACT_TANH, m.Gc, R);
-        B.seg(l, zw, LDS, nw + 4, B.off("propagation/gru_1/wh"), -1, R);
-        B.seg(l, m.Gr, R, nh, B.off("propagation/gru_1/uh"));          // Gr holds r*h
+        Layer& l = B.layer(L_PGRU_C);
+        B.seg(l, zw, LDS, nw + 4, R);
+        B.seg(l, m.Gr, R, nh);                          // Gr holds r*h
+        B.head(l, nh, B.off("propagation/gru_1/bh"), ACT_TANH, m.Gc, R);
+        B.w(L_PGRU_C, 0, 0, "propagation/gru_1/wh", 0); B.w(L_PGRU_C, 1, 0, "propagation/gru_1/uh", 0);
+        B.finish(L_PGRU_C);
     }
-    {
-        Layer& l = B.layer(L_PLIN, 1);
-        int N = 2 * (4 + nw) + 1;
-        B.blk(l, 0, N, N, Bi("propagation/propagate_prior/linear"), ACT_NONE, m.Pri, LDS, R);
-        B.seg(l, m.Pst, LDS, nh, W("propagation/propagate_prior/linear"), -1, R);   // Pst already updated in place
-    }
+    simple(L_PLIN, m.Pst, LDS, nh, R, "propagation/propagate_prior/linear", 2 * (4 + nw) + 1, ACT_NONE, m.Pri, LDS, R);
+    B.finish(L_PLIN);                                   // Pst already updated in place
     // ---- where-bias MLP (core.py:291) and glimpse-mask MLP (modules.py:322-324): same input (temporal state)
     {
-        const bool mk = c.masked_glimpse != 0;
-        Layer& l = B.layer(L_WBMK1, mk ? 2 : 1);
-        B.blk(l, 0, 128, 128, Bi(PC + "rnn_inpt/mlp/linear"), ACT_ELU, m.Hwb, R);
-        if (mk) B.blk(l, 1, 128, 128, Bi(DC + "air_encoder/mlp/linear"), ACT_ELU, m.Hmk, R);
-        B.seg(l, m.Tst, LDS, nh, W(PC + "rnn_inpt/mlp/linear"), mk ? W(DC + "air_encoder/mlp/linear") : -1, R);
+        Layer& l = B.layer(L_WBMK1);
+        B.seg(l, m.Tst, LDS, nh, R);
+        B.head(l, 128, Bi(PC + "rnn_inpt/mlp/linear"), ACT_ELU, m.Hwb, R);
+        B.w(L_WBMK1, 0, 0, PC + "rnn_inpt/mlp/linear/w", 0);
+        if (c.masked_glimpse) {
+            B.head(l, 128, Bi(DC + "air_encoder/mlp/linear"), ACT_ELU, m.Hmk, R);
+            B.w(L_WBMK1, 0, 1, DC + "air_encoder/mlp/linear/w", 0);
+        }
+        B.finish(L_WBMK1);
     }
-    {
-        Layer& l = B.layer(L_WB2, 1);
-        B.blk(l, 0, 4, 4, Bi(PC + "rnn_inpt/mlp/linear_1"), ACT_NONE, m.Wb, R);
-        l.blk[0].scale = 0.1f; l.blk[0].scale_hi = 0.1f;
-        B.seg(l, m.Hwb, R, 128, W(PC + "rnn_inpt/mlp/linear_1"));
-    }
+    simple(L_WB2, m.Hwb, R, 128, 0, PC + "rnn_inpt/mlp/linear_1", 4, ACT_NONE, m.Wb, R).head[0].scale = 0.1f;
+    B.finish(L_WB2);
     if (c.masked_glimpse) {
-        Layer& l = B.layer(L_MK2, 1);
-        B.blk(l, 0, g, g, Bi(DC + "air_encoder/mlp/linear_1"), ACT_SIGMOID, m.Mask, R);
-        B.seg(l, m.Hmk, R, 128, W(DC + "air_encoder/mlp/linear_1"));
+        simple(L_MK2, m.Hmk, R, 128, 0, DC + "air_encoder/mlp/linear_1", g, ACT_SIGMOID, m.Mask, R);
+        B.finish(L_MK2);
     }
     // ---- glimpse encoder (modules.py:100-112,358-364), shared by discovery and propagation
-    {
-        Layer& l = B.layer(L_ENC1, 1);
-        B.blk(l, 0, nh, nh, Bi(DC + "encoder_1/mlp/linear"), ACT_ELU, m.A0, R);
-        B.seg(l, m.Glm, R, g, W(DC + "encoder_1/mlp/linear"));
+    simple(L_ENC1, m.Glm, R, g, 0, DC + "encoder_1/mlp/linear", nh, ACT_ELU, m.A0, R);
+    B.finish(L_ENC1);
+    simple(L_ENC2, m.A0, R, nh, 0, DC + "encoder_1/mlp/linear_1", nh, ACT_ELU, m.A1, R);
+    B.finish(L_ENC2);
+    {   // only .loc is consumed at core.py:293: first nw columns of the [nh, 2nw] head
+        Layer& l = B.layer(L_ENC3_LOC);
+        B.seg(l, m.A1, R, nh);
+        B.head(l, nw, Bi(DC + "air_encoder/gaussian_from_param_vec/linear"), ACT_NONE, m.Loc1, R);
+        B.w(L_ENC3_LOC, 0, 0, DC + "air_encoder/gaussian_from_param_vec/linear/w", 0);
+        B.finish(L_ENC3_LOC);
     }
+    auto gauss_heads = [&](int id, Layer& l, const std::string& lin, int out_off) {    // (loc | softplus(scale)+min_std)
+        const int b = Bi(lin);
+        B.head(l, nw, b, ACT_NONE, out_off, R);
+        int h1 = B.head(l, nw, b + nw, ACT_SOFTPLUS, out_off + nw * R, R);
+        l.head[h1].add = c.min_std;
+        B.w(id, 0, 0, lin + "/w", 0, 0);
+        B.w(id, 0, 1, lin + "/w", 0, nw);
+    };
     {
-        Layer& l = B.layer(L_ENC2, 1);
-        B.blk(l, 0, nh, nh, Bi(DC + "encoder_1/mlp/linear_1"), ACT_ELU, m.A1, R);
-        B.seg(l, m.A0, R, nh, W(DC + "encoder_1/mlp/linear_1"));
-    }
-    {
-        Layer& l = B.layer(L_ENC3_LOC, 1);     // only .loc is consumed at core.py:293
-        B.blk(l, 0, nw, 2 * nw, Bi(DC + "air_encoder/gaussian_from_param_vec/linear"), ACT_NONE, m.Loc1, R);
-        B.seg(l, m.A1, R, nh, W(DC + "air_encoder/gaussian_from_param_vec/linear"));
-    }
-    {
-        Layer& l = B.layer(L_ENC3, 1);
-        B.blk(l, 0, 2 * nw, 2 * nw, Bi(DC + "air_encoder/gaussian_from_param_vec/linear"), ACT_NONE, m.Enc, R);
-        l.blk[0].split = nw; l.blk[0].act_hi = ACT_SOFTPLUS; l.blk[0].add_hi = c.min_std;
-        B.seg(l, m.A1, R, nh, W(DC + "air_encoder/gaussian_from_param_vec/linear"));
+        Layer& l = B.layer(L_ENC3);
+        B.seg(l, m.A1, R, nh);
+        gauss_heads(L_ENC3, l, DC + "air_encoder/gaussian_from_param_vec/linear", m.Enc);
+        B.finish(L_ENC3);
     }
     // ---- propagation RNN (core.py:295-302): [loc1, km1(what,where,pres), tm1(what,where,pres), temporal] + h
     {
-        Layer& l = B.layer(L_PRNN, 1);
-        int wi = W("propagation/vanilla_rnn/in_to_hidden");
-        B.blk(l, 0, nh, nh, Bi("propagation/vanilla_rnn/in_to_hidden"), ACT_TANH, m.Hrnn + nh * R, R);
-        l.blk[0].b2_off = Bi("propagation/vanilla_rnn/hidden_to_hidden");
-        B.seg(l, m.Loc1, R, nw, wi);
-        B.seg(l, m.PropOut, LDE, nw + 5, wi + nw * nh, -1, R);                 // entry s = record of slot s-1
-        B.seg(l, zw, LDS, nw + 5, wi + (2 * nw + 5) * nh, -1, R);
-        B.seg(l, m.Tst, LDS, nh, wi + (3 * nw + 10) * nh, -1, R);
-        B.seg(l, m.Hrnn, R, nh, W("propagation/vanilla_rnn/hidden_to_hidden"));  // old h in Hrnn[0], new h -> Hrnn[1]
+        Layer& l = B.layer(L_PRNN);
+        B.seg(l, m.Loc1, R, nw);
+        B.seg(l, m.PropOut, LDE, nw + 5, R);            // entry s = record of slot s-1
+        B.seg(l, zw, LDS, nw + 5, R);
+        B.seg(l, m.Tst, LDS, nh, R);
+        B.seg(l, m.Hrnn, R, nh);                        // old h in Hrnn[0], new h -> Hrnn[1]
+        int h = B.head(l, nh, Bi("propagation/vanilla_rnn/in_to_hidden"), ACT_TANH, Hnew, R);
+        l.head[h].b2_off = Bi("propagation/vanilla_rnn/hidden_to_hidden");
+        B.wrows(L_PRNN, 0, "propagation/vanilla_rnn/in_to_hidden/w", 0, 3);
+        B.w(L_PRNN, 4, 0, "propagation/vanilla_rnn/hidden_to_hidden/w", 0);
+        B.finish(L_PRNN);
     }
     // ---- propagation transform estimator (core.py:321-327): [h, where_tm1, temporal]
     {
-        Layer& l = B.layer(L_PT1, 1);
-        int w = W(PC + "stochastic_transform_param/mlp/linear");
-        B.blk(l, 0, nh, nh, Bi(PC + "stochastic_transform_param/mlp/linear"), ACT_ELU, m.A0, R);
-        B.seg(l, m.Hrnn + nh * R, R, nh, w);
-        B.seg(l, zwhere, LDS, 4, w + nh * nh, -1, R);
-        B.seg(l, m.Tst, LDS, nh, w + (nh + 4) * nh, -1, R);
+        Layer& l = B.layer(L_PT1);
+        B.seg(l, Hnew, R, nh);
+        B.seg(l, zwhere, LDS, 4, R);
+        B.seg(l, m.Tst, LDS, nh, R);
+        B.head(l, nh, Bi(PC + "stochastic_transform_param/mlp/linear"), ACT_ELU, m.A0, R);
+        B.wrows(L_PT1, 0, PC + "stochastic_transform_param/mlp/linear/w");
+        B.finish(L_PT1);
     }
-    {
-        Layer& l = B.layer(L_PT2, 1);
-        B.blk(l, 0, nh, nh, Bi(PC + "stochastic_transform_param/mlp/linear_1"), ACT_ELU, m.A1, R);
-        B.seg(l, m.A0, R, nh, W(PC + "stochastic_transform_param/mlp/linear_1"));
-    }
-    {
-        Layer& l = B.layer(L_PT3, 1);
-        B.blk(l, 0, 8, 8, Bi(PC + "stochastic_transform_param/mlp/linear_2"), ACT_NONE, m.Tp, R);
-        B.seg(l, m.A1, R, nh, W(PC + "stochastic_transform_param/mlp/linear_2"));
-    }
+    simple(L_PT2, m.A0, R, nh, 0, PC + "stochastic_transform_param/mlp/linear_1", nh, ACT_ELU, m.A1, R);
+    B.finish(L_PT2);
+    simple(L_PT3, m.A1, R, nh, 0, PC + "stochastic_transform_param/mlp/linear_2", 8, ACT_NONE, m.Tp, R);
+    B.finish(L_PT3);
     // ---- temporal GRU (core.py:339-340): x = [h, where, loc2, scale2], state = Tst
+    const int where_cur = m.PropOut + R + rf.where * LDE;          // this slot's where (entry s+1)
     {
-        Layer& l = B.layer(L_TGRU_ZR, 2);
-        int wz = B.off("propagation/gru/wz"), wr = B.off("propagation/gru/wr");
-        B.blk(l, 0, nh, nh, B.off("propagation/gru/bz"), ACT_SIGMOID, m.Gz, R);
-        B.blk(l, 1, nh, nh, B.off("propagation/gru/br"), ACT_SIGMOID, m.Gr, R);
-        B.seg(l, m.Hrnn + nh * R, R, nh, wz, wr);
-        B.seg(l, m.PropOut + R + rf.where * LDE, LDE, 4, wz + nh * nh, wr + nh * nh, R);      // this slot's where
-        B.seg(l, m.Enc, R, 2 * nw, wz + (nh + 4) * nh, wr + (nh + 4) * nh);
-        B.seg(l, m.Tst, LDS, nh, B.off("propagation/gru/uz"), B.off("propagation/gru/ur"), R);
+        Layer& l = B.layer(L_TGRU_ZR);
+        B.seg(l, Hnew, R, nh);
+        B.seg(l, where_cur, LDE, 4, R);
+        B.seg(l, m.Enc, R, 2 * nw);
+        B.seg(l, m.Tst, LDS, nh, R);
+        B.head(l, nh, B.off("propagation/gru/bz"), ACT_SIGMOID, m.Gz, R);
+        B.head(l, nh, B.off("propagation/gru/br"), ACT_SIGMOID, m.Gr, R);
+        B.wrows(L_TGRU_ZR, 0, "propagation/gru/wz", 0, 2); B.w(L_TGRU_ZR, 3, 0, "propagation/gru/uz", 0);
+        B.wrows(L_TGRU_ZR, 1, "propagation/gru/wr", 0, 2); B.w(L_TGRU_ZR, 3, 1, "propagation/gru/ur", 0);
+        B.finish(L_TGRU_ZR);
     }
     {
-        Layer& l = B.layer(L_TGRU_C, 1);
-        int wh = B.off("propagation/gru/wh");
-        B.blk(l, 0, nh, nh, B.off("propagation/gru/bh"), ACT_TANH, m.Gc, R);
-        B.seg(l, m.Hrnn + nh * R, R, nh, wh);
-        B.seg(l, m.PropOut + R + rf.where * LDE, LDE, 4, wh + nh * nh, -1, R);
-        B.seg(l, m.Enc, R, 2 * nw, wh + (nh + 4) * nh);
-        B.seg(l, m.Gr, R, nh, B.off("propagation/gru/uh"));
+        Layer& l = B.layer(L_TGRU_C);
+        B.seg(l, Hnew, R, nh);
+        B.seg(l, where_cur, LDE, 4, R);
+        B.seg(l, m.Enc, R, 2 * nw);
+        B.seg(l, m.Gr, R, nh);
+        B.head(l, nh, B.off("propagation/gru/bh"), ACT_TANH, m.Gc, R);
+        B.wrows(L_TGRU_C, 0, "propagation/gru/wh", 0, 2); B.w(L_TGRU_C, 3, 0, "propagation/gru/uh", 0);
+        B.finish(L_TGRU_C);
     }
     // ---- what heads on the new temporal state (core.py:343-349); Gc holds the new temporal state
     {
-        Layer& l = B.layer(L_PHEADS, 2);
-        B.blk(l, 0, 2 * nw, 2 * nw, Bi(PC + "what/gaussian_from_param_vec/linear"), ACT_NONE, m.Tg, R);
-        l.blk[0].split = nw; l.blk[0].act_hi = ACT_SOFTPLUS; l.blk[0].add_hi = c.min_std;
-        B.blk(l, 1, 3 * nw, 3 * nw, Bi(PC + "what/linear"), ACT_SIGMOID, m.Gt, R);
-        l.blk[1].scale = 0.9999f; l.blk[1].scale_hi = 0.9999f;
-        B.seg(l, m.Gc, R, nh, W(PC + "what/gaussian_from_param_vec/linear"), W(PC + "what/linear"));
+        Layer& l = B.layer(L_PHEADS);
+        B.seg(l, m.Gc, R, nh);
+        gauss_heads(L_PHEADS, l, PC + "what/gaussian_from_param_vec/linear", m.Tg);
+        int h = B.head(l, 3 * nw, Bi(PC + "what/linear"), ACT_SIGMOID, m.Gt, R);
+        l.head[h].scale = 0.9999f;
+        B.w(L_PHEADS, 0, h, PC + "what/linear/w", 0);
+        B.finish(L_PHEADS);
     }
     // ---- propagation steps predictor (modules.py:506-513): [h, temporal(old), what]
     {
-        Layer& l = B.layer(L_PST1, 1);
-        int w = W(PC + "steps_predictor/mlp/linear");
-        B.blk(l, 0, s, s, Bi(PC + "steps_predictor/mlp/linear"), ACT_ELU, m.Hs, R);
-        B.seg(l, m.Hrnn + nh * R, R, nh, w);
-        B.seg(l, m.Tst, LDS, nh, w + nh * s, -1, R);
-        B.seg(l, m.PropOut + R + rf.what * LDE, LDE, nw, w + 2 * nh * s, -1, R);
+        Layer& l = B.layer(L_PST1);
+        B.seg(l, Hnew, R, nh);
+        B.seg(l, m.Tst, LDS, nh, R);
+        B.seg(l, m.PropOut + R + rf.what * LDE, LDE, nw, R);
+        B.head(l, s, Bi(PC + "steps_predictor/mlp/linear"), ACT_ELU, m.Hs, R);
+        B.wrows(L_PST1, 0, PC + "steps_predictor/mlp/linear/w");
+        B.finish(L_PST1);
     }
-    {
-        Layer& l = B.layer(L_PST2, 1);
-        B.blk(l, 0, 1, 1, Bi(PC + "steps_predictor/mlp/linear_1"), ACT_NONE, m.Lg, R);
-        B.seg(l, m.Hs, R, s, W(PC + "steps_predictor/mlp/linear_1"));
-    }
+    simple(L_PST2, m.Hs, R, s, 0, PC + "steps_predictor/mlp/linear_1", 1, ACT_NONE, m.Lg, R);
+    B.finish(L_PST2);
     // ---- latent encoder (sqair_modules.py:368-385): [what, where] of a propagated slot
-    {
-        Layer& l = B.layer(L_LAT1, 1);
-        B.blk(l, 0, nh, nh, Bi(SQ + "sqair_timestep/mlp/linear"), ACT_ELU, m.A0, R);
-        B.seg(l, m.PropOut + R, LDE, nw + 4, W(SQ + "sqair_timestep/mlp/linear"), -1, R);
-    }
-    {
-        Layer& l = B.layer(L_LAT2, 1);
-        B.blk(l, 0, nh, nh, Bi(SQ + "sqair_timestep/mlp/linear_1"), ACT_ELU, m.A1, R);
-        B.seg(l, m.A0, R, nh, W(SQ + "sqair_timestep/mlp/linear_1"));
-    }
+    simple(L_LAT1, m.PropOut + R, LDE, nw + 4, R, SQ + "sqair_timestep/mlp/linear", nh, ACT_ELU, m.A0, R);
+    B.finish(L_LAT1);
+    simple(L_LAT2, m.A0, R, nh, 0, SQ + "sqair_timestep/mlp/linear_1", nh, ACT_ELU, m.A1, R);
+    B.finish(L_LAT2);
     // ---- image encoder (core.py:165), once per frame
     {
-        Layer& l = B.layer(L_IMG1, 1);
-        B.blk(l, 0, nh, nh, Bi(DC + "encoder/mlp/linear"), ACT_ELU, m.A0, R);
-        B.seg(l, 0, 0, P, W(DC + "encoder/mlp/linear"), -1, 0, SEG_IMAGE);
+        Layer& l = B.layer(L_IMG1);
+        B.seg(l, 0, 0, P, 0, SEG_IMAGE);
+        B.head(l, nh, Bi(DC + "encoder/mlp/linear"), ACT_ELU, m.A0, R);
+        B.w(L_IMG1, 0, 0, DC + "encoder/mlp/linear/w", 0);
+        B.finish(L_IMG1);
     }
-    {
-        Layer& l = B.layer(L_IMG2, 1);
-        B.blk(l, 0, nh, nh, Bi(DC + "encoder/mlp/linear_1"), ACT_ELU, m.DIn, R);
-        B.seg(l, m.A0, R, nh, W(DC + "encoder/mlp/linear_1"));
-    }
+    simple(L_IMG2, m.A0, R, nh, 0, DC + "encoder/mlp/linear_1", nh, ACT_ELU, m.DIn, R);
+    B.finish(L_IMG2);
     // ---- discovery RNN (core.py:164-176,197-198): [img_enc, conditioning, km1(what,where,pres)] + h
     {
-        Layer& l = B.layer(L_DRNN, 1);
-        int wi = W("discovery/vanilla_rnn/in_to_hidden");
-        B.blk(l, 0, nh, nh, Bi("discovery/vanilla_rnn/in_to_hidden"), ACT_TANH, m.Hrnn + nh * R, R);
-        l.blk[0].b2_off = Bi("discovery/vanilla_rnn/hidden_to_hidden");
-        B.seg(l, m.DIn, R, 2 * nh, wi);
-        B.seg(l, m.DiscOut, LDE, nw + 5, wi + 2 * nh * nh, -1, R);
-        B.seg(l, m.Hrnn, R, nh, W("discovery/vanilla_rnn/hidden_to_hidden"));
+        Layer& l = B.layer(L_DRNN);
+        B.seg(l, m.DIn, R, 2 * nh);
+        B.seg(l, m.DiscOut, LDE, nw + 5, R);
+        B.seg(l, m.Hrnn, R, nh);
+        int h = B.head(l, nh, Bi("discovery/vanilla_rnn/in_to_hidden"), ACT_TANH, Hnew, R);
+        l.head[h].b2_off = Bi("discovery/vanilla_rnn/hidden_to_hidden");
+        B.wrows(L_DRNN, 0, "discovery/vanilla_rnn/in_to_hidden/w", 0, 1);
+        B.w(L_DRNN, 2, 0, "discovery/vanilla_rnn/hidden_to_hidden/w", 0);
+        B.finish(L_DRNN);
     }
+    simple(L_DT1, Hnew, R, nh, 0, DC + "stochastic_transform_param/mlp/linear", nh, ACT_ELU, m.A0, R);
+    B.finish(L_DT1);
+    simple(L_DT2, m.A0, R, nh, 0, DC + "stochastic_transform_param/mlp/linear_1", nh, ACT_ELU, m.A1, R);
+    B.finish(L_DT2);
+    simple(L_DT3, m.A1, R, nh, 0, DC + "stochastic_transform_param/mlp/linear_2", 8, ACT_NONE, m.Tp, R);
+    B.finish(L_DT3);
     {
-        Layer& l = B.layer(L_DT1, 1);
-        B.blk(l, 0, nh, nh, Bi(DC + "stochastic_transform_param/mlp/linear"), ACT_ELU, m.A0, R);
-        B.seg(l, m.Hrnn + nh * R, R, nh, W(DC + "stochastic_transform_param/mlp/linear"));
+        Layer& l = B.layer(L_DST1);
+        B.seg(l, Hnew, R, nh);
+        B.seg(l, m.DiscOut + R + rf.what * LDE, LDE, nw, R);
+        B.head(l, s, Bi(DC + "steps_predictor/mlp/linear"), ACT_ELU, m.Hs, R);
+        B.wrows(L_DST1, 0, DC + "steps_predictor/mlp/linear/w");
+        B.finish(L_DST1);
     }
-    {
-        Layer& l = B.layer(L_DT2, 1);
-        B.blk(l, 0, nh, nh, Bi(DC + "stochastic_transform_param/mlp/linear_1"), ACT_ELU, m.A1, R);
-        B.seg(l, m.A0, R, nh, W(DC + "stochastic_transform_param/mlp/linear_1"));
-    }
-    {
-        Layer& l = B.layer(L_DT3, 1);
-        B.blk(l, 0, 8, 8, Bi(DC + "stochastic_transform_param/mlp/linear_2"), ACT_NONE, m.Tp, R);
-        B.seg(l, m.A1, R, nh, W(DC + "stochastic_transform_param/mlp/linear_2"));
-    }
-    {
-        Layer& l = B.layer(L_DST1, 1);
-        int w = W(DC + "steps_predictor/mlp/linear");
-        B.blk(l, 0, s, s, Bi(DC + "steps_predictor/mlp/linear"), ACT_ELU, m.Hs, R);
-        B.seg(l, m.Hrnn + nh * R, R, nh, w);
-        B.seg(l, m.DiscOut + R + rf.what * LDE, LDE, nw, w + nh * s, -1, R);
-    }
-    {
-        Layer& l = B.layer(L_DST2, 1);
-        B.blk(l, 0, 1, 1, Bi(DC + "steps_predictor/mlp/linear_1"), ACT_NONE, m.Lg, R);
-        B.seg(l, m.Hs, R, s, W(DC + "steps_predictor/mlp/linear_1"));
-    }
+    simple(L_DST2, m.Hs, R, s, 0, DC + "steps_predictor/mlp/linear_1", 1, ACT_NONE, m.Lg, R);
+    B.finish(L_DST2);
     // ---- recurrent where prior (modules.py:548-607)
     if (c.rec_where_prior) {
         {
-            Layer& l = B.layer(L_RN1, 1);
-            int w = W(RN + "linear_1");
-            B.blk(l, 0, 128, 128, Bi(RN + "linear_1"), ACT_ELU, m.Hrn, R);
-            B.seg(l, m.RnInit, R, 4, w);
-            B.seg(l, m.DIn + nh * R, R, nh, w + 4 * 128);          // conditioning from propagation
-            B.seg(l, m.Exp, R, 1, w + (4 + nh) * 128);
+            Layer& l = B.layer(L_RN1);
+            B.seg(l, m.RnInit, R, 4);
+            B.seg(l, m.DIn + nh * R, R, nh);            // conditioning from propagation
+            B.seg(l, m.Exp, R, 1);
+            B.head(l, 128, Bi(RN + "linear_1"), ACT_ELU, m.Hrn, R);
+            B.wrows(L_RN1, 0, RN + "linear_1/w");
+            B.finish(L_RN1);
         }
         {
-            Layer& l = B.layer(L_RN2, 1);
-            B.blk(l, 0, 4, 4, Bi(RN + "vanilla_rnn/in_to_hidden"), ACT_TANH, m.Rno, R);
-            l.blk[0].b2_off = Bi(RN + "vanilla_rnn/hidden_to_hidden");
-            B.seg(l, m.RnPrev0, LDS, 4, W(RN + "vanilla_rnn/in_to_hidden"), -1, R);
-            B.seg(l, m.Hrn, R, 128, W(RN + "vanilla_rnn/hidden_to_hidden"));
+            Layer& l = B.layer(L_RN2);
+            B.seg(l, m.RnPrev0, LDS, 4, R);
+            B.seg(l, m.Hrn, R, 128);
+            int h = B.head(l, 4, Bi(RN + "vanilla_rnn/in_to_hidden"), ACT_TANH, m.Rno, R);
+            l.head[h].b2_off = Bi(RN + "vanilla_rnn/hidden_to_hidden");
+            B.w(L_RN2, 0, 0, RN + "vanilla_rnn/in_to_hidden/w", 0);
+            B.w(L_RN2, 1, 0, RN + "vanilla_rnn/hidden_to_hidden/w", 0);
+            B.finish(L_RN2);
         }
         {
-            Layer& l = B.layer(L_RN3, 1);
-            B.blk(l, 0, 8, 8, Bi(RN + "linear"), ACT_NONE, m.Rns, R);
-            l.blk[0].split = 4; l.blk[0].act_hi = ACT_SOFTPLUS; l.blk[0].add_hi = 1e-2f;
-            B.seg(l, m.Rno, R, 4, W(RN + "linear"));
+            Layer& l = B.layer(L_RN3);
+            B.seg(l, m.Rno, R, 4);
+            const int b = Bi(RN + "linear");
+            B.head(l, 4, b, ACT_NONE, m.Rns, R);
+            int h1 = B.head(l, 4, b + 4, ACT_SOFTPLUS, m.Rns + 4 * R, R);
+            l.head[h1].add = 1e-2f;
+            B.w(L_RN3, 0, 0, RN + "linear/w", 0, 0);
+            B.w(L_RN3, 0, 1, RN + "linear/w", 0, 4);
+            B.finish(L_RN3);
         }
     }
     // ---- step-count prior MLP (sqair_modules.py:217-218)
-    {
-        Layer& l = B.layer(L_SP1, 1);
-        B.blk(l, 0, 10, 10, Bi("discovery/discover/mlp/linear"), ACT_ELU, m.Hsp, R);
-        B.seg(l, m.Exp, R, 1, W("discovery/discover/mlp/linear"));
-    }
-    {
-        Layer& l = B.layer(L_SP2, 1);
-        B.blk(l, 0, NS + 1, NS + 1, Bi("discovery/discover/mlp/linear_1"), ACT_NONE, m.Spl, R);
-        B.seg(l, m.Hsp, R, 10, W("discovery/discover/mlp/linear_1"));
-    }
+    simple(L_SP1, m.Exp, R, 1, 0, "discovery/discover/mlp/linear", 10, ACT_ELU, m.Hsp, R);
+    B.finish(L_SP1);
+    simple(L_SP2, m.Hsp, R, 10, 0, "discovery/discover/mlp/linear_1", NS + 1, ACT_NONE, m.Spl, R);
+    B.finish(L_SP2);
     // ---- glimpse decoder (modules.py:131-147)
-    {
-        Layer& l = B.layer(L_DEC1, 1);
-        B.blk(l, 0, nh, nh, Bi("decoder/air_decoder/decoder/mlp/linear"), ACT_ELU, m.A0, R);
-        B.seg(l, zw, LDS, nw, W("decoder/air_decoder/decoder/mlp/linear"), -1, R);
-    }
-    {
-        Layer& l = B.layer(L_DEC2, 1);
-        B.blk(l, 0, nh, nh, Bi("decoder/air_decoder/decoder/mlp/linear_1"), ACT_ELU, m.A1, R);
-        B.seg(l, m.A0, R, nh, W("decoder/air_decoder/decoder/mlp/linear_1"));
-    }
-    {
-        Layer& l = B.layer(L_DEC3, 1);
-        B.blk(l, 0, g, g, Bi("decoder/air_decoder/decoder/mlp/linear_2"), ACT_NONE, m.Dgl, LDS, R);
-        l.blk[0].scale_p_off = po.output_scale;
-        B.seg(l, m.A1, R, nh, W("decoder/air_decoder/decoder/mlp/linear_2"));
-    }
+    simple(L_DEC1, zw, LDS, nw, R, "decoder/air_decoder/decoder/mlp/linear", nh, ACT_ELU, m.A0, R);
+    B.finish(L_DEC1);
+    simple(L_DEC2, m.A0, R, nh, 0, "decoder/air_decoder/decoder/mlp/linear_1", nh, ACT_ELU, m.A1, R);
+    B.finish(L_DEC2);
+    simple(L_DEC3, m.A1, R, nh, 0, "decoder/air_decoder/decoder/mlp/linear_2", g, ACT_NONE, m.Dgl, LDS, R)
+        .head[0].scale_p_off = po.output_scale;
+    B.finish(L_DEC3);
 
+    // reduction scratch: every k-slice parks its partial sums, [ks][Nc][R]
     int red = 0;
     for (int i = 0; i < L_COUNT; ++i) {
-        int r = red_need(p.L[i], R);
+        if (p.L[i].nhead == 0) continue;
+        int r = dense_ks(p.L[i].Nc, NT) * p.L[i].Nc * R;
         if (r > red) red = r;
     }
+    if (red < 8 * R) red = 8 * R;                        // also used by the block reduction of the likelihood
     m.red_floats = red;
     m.Red = B.alloc(red);
     m.total = B.cursor;
+
+    std::vector<int> q = frame_sequence(c);
+    if ((int)q.size() > MAXSEQ) return "too many dense calls per frame";
+    p.nseq = (int)q.size();
+    for (size_t i = 0; i < q.size(); ++i) p.seq[i] = (unsigned char)q[i];
+    if (packed_total) *packed_total = (B.wcursor + 31) / 32 * 32 + 32;
     return B.err;
 }
 

@@ -15,6 +15,8 @@
 #include "sqair_core.h"
 
 #ifdef SQAIR_HOST_EMU
+#include <atomic>
+#include <cstdlib>
 #define SQ_DEV inline
 #define SQ_DEVNI inline
 #define SQ_LDG(p) (*(p))
@@ -28,15 +30,99 @@
 
 namespace sq {
 
+#ifdef SQAIR_HOST_EMU
+// split-phase reusable barrier for the emulated cluster (one host thread per block)
+struct EmuClusterBarrier {
+    std::atomic<long> count{0};
+    int n = 1;
+};
+#endif
+
+// Per-thread view of the block: indices, shared memory, position in the cluster and the state of
+// the weight ring (identical in all threads of a block; advanced deterministically).
 struct Ctx {
     int tid, nthreads, lane, nlanes, warp, nwarps;
     float* sm;
+    int rank, ncta;          // block rank in its cluster, cluster size
+    int cons;                // weight chunks consumed so far by this block
+    int issued;              // weight chunks issued so far (thread 0 is the producer)
+    int p_t, p_i, p_s, p_c, p_row;   // producer cursor: frame, call index, segment, chunk in segment, row in layer
+    int call_idx;            // dense calls executed in the current frame
+#ifdef SQAIR_HOST_EMU
+    float** peers;           // shared memory of every block of the cluster
+    EmuClusterBarrier* cb;
+    long cb_gen;
+#endif
     SQ_DEV void sync() const {
 #ifndef SQAIR_HOST_EMU
         __syncthreads();
 #endif
     }
 };
+
+#ifndef SQAIR_HOST_EMU
+// ---- PTX wrappers: mbarrier, bulk async copy (TMA), cluster barrier, distributed shared memory ----
+SQ_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+SQ_DEV void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+SQ_DEV void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+SQ_DEV void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+SQ_DEV bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+SQ_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+SQ_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+SQ_DEV void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+SQ_DEV void cluster_arrive_() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+SQ_DEV void cluster_wait_() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+SQ_DEV uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+SQ_DEV void st_cluster_f32(uint32_t local_addr, int rank, float v) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+#endif
+
+// cluster barrier, split phase: arrive (release) ... wait (acquire)
+SQ_DEV void cluster_arrive(Ctx& c) {
+#ifdef SQAIR_HOST_EMU
+    c.cb->count.fetch_add(1, std::memory_order_acq_rel);
+    c.cb_gen += 1;
+#else
+    cluster_arrive_();
+#endif
+}
+SQ_DEV void cluster_wait(Ctx& c) {
+#ifdef SQAIR_HOST_EMU
+    while (c.cb->count.load(std::memory_order_acquire) < c.cb_gen * c.cb->n) {}
+#else
+    cluster_wait_();
+#endif
+}
+// store one float at the same shared-memory offset of block `rank` of the cluster
+SQ_DEV void store_peer(Ctx& c, int off, int rank, float v) {
+#ifdef SQAIR_HOST_EMU
+    c.peers[rank][off] = v;
+#else
+    st_cluster_f32(smem_u32(c.sm + off), rank, v);
+#endif
+}
 
 SQ_DEV float warp_sum(float v) {
 #ifndef SQAIR_HOST_EMU
@@ -103,185 +189,230 @@ struct Job {
     sqair_outputs out;
 };
 
-SQ_DEV void dense_map(const Layer& L, int nthreads, int& G, int& Gp, int& ks) {
-    G = 0;
-    for (int b = 0; b < L.nblk; ++b) G += (L.blk[b].N + 3) >> 2;
-    Gp = (G + 7) & ~7;
-    ks = nthreads / Gp;
-    if (ks > MAX_KS) ks = MAX_KS;
-    if (ks < 1) ks = 1;
+// ---------------------------------------------------------------------------------------------
+// Weight ring.  Chunks = consecutive row blocks (<= rpc rows, never straddling a segment) of this
+// block's panel of each layer, in program order (Plan::seq repeated every frame).  Thread 0 issues
+// `cp.async.bulk` copies into NSTAGE stages as far ahead as stages are free; all threads wait on the
+// stage's "full" mbarrier before reading and every warp arrives on its "empty" mbarrier afterwards.
+// ---------------------------------------------------------------------------------------------
+SQ_DEV bool layer_has_work(const Layer& L, int rank) { return !L.split || rank < L.npanel; }
+SQ_DEV const float* panel_ptr(const Plan& P, const Layer& L, const float* prm, int rank) {
+    return prm + L.w_off + (size_t)(L.split ? rank : 0) * L.Ktot * L.Nc;
+}
+
+#ifndef SQAIR_HOST_EMU
+SQ_DEV void prod_skip_idle(Ctx& c, const Plan& P) {
+    while (c.p_t < P.cfg.T && !layer_has_work(P.L[P.seq[c.p_i]], c.rank)) {
+        if (++c.p_i >= P.nseq) { c.p_i = 0; ++c.p_t; }
+    }
+}
+SQ_DEV void prod_issue(Ctx& c, const Plan& P, const float* prm) {
+    const Layer& L = P.L[P.seq[c.p_i]];
+    const Seg& S = L.seg[c.p_s];
+    int rows = S.K - c.p_c * L.rpc;
+    if (rows > L.rpc) rows = L.rpc;
+    const float* src = panel_ptr(P, L, prm, c.rank) + (size_t)(c.p_row + c.p_c * L.rpc) * L.Nc;
+    const uint32_t bytes = (uint32_t)(rows * L.Nc) * 4u;
+    const int stage = c.issued % NSTAGE;
+    const uint32_t bar = smem_u32(c.sm + P.sm.Bar);
+    mbar_expect_tx(bar + 8u * stage, bytes);
+    bulk_g2s(smem_u32(c.sm + P.sm.Ring + stage * P.sm.stage_floats), src, bytes, bar + 8u * stage);
+    ++c.issued;
+    // advance the cursor
+    if ((c.p_c + 1) * L.rpc < S.K) { ++c.p_c; return; }
+    c.p_c = 0;
+    c.p_row += S.K;
+    if (++c.p_s < L.nseg) return;
+    c.p_s = 0; c.p_row = 0;
+    if (++c.p_i >= P.nseq) { c.p_i = 0; ++c.p_t; }
+    prod_skip_idle(c, P);
+}
+// thread 0: make sure chunk `need` is in flight, then run ahead while stages are free
+SQ_DEV void prod_fill(Ctx& c, const Plan& P, const float* prm, int need) {
+    if (c.tid != 0) return;
+    const uint32_t ebar = smem_u32(c.sm + P.sm.Bar) + 8u * NSTAGE;
+    while (c.issued <= need) {
+        mbar_wait(ebar + 8u * (c.issued % NSTAGE), ((c.issued / NSTAGE) & 1) ^ 1);
+        prod_issue(c, P, prm);
+    }
+    while (c.issued < need + NSTAGE && c.p_t < P.cfg.T &&
+           mbar_try_wait(ebar + 8u * (c.issued % NSTAGE), ((c.issued / NSTAGE) & 1) ^ 1))
+        prod_issue(c, P, prm);
+}
+#endif
+
+SQ_DEV void ring_init(Ctx& c, const Plan& P) {
+    c.cons = c.issued = 0;
+    c.p_t = c.p_i = c.p_s = c.p_c = c.p_row = 0;
+    c.call_idx = 0;
+#ifndef SQAIR_HOST_EMU
+    if (c.tid == 0) {
+        const uint32_t bar = smem_u32(c.sm + P.sm.Bar);
+        for (int i = 0; i < NSTAGE; ++i) {
+            mbar_init(bar + 8u * i, 1);                          // full: one expect_tx arrival + bytes
+            mbar_init(bar + 8u * (NSTAGE + i), c.nwarps);        // empty: one arrival per warp
+        }
+        fence_barrier_init();
+    }
+    prod_skip_idle(c, P);
+    c.sync();
+#endif
+}
+
+// head that owns virtual column vc (heads start at multiples of 4); returns -1 for padding columns
+SQ_DEV int head_of(const Layer& L, int vc, int& j) {
+    for (int h = 0; h < L.nhead; ++h) {
+        j = vc - L.head[h].col0;
+        if (j >= 0 && j < L.head[h].N) return h;
+    }
+    return -1;
+}
+
+// accumulate rows [0, rows) of a weight chunk w[rows][Nc] for the 4 columns starting at col
+template <int R>
+SQ_DEV void chunk_accum(const float* w, int Nc, int col, int rows, int k_first, int k_step, const Seg& S, int krow0,
+                        const float* sm, int slot, const float* const* imgrow, float (&acc)[4][R]) {
+    if (S.kind == SEG_SMEM) {
+        const float* x = sm + S.x_off + slot * S.x_sstride + krow0 * S.ld;
+        const int ld = S.ld;
+#pragma unroll 2
+        for (int k = k_first; k < rows; k += k_step) {
+            const float4 wv = *reinterpret_cast<const float4*>(w + k * Nc + col);
+            const float* xr = x + k * ld;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float xv = xr[r];
+                acc[0][r] += wv.x * xv; acc[1][r] += wv.y * xv; acc[2][r] += wv.z * xv; acc[3][r] += wv.w * xv;
+            }
+        }
+    } else {    // SEG_IMAGE: x[k][r] = frame pixel k of the image of row r (global, read-only)
+#pragma unroll 2
+        for (int k = k_first; k < rows; k += k_step) {
+            const float4 wv = *reinterpret_cast<const float4*>(w + k * Nc + col);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float xv = SQ_LDG(imgrow[r] + krow0 + k);
+                acc[0][r] += wv.x * xv; acc[1][r] += wv.y * xv; acc[2][r] += wv.z * xv; acc[3][r] += wv.w * xv;
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Dense layer (snt.Linear / Nonlinear, neural.py:34-47; VanillaRNN / GRU gate pre-activations):
-//   out[col][r] = act( sum_seg sum_k W_seg[k][col] * x_seg[k][r] + b[col] (+ b2[col]) ) * scale + add
-// Thread tile: 4 adjacent columns x R rows; the K range of every segment is split into `ks`
-// slices whose partial sums are combined through shared memory.
+//   out[col][r] = act( sum_seg sum_k W[k][col] * x_seg[k][r] + b[col] (+ b2[col]) ) * scale + add
+// Block `rank` owns the virtual columns [rank*Nc, rank*Nc + Nc) when the layer is split.  Thread tile:
+// 4 adjacent columns x R rows; the rows of every weight chunk are dealt round-robin to `ks` k-slices
+// whose partial sums meet in shared memory; all threads then finish one output each (bias,
+// activation) and store it into every block of the cluster.
 // ---------------------------------------------------------------------------------------------
 template <int R>
-SQ_DEV void dense_accum(const Ctx& c, const Plan& P, const float* SQ_RESTRICT prm, const Layer& L, int slot,
-                        int b, int col, int sl, int ks, const float* const* imgrow, float (&acc)[4][R]) {
-    const Blk& B = L.blk[b];
-    const int ldw = B.ldw;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[j][r] = 0.f;
-    for (int si = 0; si < L.nseg; ++si) {
-        const Seg& S = L.seg[si];
-        const int kc = (S.K + ks - 1) / ks;
-        const int k0 = sl * kc;
-        int k1 = k0 + kc;
-        if (k1 > S.K) k1 = S.K;
-        if (k0 >= k1) continue;
-        const int wbase = S.w_off[b] + col;
-        const float* SQ_RESTRICT w = prm + wbase + (size_t)k0 * ldw;
-        const bool vec = ((ldw & 3) == 0) && ((wbase & 3) == 0);
-        if (S.kind == SEG_SMEM) {
-            const float* x = c.sm + S.x_off + slot * S.x_sstride + k0 * S.ld;
-            const int ld = S.ld;
-            if (vec) {
-                int k = k0;
-                for (; k + 4 <= k1; k += 4) {
-                    float4 w0 = SQ_LDG(reinterpret_cast<const float4*>(w));
-                    float4 w1 = SQ_LDG(reinterpret_cast<const float4*>(w + ldw));
-                    float4 w2 = SQ_LDG(reinterpret_cast<const float4*>(w + 2 * ldw));
-                    float4 w3 = SQ_LDG(reinterpret_cast<const float4*>(w + 3 * ldw));
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        float x0 = x[r], x1 = x[ld + r], x2 = x[2 * ld + r], x3 = x[3 * ld + r];
-                        acc[0][r] += w0.x * x0; acc[1][r] += w0.y * x0; acc[2][r] += w0.z * x0; acc[3][r] += w0.w * x0;
-                        acc[0][r] += w1.x * x1; acc[1][r] += w1.y * x1; acc[2][r] += w1.z * x1; acc[3][r] += w1.w * x1;
-                        acc[0][r] += w2.x * x2; acc[1][r] += w2.y * x2; acc[2][r] += w2.z * x2; acc[3][r] += w2.w * x2;
-                        acc[0][r] += w3.x * x3; acc[1][r] += w3.y * x3; acc[2][r] += w3.z * x3; acc[3][r] += w3.w * x3;
-                    }
-                    w += 4 * ldw;
-                    x += 4 * ld;
-                }
-                for (; k < k1; ++k) {
-                    float4 w0 = SQ_LDG(reinterpret_cast<const float4*>(w));
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        float x0 = x[r];
-                        acc[0][r] += w0.x * x0; acc[1][r] += w0.y * x0; acc[2][r] += w0.z * x0; acc[3][r] += w0.w * x0;
-                    }
-                    w += ldw;
-                    x += ld;
-                }
-            } else {
-                const int nv = (B.N - col) < 4 ? (B.N - col) : 4;
-                for (int k = k0; k < k1; ++k) {
-                    float wv[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) wv[j] = (j < nv) ? SQ_LDG(w + j) : 0.f;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        float x0 = x[r];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[j][r] += wv[j] * x0;
-                    }
-                    w += ldw;
-                    x += ld;
-                }
-            }
-        } else {   // SEG_IMAGE: x[k][r] = frame pixel k of the image of row r (global, read-only)
-            int k = k0;
-            if (vec) {
-                for (; k + 2 <= k1; k += 2) {
-                    float4 w0 = SQ_LDG(reinterpret_cast<const float4*>(w));
-                    float4 w1 = SQ_LDG(reinterpret_cast<const float4*>(w + ldw));
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        float x0 = SQ_LDG(imgrow[r] + k), x1 = SQ_LDG(imgrow[r] + k + 1);
-                        acc[0][r] += w0.x * x0; acc[1][r] += w0.y * x0; acc[2][r] += w0.z * x0; acc[3][r] += w0.w * x0;
-                        acc[0][r] += w1.x * x1; acc[1][r] += w1.y * x1; acc[2][r] += w1.z * x1; acc[3][r] += w1.w * x1;
-                    }
-                    w += 2 * ldw;
-                }
-            }
-            const int nv = (B.N - col) < 4 ? (B.N - col) : 4;
-            for (; k < k1; ++k) {
-                float wv[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) wv[j] = (j < nv) ? SQ_LDG(w + j) : 0.f;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    float x0 = SQ_LDG(imgrow[r] + k);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[j][r] += wv[j] * x0;
-                }
-                w += ldw;
-            }
-        }
-    }
-}
-
-template <int R>
-SQ_DEV void dense_epilogue(const Ctx& c, const float* SQ_RESTRICT prm, const Layer& L, int slot, int b, int col,
-                           float (&acc)[4][R]) {
-    const Blk& B = L.blk[b];
-    const float pscale = B.scale_p_off >= 0 ? SQ_LDG(prm + B.scale_p_off) : 1.f;
-    float* out = c.sm + B.out_off + slot * B.out_sstride;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int cc = col + j;
-        if (cc < B.N) {
-            float bias = B.b_off >= 0 ? SQ_LDG(prm + B.b_off + cc) : 0.f;
-            if (B.b2_off >= 0) bias += SQ_LDG(prm + B.b2_off + cc);
-            const bool hi = cc >= B.split;
-            const int act = hi ? B.act_hi : B.act;
-            const float sc = hi ? B.scale_hi : B.scale, ad = hi ? B.add_hi : B.add;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                float v = actf(act, acc[j][r] + bias) * sc + ad;
-                out[cc * B.out_ld + r] = v * pscale;
-            }
-        }
-    }
-}
-
-template <int R>
-SQ_DEVNI void dense(const Ctx& c, const Plan& P, const float* SQ_RESTRICT prm, int layer_id, int slot,
+SQ_DEVNI void dense(Ctx& c, const Plan& P, const float* SQ_RESTRICT prm, int layer_id, int slot,
                     const float* const* imgrow) {
     const Layer& L = P.L[layer_id];
-    int G, Gp, ks;
-    dense_map(L, c.nthreads, G, Gp, ks);
-    float acc[4][R];
-    if (ks == 1) {
-        for (int g = c.tid; g < G; g += c.nthreads) {
-            int b = 0, cg = g;
-            while (cg >= ((L.blk[b].N + 3) >> 2)) { cg -= (L.blk[b].N + 3) >> 2; ++b; }
-            dense_accum<R>(c, P, prm, L, slot, b, cg * 4, 0, 1, imgrow, acc);
-            dense_epilogue<R>(c, prm, L, slot, b, cg * 4, acc);
+#ifdef SQAIR_HOST_EMU
+    if (P.seq[c.call_idx] != layer_id) {
+        fprintf(stderr, "emu: dense call %d is layer %d but Plan::seq says %d\n", c.call_idx, layer_id, P.seq[c.call_idx]);
+        abort();
+    }
+#endif
+    if (++c.call_idx >= P.nseq) c.call_idx = 0;
+    const bool exchange = L.split && c.ncta > 1;
+    const bool work = layer_has_work(L, c.rank);
+    const int Nc = L.Nc, Gc = Nc >> 2;
+    if (exchange) cluster_arrive(c);             // phase A: "my buffers may be written once you all are here"
+    float* red = c.sm + P.sm.Red;
+    int ks = 1;
+#ifdef SQAIR_HOST_EMU
+    std::vector<float> redv;
+#endif
+    if (work) {
+#ifdef SQAIR_HOST_EMU
+        // one sequential thread: all column groups, accumulators on the heap
+        std::vector<float> accs((size_t)Gc * 4 * R, 0.f);
+        const float* panel = panel_ptr(P, L, prm, c.rank);
+        int row0 = 0;
+        for (int si = 0; si < L.nseg; ++si) {
+            const Seg& S = L.seg[si];
+            for (int k0 = 0; k0 < S.K; k0 += L.rpc) {
+                const int rows = (S.K - k0 < L.rpc) ? (S.K - k0) : L.rpc;
+                const float* w = panel + (size_t)(row0 + k0) * Nc;
+                for (int g = 0; g < Gc; ++g) {
+                    float acc[4][R];
+                    for (int j = 0; j < 4; ++j) for (int r = 0; r < R; ++r) acc[j][r] = accs[((size_t)g * 4 + j) * R + r];
+                    chunk_accum<R>(w, Nc, g * 4, rows, 0, 1, S, k0, c.sm, slot, imgrow, acc);
+                    for (int j = 0; j < 4; ++j) for (int r = 0; r < R; ++r) accs[((size_t)g * 4 + j) * R + r] = acc[j][r];
+                }
+                ++c.cons;
+            }
+            row0 += S.K;
         }
-    } else {
-        const int g = c.tid % Gp, sl = c.tid / Gp;
-        const bool active = g < G && sl < ks;
-        int b = 0, cg = g;
+        redv.resize((size_t)Nc * R);
+        for (int g = 0; g < Gc; ++g)
+            for (int j = 0; j < 4; ++j) for (int r = 0; r < R; ++r) redv[(size_t)(g * 4 + j) * R + r] = accs[((size_t)g * 4 + j) * R + r];
+        red = redv.data();
+        // (falls through to the shared epilogue below with ks = 1)
+#else
+        ks = c.nthreads / Gc;
+        if (ks > MAX_KS) ks = MAX_KS;
+        const int g = c.tid % Gc, sl = c.tid / Gc;
+        const bool active = sl < ks;
+        float acc[4][R];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[j][r] = 0.f;
+        const uint32_t bar = smem_u32(c.sm + P.sm.Bar);
+        for (int si = 0; si < L.nseg; ++si) {
+            const Seg& S = L.seg[si];
+            for (int k0 = 0; k0 < S.K; k0 += L.rpc) {
+                const int rows = (S.K - k0 < L.rpc) ? (S.K - k0) : L.rpc;
+                prod_fill(c, P, prm, c.cons);
+                const int stage = c.cons % NSTAGE;
+                mbar_wait(bar + 8u * stage, (c.cons / NSTAGE) & 1);
+                if (active)
+                    chunk_accum<R>(c.sm + P.sm.Ring + stage * P.sm.stage_floats, Nc, g * 4, rows, sl, ks, S, k0, c.sm, slot,
+                                   imgrow, acc);
+                __syncwarp();
+                if (c.lane == 0) mbar_arrive(bar + 8u * (NSTAGE + stage));
+                ++c.cons;
+            }
+        }
         if (active) {
-            while (cg >= ((L.blk[b].N + 3) >> 2)) { cg -= (L.blk[b].N + 3) >> 2; ++b; }
-            dense_accum<R>(c, P, prm, L, slot, b, cg * 4, sl, ks, imgrow, acc);
-            if (sl > 0) {
-                float* red = c.sm + P.sm.Red + ((sl - 1) * Gp + g) * 4 * R;
+            float* rp = red + ((size_t)sl * Nc + g * 4) * R;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int r = 0; r < R; ++r) red[j * R + r] = acc[j][r];
-            }
+                for (int r = 0; r < R; ++r) rp[j * R + r] = acc[j][r];
         }
-        c.sync();
-        if (active && sl == 0) {
-            for (int s2 = 1; s2 < ks; ++s2) {
-                const float* red = c.sm + P.sm.Red + ((s2 - 1) * Gp + g) * 4 * R;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int r = 0; r < R; ++r) acc[j][r] += red[j * R + r];
-            }
-            dense_epilogue<R>(c, prm, L, slot, b, cg * 4, acc);
-        }
+#endif
     }
     c.sync();
+    if (exchange) cluster_wait(c);               // phase A complete: every block has entered this layer
+    if (work) {
+        const int vbase = L.split ? c.rank * Nc : 0;
+        for (int o = c.tid; o < Nc * R; o += c.nthreads) {
+            const int col = o / R, r = o - col * R;
+            int j;
+            const int h = head_of(L, vbase + col, j);
+            if (h < 0) continue;
+            const Head& H = L.head[h];
+            float v = 0.f;
+            for (int s2 = 0; s2 < ks; ++s2) v += red[((size_t)s2 * Nc + col) * R + r];
+            float bias = H.b_off >= 0 ? SQ_LDG(prm + H.b_off + j) : 0.f;
+            if (H.b2_off >= 0) bias += SQ_LDG(prm + H.b2_off + j);
+            v = actf(H.act, v + bias) * H.scale + H.add;
+            if (H.scale_p_off >= 0) v *= SQ_LDG(prm + H.scale_p_off);
+            const int off = H.out_off + slot * H.out_sstride + j * H.out_ld + r;
+            if (exchange) {
+                for (int q = 0; q < c.ncta; ++q) store_peer(c, off, q, v);
+            } else {
+                c.sm[off] = v;
+            }
+        }
+    }
+    if (exchange) { cluster_arrive(c); cluster_wait(c); }     // phase B: all slices have landed everywhere
+    else c.sync();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -289,7 +420,7 @@ SQ_DEVNI void dense(const Ctx& c, const Plan& P, const float* SQ_RESTRICT prm, i
 // ---------------------------------------------------------------------------------------------
 template <int R>
 struct Block {
-    const Ctx& c;
+    Ctx& c;
     const Plan& P;
     const Job& J;
     int row0;                       // first global row of this block
@@ -297,7 +428,7 @@ struct Block {
     int grow[R];                    // global row (clamped) of each local row
     bool valid[R];
 
-    SQ_DEV Block(const Ctx& c_, const Plan& P_, const Job& J_, int row0_) : c(c_), P(P_), J(J_), row0(row0_) {
+    SQ_DEV Block(Ctx& c_, const Plan& P_, const Job& J_, int row0_) : c(c_), P(P_), J(J_), row0(row0_) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             int gr = row0 + r;
@@ -794,7 +925,7 @@ struct Block {
             else if (f < F.prob) { dst = o.where_scale; ff = f - F.where_scale; width = 4; }
             else if (f == F.prob) { dst = o.presence_prob; }
             else { Z(nw + 5, j, r) = v; dst = o.presence_logit; }
-            if (dst && valid_row(r)) dst[((trow + grow_of(r)) * NS + j) * width + ff] = v;
+            if (dst && c.rank == 0 && valid_row(r)) dst[((trow + grow_of(r)) * NS + j) * width + ff] = v;
         }
         // GRU states travel with their slots; discovered objects start from the trainable initial states
         for (int i = c.tid; i < nh * R; i += c.nthreads) {
@@ -835,7 +966,7 @@ struct Block {
         const sqair_outputs& o = J.out;
         const size_t trow = (size_t)t * P.rows;
         for (int s = 0; s < NS; ++s) { lin(L_DEC1, s); lin(L_DEC2); lin(L_DEC3, s); }
-        if (o.glimpse)
+        if (o.glimpse && c.rank == 0)
             for (int i = c.tid; i < R * NS * g; i += c.nthreads) {
                 const int px = i % g, s = (i / g) % NS, r = i / (g * NS);
                 if (valid_row(r)) o.glimpse[((trow + grow_of(r)) * NS + s) * g + px] = c.sm[m.Dgl + px * LDS() + s * R + r];
@@ -857,9 +988,12 @@ struct Block {
         float ll[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) ll[r] = 0.f;
+        // every block of the cluster composes its share of the pixels
+        const int px_per = (PX + c.ncta - 1) / c.ncta;
+        const int px0 = c.rank * px_per, px1 = (px0 + px_per < PX) ? (px0 + px_per) : PX;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            for (int px = c.tid; px < PX; px += c.nthreads) {
+            for (int px = px0 + c.tid; px < px1; px += c.nthreads) {
                 const int iy = px / W, ix = px % W;
                 const float u = lin11(ix, W), v = lin11(iy, H);
                 float canvas = 0.f, nz = 0.f;
@@ -882,7 +1016,7 @@ struct Block {
                 if (o.canvas && valid[r]) o.canvas[(trow + grow[r]) * PX + px] = canvas;
             }
         }
-        // block reduction of the R partial sums
+        // block reduction of the R partial sums, then the cluster's partial sums meet in every block
         float* red = c.sm + m.Red;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -893,7 +1027,20 @@ struct Block {
         for (int r = c.tid; r < R; r += c.nthreads) {
             float a = 0.f;
             for (int w = 0; w < c.nwarps; ++w) a += red[w * R + r];
-            rowacc(RA_LL, r) = a;
+            if (c.ncta > 1) {
+                for (int q = 0; q < c.ncta; ++q) store_peer(c, m.RowAcc + (8 + c.rank) * R + r, q, a);
+            } else {
+                rowacc(RA_LL, r) = a;
+            }
+        }
+        if (c.ncta > 1) {
+            cluster_arrive(c);
+            cluster_wait(c);
+            for (int r = c.tid; r < R; r += c.nthreads) {
+                float a = 0.f;
+                for (int q = 0; q < c.ncta; ++q) a += rowacc(8 + q, r);
+                rowacc(RA_LL, r) = a;
+            }
         }
         c.sync();
     }
@@ -905,6 +1052,7 @@ struct Block {
         const int NS = P.NS;
         const sqair_outputs& o = J.out;
         const size_t trow = (size_t)t * P.rows;
+        if (c.rank != 0) { c.sync(); return; }                  // replicas hold identical values
         for (int i = c.tid; i < LDS(); i += c.nthreads) {
             const int s = i / R, r = i % R;
             if (!valid_row(r)) continue;
@@ -999,6 +1147,7 @@ struct Block {
     }
 
     SQ_DEV void run() {
+        ring_init(c, P);
         init_sequence();
         for (int t = 0; t < P.cfg.T; ++t) frame(t);
     }

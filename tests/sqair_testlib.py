@@ -99,18 +99,18 @@ def emu_lib():
         srcs = [os.path.join(d, 'emu.cpp'), os.path.join(ROOT, 'sqair_b200', 'csrc', 'sqair_device.cuh'),
                 os.path.join(ROOT, 'sqair_b200', 'csrc', 'sqair_core.h'), os.path.join(ROOT, 'include', 'sqair_b200.h')]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-            subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-Wno-unknown-pragmas',
+            subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-pthread', '-Wno-unknown-pragmas',
                                    '-o', so, srcs[0]])
         _emu = C.CDLL(so)
         _emu.emu_forward.argtypes = [C.POINTER(_capi.SqairCfg)] + [C.c_void_p] * 5 + \
-            [C.POINTER(_capi.SqairOutputs), C.c_int]
+            [C.POINTER(_capi.SqairOutputs), C.c_int, C.c_int]
         _emu.emu_forward.restype = C.c_int
-        _emu.emu_smem_floats.argtypes = [C.POINTER(_capi.SqairCfg), C.c_int]
+        _emu.emu_smem_floats.argtypes = [C.POINTER(_capi.SqairCfg), C.c_int, C.c_int]
         _emu.emu_smem_floats.restype = C.c_int
     return _emu
 
 
-def run_emu(cfg: O.Cfg, imgs, params, noise, R):
+def run_emu(cfg: O.Cfg, imgs, params, noise, R, cluster=1):
     ccfg = capi_cfg(cfg)
     flat = np.ascontiguousarray(O.flatten_params(params, cfg).numpy())
     shapes = _capi.output_shapes(ccfg)
@@ -121,6 +121,6 @@ def run_emu(cfg: O.Cfg, imgs, params, noise, R):
     imgs = np.ascontiguousarray(imgs, dtype=np.float32)
     nz = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in noise.items()}
     rc = emu_lib().emu_forward(C.byref(ccfg), flat.ctypes.data, imgs.ctypes.data, nz['eps_where'].ctypes.data,
-                               nz['eps_what'].ctypes.data, nz['u_pres'].ctypes.data, C.byref(so), R)
+                               nz['eps_what'].ctypes.data, nz['u_pres'].ctypes.data, C.byref(so), R, cluster)
     assert rc == 0, rc
     return outs

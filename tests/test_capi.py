@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
     # sizes implied by the header (all int32/float fields, 8-byte pointers)
     assert C.sizeof(_capi.SqairCfg) == 13 * 4 + 6 * 4 + 8 * 4
     assert C.sizeof(_capi.SqairOutputs) == 38 * 8
-    assert C.sizeof(_capi.SqairSizes) == 5 * 8 + 5 * 4 + 4      # + tail padding to 8
+    assert C.sizeof(_capi.SqairSizes) == 5 * 8 + 6 * 4
 
 
 def test_param_layout_matches_reference_listing():
@@ -60,7 +60,7 @@ def test_query_sizes_and_shapes():
     _lib()
     cfg = _capi.make_cfg(10, 32, 5, 4, 50, 50)
     s = _capi.query_sizes(cfg)
-    assert s.rows == 160 and s.n_ctas * s.rows_per_cta >= 160 and s.smem_bytes <= 232448
+    assert s.rows == 160 and s.n_ctas // s.cluster_size * s.rows_per_cta >= 160 and s.smem_bytes <= 232448
     assert s.eps_what_floats == 10 * 160 * 8 * 50 and s.u_pres_floats == 10 * 160 * 8
     shapes = _capi.output_shapes(cfg)
     assert shapes['what'] == (10, 160, 4, 50) and shapes['canvas'] == (10, 160, 50, 50)

@@ -7,22 +7,22 @@ import pytest
 import sqair_testlib as TL
 from oracle import sqair_oracle as O
 
-CASES = [
-    (dict(T=3, B=4, K=1, n=2), 2),
-    (dict(T=3, B=3, K=2, n=3), 4),
-    (dict(T=2, B=2, K=5, n=4), 5),
-    (dict(T=3, B=2, K=2, n=2, prior_type='rw'), 1),
-    (dict(T=3, B=2, K=2, n=2, prior_type='guided', disc_prior_type='geom'), 3),
-    (dict(T=2, B=2, K=1, n=2, rec_where_prior=False, masked_glimpse=False), 2),
-    (dict(T=2, B=2, K=2, n=6, H=64, W=64), 4),
+CASES = [      # (config, rows per cluster, blocks per cluster)
+    (dict(T=3, B=4, K=1, n=2), 2, 1),
+    (dict(T=3, B=3, K=2, n=3), 4, 2),
+    (dict(T=2, B=2, K=5, n=4), 5, 4),
+    (dict(T=3, B=2, K=2, n=2, prior_type='rw'), 1, 8),
+    (dict(T=3, B=2, K=2, n=2, prior_type='guided', disc_prior_type='geom'), 3, 4),
+    (dict(T=2, B=2, K=1, n=2, rec_where_prior=False, masked_glimpse=False), 2, 2),
+    (dict(T=2, B=2, K=2, n=6, H=64, W=64), 4, 4),
 ]
 
 
-@pytest.mark.parametrize('kw,R', CASES)
-def test_emulated_kernel_matches_oracle(kw, R):
+@pytest.mark.parametrize('kw,R,C', CASES)
+def test_emulated_kernel_matches_oracle(kw, R, C):
     cfg = O.Cfg(**kw)
     imgs, params, noise = TL.make_inputs(cfg)
     want, _ = TL.run_oracle(cfg, imgs, params, noise)
-    got = TL.run_emu(cfg, imgs, params, noise, R)
+    got = TL.run_emu(cfg, imgs, params, noise, R, cluster=C)
     bad = TL.compare_outputs(got, want)
     assert not bad, '\n'.join(bad)

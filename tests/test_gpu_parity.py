@@ -23,12 +23,15 @@ def _gpu():
     return ops, torch.device('cuda:0')
 
 
-def run_cuda(cfg, imgs, params, noise, rows_per_cta=None):
+def run_cuda(cfg, imgs, params, noise, rows_per_cta=None, cluster=None):
     ops, dev = _gpu()
     ccfg = TL.capi_cfg(cfg)
     old = os.environ.pop('SQAIR_ROWS_PER_CTA', None)
+    oldc = os.environ.pop('SQAIR_CLUSTER', None)
     if rows_per_cta:
         os.environ['SQAIR_ROWS_PER_CTA'] = str(rows_per_cta)
+    if cluster:
+        os.environ['SQAIR_CLUSTER'] = str(cluster)
     try:
         flat = O.flatten_params(params, cfg).to(dev)
         packed = ops.pack_params(ccfg, flat)
@@ -37,8 +40,11 @@ def run_cuda(cfg, imgs, params, noise, rows_per_cta=None):
         torch.cuda.synchronize()
     finally:
         os.environ.pop('SQAIR_ROWS_PER_CTA', None)
+        os.environ.pop('SQAIR_CLUSTER', None)
         if old is not None:
             os.environ['SQAIR_ROWS_PER_CTA'] = old
+        if oldc is not None:
+            os.environ['SQAIR_CLUSTER'] = oldc
     return {k: v.cpu().numpy() for k, v in out.items()}
 
 
@@ -63,13 +69,14 @@ def test_forward_parity(name):
     assert not bad, '\n'.join(bad)
 
 
-@pytest.mark.parametrize('R', [1, 2, 3, 4, 5])
-def test_rows_per_block_variants(R):
-    """Every instantiation of the persistent kernel, including row counts that do not divide."""
+@pytest.mark.parametrize('R,C', [(1, 1), (2, 1), (3, 2), (4, 2), (5, 4), (2, 4), (1, 8), (3, 8)])
+def test_launch_shape_variants(R, C):
+    """Every instantiation of the persistent kernel (rows per cluster R) and every cluster size C,
+    including row counts that do not divide."""
     cfg = O.Cfg(T=3, B=3, K=3, n=2)
     imgs, params, noise = TL.make_inputs(cfg)
     want, _ = TL.run_oracle(cfg, imgs, params, noise)
-    got = run_cuda(cfg, imgs, params, noise, rows_per_cta=R)
+    got = run_cuda(cfg, imgs, params, noise, rows_per_cta=R, cluster=C)
     bad = TL.compare_outputs(got, want)
     assert not bad, '\n'.join(bad)
 

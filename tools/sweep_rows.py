@@ -16,12 +16,15 @@ def main():
     noise = ops.fill_noise(cfg, 7, 0, device=dev)
     outs = ops.alloc_outputs(cfg, dev)
     res = {}
-    for R in (1, 2, 3, 4, 5, 8):
+    shapes = [(int(a), int(b)) for a, b in (x.split(':') for x in os.environ.get('SWEEP', '5:4,5:2,5:1,4:4,3:4,2:4,2:2,2:1,1:8,1:4,1:1').split(','))]
+    for R, C in shapes:
         os.environ['SQAIR_ROWS_PER_CTA'] = str(R)
+        os.environ['SQAIR_CLUSTER'] = str(C)
         try:
             s = _capi.query_sizes(cfg)
+            packed = ops.pack_params(cfg, flat)
         except Exception as e:
-            print('R=%d: %s' % (R, e)); continue
+            print('R=%d C=%d: %s' % (R, C, e)); continue
         for _ in range(3):
             ops.forward(cfg, packed, obs, noise, outs)
         torch.cuda.synchronize()
@@ -31,9 +34,9 @@ def main():
             ops.forward(cfg, packed, obs, noise, outs)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        res[R] = ms
-        print('R=%d ctas=%d smem=%d B: %.3f ms/step  %.0f frames/s' % (R, s.n_ctas, s.smem_bytes, ms, B * T / ms * 1e3), flush=True)
-    os.environ.pop('SQAIR_ROWS_PER_CTA', None)
+        res['%d:%d' % (R, C)] = ms
+        print('R=%d C=%d ctas=%d smem=%d B: %.3f ms/step  %.0f frames/s' % (R, C, s.n_ctas, s.smem_bytes, ms, B * T / ms * 1e3), flush=True)
+    os.environ.pop('SQAIR_ROWS_PER_CTA', None); os.environ.pop('SQAIR_CLUSTER', None)
     print(json.dumps(res))
 
 if __name__ == '__main__':
