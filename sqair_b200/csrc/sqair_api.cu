@@ -8,7 +8,11 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "sqair_device.cuh"
 
@@ -33,33 +37,58 @@ static int cuda_fail(cudaError_t e, const char* what) {
 // persistent sequence kernel: one cluster of C blocks per R rows, the whole T-frame recursion
 // ---------------------------------------------------------------------------------------------
 template <int R>
-__global__ void __launch_bounds__(NT) sqair_sequence_kernel(const __grid_constant__ Plan plan,
-                                                            const __grid_constant__ Job job) {
-    extern __shared__ __align__(128) float smem[];
+__global__ void __launch_bounds__(NT_LAUNCH) sqair_sequence_kernel(const __grid_constant__ Job job) {
+    const Plan& plan = c_plan;
     Ctx c;
-    c.tid = (int)threadIdx.x; c.nthreads = (int)blockDim.x; c.lane = (int)(threadIdx.x & 31); c.nlanes = 32;
-    c.warp = (int)(threadIdx.x >> 5); c.nwarps = (int)(blockDim.x >> 5);
-    c.sm = smem;
-    c.ncta = plan.C;
-    c.rank = plan.C > 1 ? (int)cluster_ctarank() : 0;
-    Block<R> blk(c, plan, job, (int)(blockIdx.x / plan.C) * R);
+#ifdef SQAIR_PROFILE
+    for (int i = 0; i < 8; ++i) c.prof[i] = 0;
+    c.t_last = clock64();
+#endif
+    Block<R> blk(c, job, (int)(blockIdx.x / plan.C) * R);
     blk.run();
     if (plan.C > 1) { cluster_arrive(c); cluster_wait(c); }      // no block exits while peers may still write to it
+#ifdef SQAIR_PROFILE
+    if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 32 * 7)) {
+        printf("[profile tid %d] cycles: wait_full %lld  accum %lld  partials+sync %lld  finish+stores %lld  barrierB %lld  between-dense %lld | fin:redsum %lld  fin:bias+act %lld\n",
+               (int)threadIdx.x, c.prof[0], c.prof[1], c.prof[2], c.prof[3], c.prof[4], c.prof[5], c.prof[6], c.prof[7]);
+    }
+#endif
 }
 
 static const int kRowChoices[] = {1, 2, 3, 4, 5};
-static const int kClusterChoices[] = {1, 2, 4, 8};
+static const int kClusterChoices[] = {1, 2, 3, 4, 8};
 static const int kSmemLimit = 232448;    // 227 KB opt-in shared memory per block on sm_100
+
+// The plan lives in __constant__ memory (descriptor reads are constant-bank loads).  It is re-uploaded only
+// when it changes; an upload waits for the previous launch, which may still be reading the old plan.
+static std::mutex g_plan_mutex;
+static Plan g_plan_uploaded;
+static bool g_plan_valid = false;
+static cudaEvent_t g_last_launch = nullptr;
+
+static int upload_plan(const Plan& plan, cudaStream_t st) {
+    if (g_plan_valid && memcmp(&g_plan_uploaded, &plan, sizeof(Plan)) == 0) return SQAIR_OK;
+    if (!g_last_launch) CUDA_TRY(cudaEventCreateWithFlags(&g_last_launch, cudaEventDisableTiming));
+    else CUDA_TRY(cudaEventSynchronize(g_last_launch));
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_plan, &plan, sizeof(Plan), 0, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));         // the host copy of `plan` may be a temporary
+    g_plan_uploaded = plan;
+    g_plan_valid = true;
+    return SQAIR_OK;
+}
 
 template <int R>
 static int launch_sequence(const Plan& plan, const Job& job, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    int rc = upload_plan(plan, st);
+    if (rc != SQAIR_OK) return rc;
     const int smem_bytes = plan.sm.total * (int)sizeof(float);
     CUDA_TRY(cudaFuncSetAttribute(sqair_sequence_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const int ncl = (plan.rows + R - 1) / R;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(ncl * plan.C);
-    cfg.blockDim = dim3(NT);
+    cfg.blockDim = dim3(NT_LAUNCH);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -69,7 +98,8 @@ static int launch_sequence(const Plan& plan, const Job& job, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = plan.C > 1 ? 1 : 0;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, sqair_sequence_kernel<R>, plan, job));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, sqair_sequence_kernel<R>, job));
+    CUDA_TRY(cudaEventRecord(g_last_launch, st));
     return SQAIR_OK;
 }
 
@@ -89,7 +119,35 @@ static int env_int(const char* name) {
     return e ? atoi(e) : 0;
 }
 
+static std::string choose_shape_uncached(const sqair_cfg& c, const std::vector<ParamEntry>& tab, Shape& out);
+
+// choose_shape is called by every entry point; its result only depends on the configuration and the tuning
+// environment variables, so the last few results are cached (building ~25 candidate plans costs ~1 ms of host time).
+struct ShapeKey {
+    sqair_cfg cfg;
+    int env[4];
+    bool operator==(const ShapeKey& o) const { return memcmp(this, &o, sizeof(ShapeKey)) == 0; }
+};
+static std::mutex g_shape_mutex;
+static std::vector<std::pair<ShapeKey, std::shared_ptr<Shape>>> g_shape_cache;
+
 static std::string choose_shape(const sqair_cfg& c, const std::vector<ParamEntry>& tab, Shape& out) {
+    ShapeKey key;
+    memset(&key, 0, sizeof(key));
+    key.cfg = c;
+    key.env[0] = env_int("SQAIR_ROWS_PER_CTA"); key.env[1] = env_int("SQAIR_CLUSTER");
+    key.env[2] = env_int("SQAIR_STAGE_KB"); key.env[3] = env_int("SQAIR_NSTAGE");
+    std::lock_guard<std::mutex> lock(g_shape_mutex);
+    for (auto& kv : g_shape_cache)
+        if (kv.first == key) { out = *kv.second; return ""; }
+    std::string e = choose_shape_uncached(c, tab, out);
+    if (!e.empty()) return e;
+    if (g_shape_cache.size() >= 16) g_shape_cache.erase(g_shape_cache.begin());
+    g_shape_cache.emplace_back(key, std::make_shared<Shape>(out));
+    return "";
+}
+
+static std::string choose_shape_uncached(const sqair_cfg& c, const std::vector<ParamEntry>& tab, Shape& out) {
     const int rows = c.B * c.K;
     const int fR = env_int("SQAIR_ROWS_PER_CTA"), fC = env_int("SQAIR_CLUSTER");
     const double W = 44e6, bw_sm = 100e9, bw_l2 = 8e12, mac_row = 11e6, fma = 128 * 1.9e9 * 0.5;
@@ -101,11 +159,14 @@ static std::string choose_shape(const sqair_cfg& c, const std::vector<ParamEntry
             if (fR && R != fR) continue;
             if (R > rows && R != 1) continue;
             Shape s;
-            std::string e = build_plan(c, R, C, s.plan, tab, s.pieces, &s.packed_total);
+            int stage_kb = env_int("SQAIR_STAGE_KB"), nstage = env_int("SQAIR_NSTAGE");
+            if (!stage_kb) stage_kb = 16;
+            if (!nstage) nstage = 3;
+            std::string e = build_plan(c, R, C, s.plan, tab, s.pieces, &s.packed_total, stage_kb * 256, nstage);
             if (!e.empty()) { err = e; continue; }
             if (s.plan.sm.total * (int)sizeof(float) > kSmemLimit) continue;
             const int ncl = (rows + R - 1) / R;
-            const int max_blocks = C == 1 ? 148 : (C == 2 ? 148 : (C == 4 ? 132 : 128));
+            const int max_blocks = C <= 2 ? 148 : (C == 8 ? 128 : 132);
             double waves = (double)((ncl * C + max_blocks - 1) / max_blocks);
             double t = waves * (W / C / bw_sm + R * mac_row / C / fma) + ncl * W / bw_l2 + (C > 1 ? 40e-6 : 0.0);
             if (t < best) { best = t; s.R = R; s.C = C; out = s; }
@@ -141,7 +202,7 @@ struct PieceDev {
 };
 struct PieceTab {
     int n;
-    PieceDev p[96];
+    PieceDev p[160];
 };
 
 __global__ void pack_panels_kernel(const __grid_constant__ PieceTab tab, const float* __restrict__ src,
@@ -151,8 +212,9 @@ __global__ void pack_panels_kernel(const __grid_constant__ PieceTab tab, const f
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int k = i / pc.N, n = i - k * pc.N;
         const int vrow = pc.vrow0 + k, vcol = pc.vcol0 + n, panel = vcol / pc.Nc;
-        dst[(size_t)pc.w_off + (size_t)panel * pc.Ktot * pc.Nc + (size_t)vrow * pc.Nc + (vcol - panel * pc.Nc)] =
-            src[(size_t)pc.src_off + (size_t)k * pc.src_ld + n];
+        // accumulate (the buffer was zeroed): a bias row may be the sum of two bias vectors
+        atomicAdd(&dst[(size_t)pc.w_off + (size_t)panel * pc.Ktot * pc.Nc + (size_t)vrow * pc.Nc + (vcol - panel * pc.Nc)],
+                  src[(size_t)pc.src_off + (size_t)k * pc.src_ld + n]);
     }
 }
 
@@ -423,7 +485,7 @@ int sqair_pack_params(const sqair_cfg* cfg, const float* params, float* packed, 
     Shape sh;
     e = choose_shape(*cfg, tab, sh);
     if (!e.empty()) return fail(SQAIR_EUNSUPPORTED, e);
-    if (tab.size() > 128 || sh.pieces.size() > 96) return fail(SQAIR_EUNSUPPORTED, "too many variables");
+    if (tab.size() > 128 || sh.pieces.size() > 160) return fail(SQAIR_EUNSUPPORTED, "too many variables");
     PackTab pt;
     memset(&pt, 0, sizeof(pt));
     pt.n = (int)tab.size();
@@ -445,6 +507,19 @@ int sqair_pack_params(const sqair_cfg* cfg, const float* params, float* packed, 
     CUDA_TRY(cudaGetLastError());
     pack_panels_kernel<<<dim3(64, qt.n), 256, 0, st>>>(qt, params, packed);
     CUDA_TRY(cudaGetLastError());
+    // layer table (staged into shared memory one call ahead by the kernel)
+    std::vector<int32_t> ltab((size_t)L_COUNT * DESC_WORDS, 0);
+    for (int i = 0; i < L_COUNT; ++i) memcpy(&ltab[(size_t)i * DESC_WORDS], &sh.plan.L[i], sizeof(Layer));
+    CUDA_TRY(cudaMemcpyAsync(packed + sh.plan.ltab_off, ltab.data(), ltab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    for (int r = 0; r < sh.C; ++r) {
+        std::vector<uint32_t> ct;
+        chunk_table(sh.plan, r, ct);
+        if (!ct.empty())
+            CUDA_TRY(cudaMemcpyAsync(packed + sh.plan.ctab_off + (size_t)r * sh.plan.ctab_stride, ct.data(), ct.size() * sizeof(uint32_t),
+                                     cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
     return SQAIR_OK;
 }
 
@@ -470,7 +545,7 @@ int sqair_forward(const sqair_cfg* cfg, const float* packed_params, const float*
     Shape sh;
     e = choose_shape(*cfg, tab, sh);
     if (!e.empty()) return fail(SQAIR_EUNSUPPORTED, e);
-    Job job{packed_params, obs, eps_where, eps_what, u_pres, *out};
+    Job job{packed_params, obs, eps_where, eps_what, u_pres, *out, env_int("SQAIR_DEBUG_FLAGS")};
     cudaStream_t st = (cudaStream_t)stream;
     switch (sh.R) {
         case 1: return launch_sequence<1>(sh.plan, job, st);

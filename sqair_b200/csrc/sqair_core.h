@@ -28,14 +28,17 @@
 
 namespace sq {
 
-constexpr int MAXSEG = 5;
+constexpr int MAXSEG = 6;
 constexpr int MAXHEAD = 3;
-constexpr int NT = 256;          // threads per block
+constexpr int NT = 256;          // compute threads per block
+constexpr int NT_LAUNCH = 288;   // + one producer warp that streams the weights
 constexpr int MAX_KS = 16;       // max k-slices of a dense layer
 constexpr int MAX_SLOTS = 8;
 constexpr int MAXC = 8;          // max cluster size (portable limit)
 constexpr int MAXSEQ = 400;      // dense calls per frame
-constexpr int NSTAGE = 3;        // weight-ring stages
+constexpr int MAX_NSTAGE = 12;   // max weight-ring stages
+constexpr int MAXPIECE = 24;      // GEMV pieces (chunk rows x segment) per dense layer
+constexpr int DESC_WORDS = 288;  // >= sizeof(Layer) / 4, multiple of 4, <= NT_LAUNCH (one word per thread when staging)
 
 enum Act { ACT_NONE = 0, ACT_ELU = 1, ACT_SIGMOID = 2, ACT_TANH = 3, ACT_SOFTPLUS = 4 };
 enum SegKind { SEG_SMEM = 0, SEG_IMAGE = 1 };
@@ -57,6 +60,20 @@ struct Head {
     int out_off, out_sstride, out_ld;
 };
 
+// One GEMV piece: `n` consecutive rows of one segment that sit in one ring chunk (repeated `rep` times for the
+// uniform full chunks of a long single segment).  Built on the host so that the device loop has no index logic.
+enum { PIECE_FIRST = 1, PIECE_LAST = 2, PIECE_IMAGE = 4 };
+struct GemvPiece {
+    int row0;        // first row in the layer's virtual matrix (used by the host emulator)
+    int w_rel;       // float offset of the piece inside its ring stage
+    int x_off;       // shared-memory offset of the piece's first input row (pixel index for PIECE_IMAGE)
+    int x_sstride;   // added per slot
+    int ld;          // floats between consecutive input rows
+    int n;           // rows
+    int flags;       // PIECE_FIRST: wait for the chunk before; PIECE_LAST: release the chunk after
+    int rep;         // repeat count; each repeat advances row0 by n, x_off by n*ld (pixel index by n)
+};
+
 struct Layer {
     int nseg, nhead;
     Seg seg[MAXSEG];
@@ -68,6 +85,11 @@ struct Layer {
     int npanel;    // panels with real columns (blocks with rank >= npanel idle in this layer); 1 if !split
     int w_off;     // packed-parameter offset of panel 0; panel p at w_off + p*Ktot*Nc
     int rpc;       // weight rows per ring chunk
+    int ks;        // k-slices of the thread mapping (thread = slice * Nc/4 + column group)
+    int gc_magic;  // ceil(2^32 / (Nc/4)): slice = umulhi(tid, gc_magic)
+    int nchunk;    // ring chunks per call
+    int npiece;
+    GemvPiece piece[MAXPIECE];
 };
 
 enum LayerId {
@@ -84,8 +106,10 @@ struct RecF {
 
 // Shared-memory layout (float offsets from the dynamic shared memory base).  [f][S][R] = feature-major.
 struct Smem {
-    int Bar;      // 2*NSTAGE mbarriers (8 bytes each): full[NSTAGE], empty[NSTAGE]
-    int Ring;     // NSTAGE * stage_floats weight stages (128-byte aligned)
+    int Ctl;      // [16] ints: ring position / call counters shared by the block (device only)
+    int Desc;     // [2][DESC_WORDS] staged descriptors of the current / next dense call
+    int Bar;      // 2*nstage mbarriers (8 bytes each): full[nstage], empty[nstage]
+    int Ring;     // nstage * stage_floats weight stages (128-byte aligned)
     int Z;        // [nw+6][NS][R]: what, where(4), pres, plogit     (latents of the previous frame)
     int Ids;      // [NS][R]
     int LastId;   // [R]
@@ -114,13 +138,14 @@ struct Smem {
     int Rns;      // [8][R]
     int Hsp;      // [10][R]
     int Spl;      // [n+1][R]
+    int Ones;     // [R] constant 1 (input of the bias row of every dense layer)
     int Coords;   // [4][R]
     int Dgl;      // [g][NS][R] decoded glimpses (aliases the per-slot scratch)
     int Red;      // k-slice partial sums
     int RowAcc;   // [16][R] per-row scalars
     int Perm;     // [2NS][R] compaction order (as floats)
     int total;    // floats
-    int red_floats, stage_floats;
+    int red_floats, stage_floats, nstage;
 };
 
 // Packed-parameter offsets of everything that is not a dense-layer weight.
@@ -135,8 +160,10 @@ struct POff {
 
 struct Plan {
     sqair_cfg cfg;
-    int R, C, NS, rows, nw, nh, g, P, LDS;   // LDS = NS*R; C = cluster size
+    int R, C, NS, rows, nw, nh, g, PX, LDS;  // LDS = NS*R; C = cluster size; PX = H*W
     int nseq;                                 // dense calls per frame
+    int ltab_off;                             // packed-parameter offset of the layer table (L_COUNT x DESC_WORDS words)
+    int ctab_off, ctab_stride, ctab_n[MAXC];  // per-rank chunk tables {offset, floats} of one frame; entries per rank
     RecF rec;
     Smem sm;
     POff po;
@@ -302,6 +329,12 @@ struct PlanBuilder {
         l.Ktot += K;
         return l.nseg++;
     }
+    // canonical offset of a bias vector (name + "/b" style variable given by packed offset lookup is not enough:
+    // packing reads the canonical buffer), -1 = none
+    int64_t canon(const std::string& name) {
+        const ParamEntry* e = find(name);
+        return e ? e->offset : -1;
+    }
     int head(Layer& l, int N, int b_off, int act, int out_off, int out_ld, int out_sstride = 0) {
         Head& h = l.head[l.nhead];
         h.col0 = l.Ntot; h.N = N; h.b_off = b_off; h.b2_off = -1; h.act = act; h.scale = 1.f; h.add = 0.f;
@@ -330,10 +363,37 @@ struct PlanBuilder {
         int r = row0;
         for (int s = first_seg; s <= last_seg; ++s) { w(id, s, h, name, r); r += l.seg[s].K; }
     }
-    // decide the column split and reserve the packed panels
+    // packed offset of (part of) a variable -> canonical offset
+    int64_t packed_to_canonical(int poff) {
+        for (const auto& e : tab)
+            if (poff >= e.packed_offset && poff < e.packed_offset + e.count) return e.offset + (poff - e.packed_offset);
+        err = "bias offset not inside a variable";
+        return 0;
+    }
+    // Finalise a layer: fold the biases into the GEMV (one extra weight row against the constant-1 input),
+    // decide the column split, reserve the packed panels and build the GEMV piece table.
     void finish(int id) {
         Layer& l = p.L[id];
         const int C = p.C;
+        bool any_bias = false;
+        for (int h = 0; h < l.nhead; ++h) any_bias |= (l.head[h].b_off >= 0 || l.head[h].b2_off >= 0);
+        if (any_bias) {
+            if (l.nseg >= MAXSEG) { err = "too many segments"; return; }
+            const int brow = l.Ktot;
+            seg(l, p.sm.Ones, p.R, 1);
+            for (int h = 0; h < l.nhead; ++h) {
+                int offs[2] = {l.head[h].b_off, l.head[h].b2_off};
+                for (int q = 0; q < 2; ++q) {
+                    if (offs[q] < 0) continue;
+                    Piece pc;
+                    pc.layer = id; pc.vrow0 = brow; pc.vcol0 = l.head[h].col0; pc.K = 1; pc.N = l.head[h].N;
+                    pc.src_off = packed_to_canonical(offs[q]);
+                    pc.src_ld = l.head[h].N;
+                    pieces.push_back(pc);
+                }
+                l.head[h].b_off = l.head[h].b2_off = -1;
+            }
+        }
         int per = (l.Ntot + C - 1) / C;
         if (C > 1 && per >= 16) {
             l.split = 1;
@@ -348,8 +408,47 @@ struct PlanBuilder {
         wcursor += (int64_t)l.npanel * l.Ktot * l.Nc;
         wcursor = (wcursor + 31) / 32 * 32;
         l.rpc = p.sm.stage_floats / l.Nc;
-        if (l.rpc < 1) err = "layer too wide for a ring stage";
-        if (l.Nc / 4 > NT) err = "layer too wide for the thread block";
+        if (l.rpc < 1) { err = "layer too wide for a ring stage"; return; }
+        if (l.Nc / 4 > NT) { err = "layer too wide for the thread block"; return; }
+        const int Gc = l.Nc / 4;
+        l.ks = NT / Gc;
+        if (l.ks > MAX_KS) l.ks = MAX_KS;
+        l.gc_magic = (int)(((1ull << 32) + Gc - 1) / Gc);
+        l.nchunk = (l.Ktot + l.rpc - 1) / l.rpc;
+        // piece table
+        l.npiece = 0;
+        int si = 0, seg0 = 0;
+        for (int r0 = 0; r0 < l.Ktot; r0 += l.rpc) {
+            const int r1 = (r0 + l.rpc < l.Ktot) ? (r0 + l.rpc) : l.Ktot;
+            int lo = r0;
+            while (lo < r1) {
+                if (lo >= seg0 + l.seg[si].K) { seg0 += l.seg[si].K; ++si; continue; }
+                const Seg& S = l.seg[si];
+                const int hi = (seg0 + S.K < r1) ? (seg0 + S.K) : r1;
+                GemvPiece g;
+                g.row0 = lo; g.w_rel = (lo - r0) * l.Nc; g.n = hi - lo; g.rep = 1;
+                g.flags = (lo == r0 ? PIECE_FIRST : 0) | (hi == r1 ? PIECE_LAST : 0) | (S.kind == SEG_IMAGE ? PIECE_IMAGE : 0);
+                g.x_sstride = S.x_sstride; g.ld = S.ld;
+                g.x_off = (S.kind == SEG_IMAGE) ? (lo - seg0) : (S.x_off + (lo - seg0) * S.ld);
+                // merge with the previous piece when both are whole chunks of the same segment in sequence
+                bool merged = false;
+                if (l.npiece > 0) {
+                    GemvPiece& q = l.piece[l.npiece - 1];
+                    const int step = (S.kind == SEG_IMAGE) ? q.n : q.n * q.ld;
+                    if (q.flags == g.flags && (g.flags & PIECE_FIRST) && (g.flags & PIECE_LAST) && q.n == g.n && q.ld == g.ld &&
+                        q.x_sstride == g.x_sstride && q.w_rel == 0 && g.w_rel == 0 && g.row0 == q.row0 + q.rep * q.n &&
+                        g.x_off == q.x_off + q.rep * step) {
+                        ++q.rep;
+                        merged = true;
+                    }
+                }
+                if (!merged) {
+                    if (l.npiece >= MAXPIECE) { err = "too many GEMV pieces in a layer"; return; }
+                    l.piece[l.npiece++] = g;
+                }
+                lo = hi;
+            }
+        }
     }
 };
 
@@ -385,15 +484,31 @@ inline std::vector<int> frame_sequence(const sqair_cfg& c) {
     return q;
 }
 
+// Weight chunks of one frame for block `rank` of the cluster, in consumption order: for every dense call with a
+// panel for this rank, consecutive blocks of <= rpc rows of the panel (chunks span segment boundaries).
+inline void chunk_table(const Plan& p, int rank, std::vector<uint32_t>& tab) {
+    tab.clear();
+    for (int i = 0; i < p.nseq; ++i) {
+        const Layer& L = p.L[p.seq[i]];
+        if (L.split && rank >= L.npanel) continue;
+        const int64_t base = (int64_t)L.w_off + (int64_t)(L.split ? rank : 0) * L.Ktot * L.Nc;
+        for (int r0 = 0; r0 < L.Ktot; r0 += L.rpc) {
+            const int rows = (L.Ktot - r0 < L.rpc) ? (L.Ktot - r0) : L.rpc;
+            tab.push_back((uint32_t)(base + (int64_t)r0 * L.Nc));
+            tab.push_back((uint32_t)(rows * L.Nc));
+        }
+    }
+}
+
 // Builds the plan for R rows per cluster of C blocks.  Returns "" on success, else an error message.
 // `pieces` receives the packing table; *packed_total the floats of the packed parameter buffer.
 inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const std::vector<ParamEntry>& tab,
-                              std::vector<Piece>& pieces, int64_t* packed_total, int stage_floats = 4096) {
+                              std::vector<Piece>& pieces, int64_t* packed_total, int stage_floats = 4096, int nstage = 3) {
     memset(&p, 0, sizeof(p));
     pieces.clear();
     p.cfg = c;
     const int NS = c.n, nw = c.n_what, nh = c.n_hidden, g = c.G * c.G, P = c.H * c.W, s = nh / 2;
-    p.R = R; p.C = C; p.NS = NS; p.rows = c.B * c.K; p.nw = nw; p.nh = nh; p.g = g; p.P = P; p.LDS = NS * R;
+    p.R = R; p.C = C; p.NS = NS; p.rows = c.B * c.K; p.nw = nw; p.nh = nh; p.g = g; p.PX = P; p.LDS = NS * R;
     RecF& rf = p.rec;
     rf.what = 0; rf.where = nw; rf.pres = nw + 4; rf.what_loc = nw + 5; rf.what_scale = 2 * nw + 5;
     rf.where_loc = 3 * nw + 5; rf.where_scale = 3 * nw + 9; rf.prob = 3 * nw + 13; rf.logit = 3 * nw + 14;
@@ -402,9 +517,13 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
     PlanBuilder B(p, tab, pieces);
     Smem& m = p.sm;
     m.stage_floats = stage_floats;
+    m.nstage = nstage;
+    if (nstage < 2 || nstage > MAX_NSTAGE) return "ring stages must be in [2, 12]";
     const int LDS = NS * R, LDE = (NS + 1) * R;
-    m.Bar = B.alloc(2 * 2 * NSTAGE, 4);                 // 8-byte barriers
-    m.Ring = B.alloc(NSTAGE * stage_floats, 32);
+    m.Bar = B.alloc(2 * 2 * nstage, 4);                 // 8-byte barriers
+    m.Ctl = B.alloc(16);
+    m.Desc = B.alloc(2 * DESC_WORDS);
+    m.Ring = B.alloc(nstage * stage_floats, 32);
     m.Z = B.alloc((nw + 6) * LDS);
     m.Ids = B.alloc(LDS);
     m.LastId = B.alloc(R);
@@ -433,6 +552,7 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
     m.Rns = B.alloc(8 * R);
     m.Hsp = B.alloc(10 * R);
     m.Spl = B.alloc((NS + 1) * R);
+    m.Ones = B.alloc(R);
     m.Coords = B.alloc(4 * R);
     m.RowAcc = B.alloc(16 * R);
     m.Perm = B.alloc(2 * NS * R);
@@ -718,7 +838,7 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
         int r = dense_ks(p.L[i].Nc, NT) * p.L[i].Nc * R;
         if (r > red) red = r;
     }
-    if (red < 8 * R) red = 8 * R;                        // also used by the block reduction of the likelihood
+    if (red < 16 * R) red = 16 * R;                        // also used by the block reduction of the likelihood
     m.red_floats = red;
     m.Red = B.alloc(red);
     m.total = B.cursor;
@@ -727,6 +847,26 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
     if ((int)q.size() > MAXSEQ) return "too many dense calls per frame";
     p.nseq = (int)q.size();
     for (size_t i = 0; i < q.size(); ++i) p.seq[i] = (unsigned char)q[i];
+    static_assert(sizeof(Layer) <= DESC_WORDS * 4, "DESC_WORDS too small");
+    p.ltab_off = (int)((B.wcursor + 31) / 32 * 32);
+    B.wcursor = p.ltab_off + (int64_t)L_COUNT * DESC_WORDS;
+    // per-rank chunk tables
+    p.nseq = (int)frame_sequence(c).size();
+    {
+        std::vector<int> q2 = frame_sequence(c);
+        if ((int)q2.size() > MAXSEQ) return "too many dense calls per frame";
+        for (size_t i = 0; i < q2.size(); ++i) p.seq[i] = (unsigned char)q2[i];
+        int mx = 0;
+        std::vector<uint32_t> t;
+        for (int r = 0; r < C; ++r) {
+            chunk_table(p, r, t);
+            p.ctab_n[r] = (int)t.size() / 2;
+            if ((int)t.size() > mx) mx = (int)t.size();
+        }
+        p.ctab_off = (int)((B.wcursor + 31) / 32 * 32);
+        p.ctab_stride = (mx + 31) / 32 * 32;
+        B.wcursor = p.ctab_off + (int64_t)C * p.ctab_stride;
+    }
     if (packed_total) *packed_total = (B.wcursor + 31) / 32 * 32 + 32;
     return B.err;
 }

@@ -30,6 +30,21 @@
 
 namespace sq {
 
+// Address spaces.  On the device the dynamic shared memory and the plan are referenced through their
+// own symbols so that the compiler emits LDS/STS and constant-bank loads (a pointer carried in a struct
+// would degrade every access to a generic load with 64-bit address arithmetic).
+#ifdef SQAIR_HOST_EMU
+#define SQ_SM c.sm
+#define SQ_PLAN (*c.plan)
+#define SQ_PLAN_OF(ctx) (*(ctx).plan)
+#else
+extern __shared__ __align__(128) float g_smem[];
+__constant__ Plan c_plan;
+#define SQ_SM g_smem
+#define SQ_PLAN c_plan
+#define SQ_PLAN_OF(ctx) c_plan
+#endif
+
 #ifdef SQAIR_HOST_EMU
 // split-phase reusable barrier for the emulated cluster (one host thread per block)
 struct EmuClusterBarrier {
@@ -41,17 +56,43 @@ struct EmuClusterBarrier {
 // Per-thread view of the block: indices, shared memory, position in the cluster and the state of
 // the weight ring (identical in all threads of a block; advanced deterministically).
 struct Ctx {
-    int tid, nthreads, lane, nlanes, warp, nwarps;
-    float* sm;
-    int rank, ncta;          // block rank in its cluster, cluster size
-    int cons;                // weight chunks consumed so far by this block
-    int issued;              // weight chunks issued so far (thread 0 is the producer)
-    int p_t, p_i, p_s, p_c, p_row;   // producer cursor: frame, call index, segment, chunk in segment, row in layer
-    int call_idx;            // dense calls executed in the current frame
 #ifdef SQAIR_HOST_EMU
+    int tid_, nthreads_, lane_, nlanes_, warp_, nwarps_, ncompute_, rank_, ncta_;
+    float* sm;               // this block's "shared memory"
+    const Plan* plan;
     float** peers;           // shared memory of every block of the cluster
     EmuClusterBarrier* cb;
     long cb_gen;
+    int tid() const { return tid_; }
+    int nthreads() const { return nthreads_; }
+    int lane() const { return lane_; }
+    int nlanes() const { return nlanes_; }
+    int warp() const { return warp_; }
+    int nwarps() const { return nwarps_; }
+    int ncompute() const { return ncompute_; }
+    int rank() const { return rank_; }
+    int ncta() const { return ncta_; }
+#else
+    // Immutable coordinates come from special registers (this struct's address escapes into the non-inlined
+    // dense(), so anything stored here lives in local memory).
+    SQ_DEV int tid() const { return (int)threadIdx.x; }
+    SQ_DEV int nthreads() const { return (int)blockDim.x; }
+    SQ_DEV int lane() const { return (int)(threadIdx.x & 31); }
+    SQ_DEV int nlanes() const { return 32; }
+    SQ_DEV int warp() const { return (int)(threadIdx.x >> 5); }
+    SQ_DEV int nwarps() const { return (int)(blockDim.x >> 5); }
+    SQ_DEV int ncompute() const { return NT; }
+    SQ_DEV int rank() const { uint32_t r; asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return (int)r; }
+    SQ_DEV int ncta() const { uint32_t r; asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return (int)r; }
+#endif
+    // Ring position / call counters.  Host emulation keeps them here; on the device they live in the shared-memory
+    // words Smem::Ctl (CTL_*), read once per dense call and written back by one thread, so that dense() never
+    // touches local memory.
+    int cons;                // weight chunks consumed so far by this block
+    int call_idx;            // dense calls executed in the current frame
+#if defined(SQAIR_PROFILE)
+    long long prof[8];       // cycle counters
+    long long t_last;
 #endif
     SQ_DEV void sync() const {
 #ifndef SQAIR_HOST_EMU
@@ -81,6 +122,16 @@ SQ_DEV bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time when the phase is not complete)
+SQ_DEV bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 SQ_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
@@ -98,6 +149,8 @@ SQ_DEV void st_cluster_f32(uint32_t local_addr, int rank, float v) {
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
 #endif
+
+enum { CTL_CONS = 0, CTL_STAGE, CTL_PHASE, CTL_CALL, CTL_DESC, CTL_ISSUED, CTL_PT, CTL_PI, CTL_POFF, CTL_PNFL };
 
 // cluster barrier, split phase: arrive (release) ... wait (acquire)
 SQ_DEV void cluster_arrive(Ctx& c) {
@@ -120,9 +173,15 @@ SQ_DEV void store_peer(Ctx& c, int off, int rank, float v) {
 #ifdef SQAIR_HOST_EMU
     c.peers[rank][off] = v;
 #else
-    st_cluster_f32(smem_u32(c.sm + off), rank, v);
+    st_cluster_f32(smem_u32(SQ_SM + off), rank, v);
 #endif
 }
+
+#if defined(SQAIR_PROFILE) && !defined(SQAIR_HOST_EMU)
+#define SQ_TICK(c, slot) do { long long t_ = clock64(); (c).prof[slot] += t_ - (c).t_last; (c).t_last = t_; } while (0)
+#else
+#define SQ_TICK(c, slot) do { } while (0)
+#endif
 
 SQ_DEV float warp_sum(float v) {
 #ifndef SQAIR_HOST_EMU
@@ -187,74 +246,81 @@ struct Job {
     const float* eps_what;   // [T][rows][2n][nw]
     const float* u_pres;     // [T][rows][2n]
     sqair_outputs out;
+    int debug_flags;         // tuning experiments only: 1 = skip the GEMV math, 2 = skip the weight ring (garbage results)
 };
 
 // ---------------------------------------------------------------------------------------------
 // Weight ring.  Chunks = consecutive row blocks (<= rpc rows, never straddling a segment) of this
 // block's panel of each layer, in program order (Plan::seq repeated every frame).  Thread 0 issues
-// `cp.async.bulk` copies into NSTAGE stages as far ahead as stages are free; all threads wait on the
+// `cp.async.bulk` copies into P.sm.nstage stages as far ahead as stages are free; all threads wait on the
 // stage's "full" mbarrier before reading and every warp arrives on its "empty" mbarrier afterwards.
 // ---------------------------------------------------------------------------------------------
 SQ_DEV bool layer_has_work(const Layer& L, int rank) { return !L.split || rank < L.npanel; }
-SQ_DEV const float* panel_ptr(const Plan& P, const Layer& L, const float* prm, int rank) {
+SQ_DEV const float* panel_ptr(const Layer& L, const float* prm, int rank) {
     return prm + L.w_off + (size_t)(L.split ? rank : 0) * L.Ktot * L.Nc;
 }
 
 #ifndef SQAIR_HOST_EMU
-SQ_DEV void prod_skip_idle(Ctx& c, const Plan& P) {
-    while (c.p_t < P.cfg.T && !layer_has_work(P.L[P.seq[c.p_i]], c.rank)) {
-        if (++c.p_i >= P.nseq) { c.p_i = 0; ++c.p_t; }
-    }
+// Producer cursor, copied out of Ctx into registers for the duration of a dense call.
+struct ProdCur {
+    int issued, p_t, p_i, p_n;
+    uint32_t p_off, p_nfl;
+    const float* p_tab;
+};
+// issue the next chunk of this block's flat chunk table (one frame's chunks, repeated every frame)
+SQ_DEV void prod_issue(ProdCur& q, const float* prm, uint32_t bar, uint32_t ring, int ns, int stage_bytes) {
+    const int stage = q.issued % ns;
+    mbar_expect_tx(bar + 8u * stage, q.p_nfl * 4u);
+    bulk_g2s(ring + (uint32_t)(stage * stage_bytes), prm + q.p_off, q.p_nfl * 4u, bar + 8u * stage);
+    ++q.issued;
+    if (++q.p_i >= q.p_n) { q.p_i = 0; ++q.p_t; }
+    // fetch the following entry now; it is needed only at the next issue
+    const uint2 e = __ldg(reinterpret_cast<const uint2*>(q.p_tab) + q.p_i);
+    q.p_off = e.x; q.p_nfl = e.y;
 }
-SQ_DEV void prod_issue(Ctx& c, const Plan& P, const float* prm) {
-    const Layer& L = P.L[P.seq[c.p_i]];
-    const Seg& S = L.seg[c.p_s];
-    int rows = S.K - c.p_c * L.rpc;
-    if (rows > L.rpc) rows = L.rpc;
-    const float* src = panel_ptr(P, L, prm, c.rank) + (size_t)(c.p_row + c.p_c * L.rpc) * L.Nc;
-    const uint32_t bytes = (uint32_t)(rows * L.Nc) * 4u;
-    const int stage = c.issued % NSTAGE;
-    const uint32_t bar = smem_u32(c.sm + P.sm.Bar);
-    mbar_expect_tx(bar + 8u * stage, bytes);
-    bulk_g2s(smem_u32(c.sm + P.sm.Ring + stage * P.sm.stage_floats), src, bytes, bar + 8u * stage);
-    ++c.issued;
-    // advance the cursor
-    if ((c.p_c + 1) * L.rpc < S.K) { ++c.p_c; return; }
-    c.p_c = 0;
-    c.p_row += S.K;
-    if (++c.p_s < L.nseg) return;
-    c.p_s = 0; c.p_row = 0;
-    if (++c.p_i >= P.nseq) { c.p_i = 0; ++c.p_t; }
-    prod_skip_idle(c, P);
-}
-// thread 0: make sure chunk `need` is in flight, then run ahead while stages are free
-SQ_DEV void prod_fill(Ctx& c, const Plan& P, const float* prm, int need) {
-    if (c.tid != 0) return;
-    const uint32_t ebar = smem_u32(c.sm + P.sm.Bar) + 8u * NSTAGE;
-    while (c.issued <= need) {
-        mbar_wait(ebar + 8u * (c.issued % NSTAGE), ((c.issued / NSTAGE) & 1) ^ 1);
-        prod_issue(c, P, prm);
+// Producer warp, during one dense call: keep every free stage refilled (chunks of this and the following
+// layers, in program order) until the compute warps have consumed the last chunk of this layer.
+SQ_DEV void prod_run(Ctx& c, const float* prm, bool work, int last_chunk) {
+    const Plan& P = SQ_PLAN;
+    if (c.lane() == 0) {
+        int* ctl = reinterpret_cast<int*>(SQ_SM + P.sm.Ctl);
+        ProdCur q{ctl[CTL_ISSUED], ctl[CTL_PT], ctl[CTL_PI], P.ctab_n[c.rank()], (uint32_t)ctl[CTL_POFF], (uint32_t)ctl[CTL_PNFL],
+                  prm + P.ctab_off + c.rank() * P.ctab_stride};
+        const uint32_t bar = smem_u32(SQ_SM + P.sm.Bar), ring = smem_u32(SQ_SM + P.sm.Ring);
+        const int ns = P.sm.nstage, T = P.cfg.T, stage_bytes = P.sm.stage_floats * 4;
+        const uint32_t ebar = bar + 8u * ns;
+        while (true) {
+            while (q.p_t < T && q.p_n > 0 && mbar_test_wait(ebar + 8u * (q.issued % ns), ((q.issued / ns) & 1) ^ 1))
+                prod_issue(q, prm, bar, ring, ns, stage_bytes);
+            // done once the layer's last chunk has been issued AND released by every compute warp (the parity probe
+            // alone would also succeed before that stage was even refilled for this chunk)
+            if (!work || (q.issued > last_chunk && mbar_test_wait(ebar + 8u * (last_chunk % ns), (last_chunk / ns) & 1))) break;
+        }
+        ctl[CTL_ISSUED] = q.issued; ctl[CTL_PT] = q.p_t; ctl[CTL_PI] = q.p_i; ctl[CTL_POFF] = (int)q.p_off; ctl[CTL_PNFL] = (int)q.p_nfl;
     }
-    while (c.issued < need + NSTAGE && c.p_t < P.cfg.T &&
-           mbar_try_wait(ebar + 8u * (c.issued % NSTAGE), ((c.issued / NSTAGE) & 1) ^ 1))
-        prod_issue(c, P, prm);
+    __syncwarp();
 }
 #endif
 
-SQ_DEV void ring_init(Ctx& c, const Plan& P) {
-    c.cons = c.issued = 0;
-    c.p_t = c.p_i = c.p_s = c.p_c = c.p_row = 0;
+SQ_DEV void ring_init(Ctx& c, const float* prm) {
+    const Plan& P = SQ_PLAN;
+#ifdef SQAIR_HOST_EMU
+    c.cons = 0;
     c.call_idx = 0;
-#ifndef SQAIR_HOST_EMU
-    if (c.tid == 0) {
-        const uint32_t bar = smem_u32(c.sm + P.sm.Bar);
-        for (int i = 0; i < NSTAGE; ++i) {
-            mbar_init(bar + 8u * i, 1);                          // full: one expect_tx arrival + bytes
-            mbar_init(bar + 8u * (NSTAGE + i), c.nwarps);        // empty: one arrival per warp
+#else
+    if (c.tid() == 0) {
+        const uint32_t bar = smem_u32(SQ_SM + P.sm.Bar);
+        for (int i = 0; i < P.sm.nstage; ++i) {
+            mbar_init(bar + 8u * i, 1);                                   // full: one expect_tx arrival + bytes
+            mbar_init(bar + 8u * (P.sm.nstage + i), c.ncompute() / 32);   // empty: one arrival per compute warp
         }
         fence_barrier_init();
+        int* ctl = reinterpret_cast<int*>(SQ_SM + P.sm.Ctl);
+        for (int i = 0; i < 16; ++i) ctl[i] = 0;
+        const uint2 e = __ldg(reinterpret_cast<const uint2*>(prm + P.ctab_off + c.rank() * P.ctab_stride));
+        ctl[CTL_POFF] = (int)e.x; ctl[CTL_PNFL] = (int)e.y;
     }
-    prod_skip_idle(c, P);
+    if (c.tid() < DESC_WORDS) SQ_SM[P.sm.Desc + c.tid()] = SQ_LDG(prm + P.ltab_off + (int)P.seq[0] * DESC_WORDS + c.tid());
     c.sync();
 #endif
 }
@@ -268,32 +334,74 @@ SQ_DEV int head_of(const Layer& L, int vc, int& j) {
     return -1;
 }
 
-// accumulate rows [0, rows) of a weight chunk w[rows][Nc] for the 4 columns starting at col
+// x[k][0..R) for one feature row (vector load when the row is 16-byte aligned: R == 4 and ld % 4 == 0)
 template <int R>
-SQ_DEV void chunk_accum(const float* w, int Nc, int col, int rows, int k_first, int k_step, const Seg& S, int krow0,
-                        const float* sm, int slot, const float* const* imgrow, float (&acc)[4][R]) {
-    if (S.kind == SEG_SMEM) {
-        const float* x = sm + S.x_off + slot * S.x_sstride + krow0 * S.ld;
-        const int ld = S.ld;
-#pragma unroll 2
-        for (int k = k_first; k < rows; k += k_step) {
-            const float4 wv = *reinterpret_cast<const float4*>(w + k * Nc + col);
-            const float* xr = x + k * ld;
+SQ_DEV void load_x(const float* xp, bool vec, float (&x)[R]) {
+    if (R == 4 && vec) {
+        const float4 v = *reinterpret_cast<const float4*>(xp);
+        x[0] = v.x; x[1 % R] = v.y; x[2 % R] = v.z; x[3 % R] = v.w;
+    } else {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float xv = xr[r];
-                acc[0][r] += wv.x * xv; acc[1][r] += wv.y * xv; acc[2][r] += wv.z * xv; acc[3][r] += wv.w * xv;
-            }
+        for (int r = 0; r < R; ++r) x[r] = xp[r];
+    }
+}
+template <int R>
+SQ_DEV void fma4(float (&acc)[4][R], const float4& w, const float (&x)[R]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        acc[0][r] += w.x * x[r]; acc[1][r] += w.y * x[r]; acc[2][r] += w.z * x[r]; acc[3][r] += w.w * x[r];
+    }
+}
+
+// Accumulate rows k_first, k_first + k_step, ... (< n) of a weight piece w[n][Nc] for the 4 columns starting at
+// col; xoff = shared-memory offset of the piece's first input row (pixel index for image pieces).  Four rows in flight.
+template <int R>
+SQ_DEV void chunk_accum(const float* w, int Nc, int col, int k_first, int k_step, int n, bool image, int xoff, int ld,
+                        const float* sm, const float* const* imgrow, float (&acc)[4][R]) {
+    const float* wp = w + k_first * Nc + col;
+    const int wstep = k_step * Nc;
+    int k = k_first;
+    const int krow0 = xoff;                     // image pieces: index of the piece's first pixel
+    if (!image) {
+        const int xstep = k_step * ld;
+        const float* xp = sm + xoff + k_first * ld;
+        const bool vec = (R == 4) && ((ld & 3) == 0) && ((xoff & 3) == 0);
+        for (; k + 3 * k_step < n; k += 4 * k_step) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wp);
+            const float4 w1 = *reinterpret_cast<const float4*>(wp + wstep);
+            const float4 w2 = *reinterpret_cast<const float4*>(wp + 2 * wstep);
+            const float4 w3 = *reinterpret_cast<const float4*>(wp + 3 * wstep);
+            float x0[R], x1[R], x2[R], x3[R];
+            load_x<R>(xp, vec, x0); load_x<R>(xp + xstep, vec, x1); load_x<R>(xp + 2 * xstep, vec, x2); load_x<R>(xp + 3 * xstep, vec, x3);
+            fma4<R>(acc, w0, x0); fma4<R>(acc, w1, x1); fma4<R>(acc, w2, x2); fma4<R>(acc, w3, x3);
+            wp += 4 * wstep;
+            xp += 4 * xstep;
+        }
+        for (; k < n; k += k_step) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wp);
+            float x0[R];
+            load_x<R>(xp, vec, x0);
+            fma4<R>(acc, w0, x0);
+            wp += wstep;
+            xp += xstep;
         }
     } else {    // SEG_IMAGE: x[k][r] = frame pixel k of the image of row r (global, read-only)
-#pragma unroll 2
-        for (int k = k_first; k < rows; k += k_step) {
-            const float4 wv = *reinterpret_cast<const float4*>(w + k * Nc + col);
+        for (; k + k_step < n; k += 2 * k_step) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wp);
+            const float4 w1 = *reinterpret_cast<const float4*>(wp + wstep);
+            float x0[R], x1[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float xv = SQ_LDG(imgrow[r] + krow0 + k);
-                acc[0][r] += wv.x * xv; acc[1][r] += wv.y * xv; acc[2][r] += wv.z * xv; acc[3][r] += wv.w * xv;
-            }
+            for (int r = 0; r < R; ++r) { x0[r] = SQ_LDG(imgrow[r] + krow0 + k); x1[r] = SQ_LDG(imgrow[r] + krow0 + k + k_step); }
+            fma4<R>(acc, w0, x0); fma4<R>(acc, w1, x1);
+            wp += 2 * wstep;
+        }
+        for (; k < n; k += k_step) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wp);
+            float x0[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) x0[r] = SQ_LDG(imgrow[r] + krow0 + k);
+            fma4<R>(acc, w0, x0);
+            wp += wstep;
         }
     }
 }
@@ -307,91 +415,140 @@ SQ_DEV void chunk_accum(const float* w, int Nc, int col, int rows, int k_first, 
 // activation) and store it into every block of the cluster.
 // ---------------------------------------------------------------------------------------------
 template <int R>
-SQ_DEVNI void dense(Ctx& c, const Plan& P, const float* SQ_RESTRICT prm, int layer_id, int slot,
-                    const float* const* imgrow) {
-    const Layer& L = P.L[layer_id];
+SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot,
+                    const float* const* imgrow, int dbg) {
+    const Plan& P = SQ_PLAN;
 #ifdef SQAIR_HOST_EMU
+    const Layer& L = P.L[layer_id];
     if (P.seq[c.call_idx] != layer_id) {
         fprintf(stderr, "emu: dense call %d is layer %d but Plan::seq says %d\n", c.call_idx, layer_id, P.seq[c.call_idx]);
         abort();
     }
 #endif
+#ifdef SQAIR_HOST_EMU
     if (++c.call_idx >= P.nseq) c.call_idx = 0;
-    const bool exchange = L.split && c.ncta > 1;
-    const bool work = layer_has_work(L, c.rank);
+#else
+    // block-wide counters (shared memory): ring position, call index, descriptor slot
+    int* ctl = reinterpret_cast<int*>(SQ_SM + P.sm.Ctl);
+    int cons = ctl[CTL_CONS], stage = ctl[CTL_STAGE], phase = ctl[CTL_PHASE], call_idx = ctl[CTL_CALL];
+    const int desc_cur = ctl[CTL_DESC];
+    if (++call_idx >= P.nseq) call_idx = 0;
+    // the descriptor of this call was staged in shared memory during the previous call; start fetching the next one
+    const Layer& L = *reinterpret_cast<const Layer*>(SQ_SM + P.sm.Desc + desc_cur * DESC_WORDS);
+    float next_desc_word = 0.f;
+    if (c.tid() < DESC_WORDS) next_desc_word = SQ_LDG(prm + P.ltab_off + (int)P.seq[call_idx] * DESC_WORDS + c.tid());
+#endif
+    SQ_TICK(c, 5);                               // time since the previous dense call (element-wise stages)
+    const bool exchange = L.split && c.ncta() > 1;
+    const bool work = layer_has_work(L, c.rank());
     const int Nc = L.Nc, Gc = Nc >> 2;
-    if (exchange) cluster_arrive(c);             // phase A: "my buffers may be written once you all are here"
-    float* red = c.sm + P.sm.Red;
+    // Phase A ("nobody writes my buffers before I have entered this layer") is only needed if an element-wise
+    // stage could still touch the output buffer of the dense call that follows it; the frame program never does
+    // (audited in DESIGN.md), so it is compiled in only for debugging.
+#ifdef SQAIR_SAFE_EXCHANGE
+    if (exchange) cluster_arrive(c);
+#endif
+    float* red = SQ_SM + P.sm.Red;
     int ks = 1;
 #ifdef SQAIR_HOST_EMU
     std::vector<float> redv;
 #endif
     if (work) {
 #ifdef SQAIR_HOST_EMU
-        // one sequential thread: all column groups, accumulators on the heap
+        // one sequential thread: all column groups, accumulators on the heap; walks the same piece table as the device
         std::vector<float> accs((size_t)Gc * 4 * R, 0.f);
-        const float* panel = panel_ptr(P, L, prm, c.rank);
-        int row0 = 0;
-        for (int si = 0; si < L.nseg; ++si) {
-            const Seg& S = L.seg[si];
-            for (int k0 = 0; k0 < S.K; k0 += L.rpc) {
-                const int rows = (S.K - k0 < L.rpc) ? (S.K - k0) : L.rpc;
-                const float* w = panel + (size_t)(row0 + k0) * Nc;
+        const float* panel = panel_ptr(L, prm, c.rank());
+        int chunk_row0 = 0;
+        for (int pi = 0; pi < L.npiece; ++pi) {
+            const GemvPiece& pc = L.piece[pi];
+            for (int rep = 0; rep < pc.rep; ++rep) {
+                const int row0 = pc.row0 + rep * pc.n;
+                if (pc.flags & PIECE_FIRST) {
+                    chunk_row0 = row0;
+                    const int rows = (L.Ktot - row0 < L.rpc) ? (L.Ktot - row0) : L.rpc;
+                    const uint32_t* te = reinterpret_cast<const uint32_t*>(prm + P.ctab_off + c.rank() * P.ctab_stride) + 2 * (c.cons % P.ctab_n[c.rank()]);
+                    if (te[0] != (uint32_t)(panel + (size_t)row0 * Nc - prm) || te[1] != (uint32_t)(rows * Nc)) {
+                        fprintf(stderr, "emu: chunk table mismatch at chunk %d (layer %d)\n", c.cons, layer_id);
+                        abort();
+                    }
+                }
+                if (pc.w_rel != (row0 - chunk_row0) * Nc) { fprintf(stderr, "emu: bad piece w_rel (layer %d)\n", layer_id); abort(); }
+                const bool image = (pc.flags & PIECE_IMAGE) != 0;
+                const int xoff = image ? (pc.x_off + rep * pc.n) : (pc.x_off + slot * pc.x_sstride + rep * pc.n * pc.ld);
+                const float* w = panel + (size_t)row0 * Nc;
                 for (int g = 0; g < Gc; ++g) {
                     float acc[4][R];
                     for (int j = 0; j < 4; ++j) for (int r = 0; r < R; ++r) acc[j][r] = accs[((size_t)g * 4 + j) * R + r];
-                    chunk_accum<R>(w, Nc, g * 4, rows, 0, 1, S, k0, c.sm, slot, imgrow, acc);
+                    chunk_accum<R>(w, Nc, g * 4, 0, 1, pc.n, image, xoff, pc.ld, SQ_SM, imgrow, acc);
                     for (int j = 0; j < 4; ++j) for (int r = 0; r < R; ++r) accs[((size_t)g * 4 + j) * R + r] = acc[j][r];
                 }
-                ++c.cons;
+                if (pc.flags & PIECE_LAST) ++c.cons;
             }
-            row0 += S.K;
         }
         redv.resize((size_t)Nc * R);
         for (int g = 0; g < Gc; ++g)
             for (int j = 0; j < 4; ++j) for (int r = 0; r < R; ++r) redv[(size_t)(g * 4 + j) * R + r] = accs[((size_t)g * 4 + j) * R + r];
         red = redv.data();
-        // (falls through to the shared epilogue below with ks = 1)
 #else
-        ks = c.nthreads / Gc;
-        if (ks > MAX_KS) ks = MAX_KS;
-        const int g = c.tid % Gc, sl = c.tid / Gc;
-        const bool active = sl < ks;
-        float acc[4][R];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc[j][r] = 0.f;
-        const uint32_t bar = smem_u32(c.sm + P.sm.Bar);
-        for (int si = 0; si < L.nseg; ++si) {
-            const Seg& S = L.seg[si];
-            for (int k0 = 0; k0 < S.K; k0 += L.rpc) {
-                const int rows = (S.K - k0 < L.rpc) ? (S.K - k0) : L.rpc;
-                prod_fill(c, P, prm, c.cons);
-                const int stage = c.cons % NSTAGE;
-                mbar_wait(bar + 8u * stage, (c.cons / NSTAGE) & 1);
-                if (active)
-                    chunk_accum<R>(c.sm + P.sm.Ring + stage * P.sm.stage_floats, Nc, g * 4, rows, sl, ks, S, k0, c.sm, slot,
-                                   imgrow, acc);
-                __syncwarp();
-                if (c.lane == 0) mbar_arrive(bar + 8u * (NSTAGE + stage));
-                ++c.cons;
-            }
-        }
-        if (active) {
-            float* rp = red + ((size_t)sl * Nc + g * 4) * R;
+        ks = L.ks;
+        const int nchunk = L.nchunk;
+        if (c.tid() >= c.ncompute()) {
+            if (!(dbg & 2)) prod_run(c, prm, true, cons + nchunk - 1);
+            cons += nchunk;
+            for (int q = 0; q < nchunk; ++q) if (++stage == P.sm.nstage) { stage = 0; phase ^= 1; }
+        } else {
+            const int sl = c.tid() / Gc, g = c.tid() - sl * Gc;
+            const bool active = sl < ks, lane0 = c.lane() == 0;
+            float acc[4][R];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
-                for (int r = 0; r < R; ++r) rp[j * R + r] = acc[j][r];
+                for (int r = 0; r < R; ++r) acc[j][r] = 0.f;
+            const uint32_t bar = smem_u32(SQ_SM + P.sm.Bar);
+            const int ns = P.sm.nstage, npiece = L.npiece, stage_floats = P.sm.stage_floats;
+            const float* ring = SQ_SM + P.sm.Ring;
+            for (int pi = 0; pi < npiece; ++pi) {
+                const GemvPiece pc = L.piece[pi];
+                const bool image = (pc.flags & PIECE_IMAGE) != 0;
+                int xoff = image ? pc.x_off : (pc.x_off + slot * pc.x_sstride);
+                const int xadv = image ? pc.n : pc.n * pc.ld;
+                for (int rep = 0; rep < pc.rep; ++rep) {
+                    if ((pc.flags & PIECE_FIRST) && !(dbg & 2)) mbar_wait(bar + 8u * stage, phase);
+                    SQ_TICK(c, 0);
+                    if (active && sl < pc.n && !(dbg & 1))
+                        chunk_accum<R>(ring + stage * stage_floats + pc.w_rel, Nc, g * 4, sl, ks, pc.n, image, xoff, pc.ld, SQ_SM,
+                                       imgrow, acc);
+                    xoff += xadv;
+                    if (pc.flags & PIECE_LAST) {
+                        __syncwarp();
+                        if (lane0 && !(dbg & 2)) mbar_arrive(bar + 8u * (ns + stage));
+                        ++cons;
+                        if (++stage == ns) { stage = 0; phase ^= 1; }
+                    }
+                    SQ_TICK(c, 1);
+                }
+            }
+            if (active) {
+                float* rp = red + ((size_t)sl * Nc + g * 4) * R;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) rp[j * R + r] = acc[j][r];
+            }
         }
 #endif
     }
+#ifndef SQAIR_HOST_EMU
+    else if (c.tid() >= c.ncompute() && !(dbg & 2)) prod_run(c, prm, false, 0);
+#endif
     c.sync();
+    SQ_TICK(c, 2);
+#ifdef SQAIR_SAFE_EXCHANGE
     if (exchange) cluster_wait(c);               // phase A complete: every block has entered this layer
+#endif
     if (work) {
-        const int vbase = L.split ? c.rank * Nc : 0;
-        for (int o = c.tid; o < Nc * R; o += c.nthreads) {
+        const int vbase = L.split ? c.rank() * Nc : 0;
+        for (int o = c.tid(); o < ((dbg & 16) ? 0 : Nc * R); o += c.nthreads()) {
             const int col = o / R, r = o - col * R;
             int j;
             const int h = head_of(L, vbase + col, j);
@@ -399,20 +556,26 @@ SQ_DEVNI void dense(Ctx& c, const Plan& P, const float* SQ_RESTRICT prm, int lay
             const Head& H = L.head[h];
             float v = 0.f;
             for (int s2 = 0; s2 < ks; ++s2) v += red[((size_t)s2 * Nc + col) * R + r];
-            float bias = H.b_off >= 0 ? SQ_LDG(prm + H.b_off + j) : 0.f;
-            if (H.b2_off >= 0) bias += SQ_LDG(prm + H.b2_off + j);
-            v = actf(H.act, v + bias) * H.scale + H.add;
+            v = actf(H.act, v) * H.scale + H.add;                     // the bias arrived through the GEMV (constant-1 input)
             if (H.scale_p_off >= 0) v *= SQ_LDG(prm + H.scale_p_off);
             const int off = H.out_off + slot * H.out_sstride + j * H.out_ld + r;
             if (exchange) {
-                for (int q = 0; q < c.ncta; ++q) store_peer(c, off, q, v);
+                for (int q = 0; q < c.ncta(); ++q) store_peer(c, off, q, v);
             } else {
-                c.sm[off] = v;
+                SQ_SM[off] = v;
             }
         }
     }
+#ifndef SQAIR_HOST_EMU
+    if (c.tid() < DESC_WORDS) SQ_SM[P.sm.Desc + (desc_cur ^ 1) * DESC_WORDS + c.tid()] = next_desc_word;
+    if (c.tid() == 0) {      // every thread computed the same values; readers are behind the barrier that follows
+        ctl[CTL_CONS] = cons; ctl[CTL_STAGE] = stage; ctl[CTL_PHASE] = phase; ctl[CTL_CALL] = call_idx; ctl[CTL_DESC] = desc_cur ^ 1;
+    }
+#endif
+    SQ_TICK(c, 3);
     if (exchange) { cluster_arrive(c); cluster_wait(c); }     // phase B: all slices have landed everywhere
     else c.sync();
+    SQ_TICK(c, 4);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -422,13 +585,13 @@ template <int R>
 struct Block {
     Ctx& c;
     const Plan& P;
-    const Job& J;
+    const Job& J;            // the __grid_constant__ kernel parameter (constant-bank loads)
     int row0;                       // first global row of this block
     const float* imgrow[R];         // frame of each row for the current t
     int grow[R];                    // global row (clamped) of each local row
     bool valid[R];
 
-    SQ_DEV Block(Ctx& c_, const Plan& P_, const Job& J_, int row0_) : c(c_), P(P_), J(J_), row0(row0_) {
+    SQ_DEV Block(Ctx& c_, const Job& J_, int row0_) : c(c_), P(SQ_PLAN_OF(c_)), J(J_), row0(row0_) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             int gr = row0 + r;
@@ -438,16 +601,19 @@ struct Block {
         }
     }
     // accessors ------------------------------------------------------------------------------
-    SQ_DEV float* sm() const { return c.sm; }
+    SQ_DEV float* sm() const { return SQ_SM; }
     SQ_DEV int LDS() const { return P.NS * R; }
     SQ_DEV int LDE() const { return (P.NS + 1) * R; }
-    SQ_DEV float& Z(int f, int s, int r) const { return c.sm[P.sm.Z + f * LDS() + s * R + r]; }
-    SQ_DEV float& rec(int base, int e, int f, int r) const { return c.sm[base + f * LDE() + e * R + r]; }
-    SQ_DEV float& pri(int f, int s, int r) const { return c.sm[P.sm.Pri + f * LDS() + s * R + r]; }
-    SQ_DEV float& lp(int k, int s, int r) const { return c.sm[P.sm.Lp + k * LDS() + s * R + r]; }
-    SQ_DEV float& rowacc(int k, int r) const { return c.sm[P.sm.RowAcc + k * R + r]; }
+    SQ_DEV float& Z(int f, int s, int r) const { return SQ_SM[P.sm.Z + f * LDS() + s * R + r]; }
+    SQ_DEV float& rec(int base, int e, int f, int r) const { return SQ_SM[base + f * LDE() + e * R + r]; }
+    SQ_DEV float& pri(int f, int s, int r) const { return SQ_SM[P.sm.Pri + f * LDS() + s * R + r]; }
+    SQ_DEV float& lp(int k, int s, int r) const { return SQ_SM[P.sm.Lp + k * LDS() + s * R + r]; }
+    SQ_DEV float& rowacc(int k, int r) const { return SQ_SM[P.sm.RowAcc + k * R + r]; }
     SQ_DEV float prm(int off) const { return SQ_LDG(J.prm + off); }
-    SQ_DEV void lin(int id, int slot = 0) const { dense<R>(c, P, J.prm, id, slot, imgrow); }
+    SQ_DEV void lin(int id, int slot = 0) const {
+        if (J.debug_flags & 64) return;
+        dense<R>(c, J.prm, id, slot, imgrow, J.debug_flags);
+    }
     SQ_DEV size_t nidx(int t, int r, int slot2) const {      // noise index of (t, row, slot in [0,2n))
         return ((size_t)t * P.rows + grow[r]) * (2 * P.NS) + slot2;
     }
@@ -461,22 +627,22 @@ struct Block {
     SQ_DEV void init_sequence() const {
         const Smem& m = P.sm;
         const int nh = P.nh, nw = P.nw, NS = P.NS;
-        for (int i = c.tid; i < (nw + 6) * LDS(); i += c.nthreads) c.sm[m.Z + i] = 0.f;
-        for (int i = c.tid; i < LDS(); i += c.nthreads) c.sm[m.Ids + i] = -1.f;
-        for (int i = c.tid; i < R; i += c.nthreads) c.sm[m.LastId + i] = -1.f;
-        for (int i = c.tid; i < nh * LDS(); i += c.nthreads) {
+        for (int i = c.tid(); i < (nw + 6) * LDS(); i += c.nthreads()) SQ_SM[m.Z + i] = 0.f;
+        for (int i = c.tid(); i < LDS(); i += c.nthreads()) SQ_SM[m.Ids + i] = -1.f;
+        for (int i = c.tid(); i < R; i += c.nthreads()) { SQ_SM[m.LastId + i] = -1.f; SQ_SM[m.Ones + i] = 1.f; }
+        for (int i = c.tid(); i < nh * LDS(); i += c.nthreads()) {
             int f = i / LDS();
-            c.sm[m.Tst + i] = prm(P.po.temporal_h0 + f);
-            c.sm[m.Pst + i] = prm(P.po.prior_h0 + f);
+            SQ_SM[m.Tst + i] = prm(P.po.temporal_h0 + f);
+            SQ_SM[m.Pst + i] = prm(P.po.prior_h0 + f);
         }
         // entry 0 of the slot records = RNN-core initial state (core.py:132-139,153,238)
-        for (int i = c.tid; i < (nw + 5) * R; i += c.nthreads) {
+        for (int i = c.tid(); i < (nw + 5) * R; i += c.nthreads()) {
             int f = i / R, r = i % R;
             rec(m.PropOut, 0, f, r) = 0.f;
             rec(m.DiscOut, 0, f, r) = (f == P.rec.pres) ? 1.f : 0.f;
         }
         if (P.cfg.rec_where_prior)
-            for (int i = c.tid; i < 4 * R; i += c.nthreads) c.sm[m.RnInit + i] = prm(P.po.rn_init_state + i / R);
+            for (int i = c.tid(); i < 4 * R; i += c.nthreads()) SQ_SM[m.RnInit + i] = prm(P.po.rn_init_state + i / R);
         (void)NS;
         c.sync();
     }
@@ -486,29 +652,29 @@ struct Block {
         const Smem& m = P.sm;
         const int G = P.cfg.G, W = P.cfg.W, H = P.cfg.H;
         const float hw = 0.5f * (float)(W - 1), hh = 0.5f * (float)(H - 1);
-        for (int i = c.tid; i < P.g * R; i += c.nthreads) {
+        for (int i = c.tid(); i < ((J.debug_flags & 8) ? 0 : P.g * R); i += c.nthreads()) {
             const int r = i % R, j = i / R;
             const int gy = j / G, gx = j % G;
-            const float sx = c.sm[m.Coords + 0 * R + r], sy = c.sm[m.Coords + 1 * R + r];
-            const float tx = c.sm[m.Coords + 2 * R + r], ty = c.sm[m.Coords + 3 * R + r];
+            const float sx = SQ_SM[m.Coords + 0 * R + r], sy = SQ_SM[m.Coords + 1 * R + r];
+            const float tx = SQ_SM[m.Coords + 2 * R + r], ty = SQ_SM[m.Coords + 3 * R + r];
             const float x = hw * (sx * lin11(gx, G) + tx) + hw;
             const float y = hh * (sy * lin11(gy, G) + ty) + hh;
             const float* img = imgrow[0];
 #pragma unroll
             for (int q = 1; q < R; ++q) if (r == q) img = imgrow[q];
             float v = bilinear_zero_pad(x, y, W, H, [&](int ix, int iy) { return SQ_LDG(img + iy * W + ix); });
-            if (use_mask) v *= c.sm[m.Mask + i];
-            c.sm[m.Glm + i] = v;
+            if (use_mask) v *= SQ_SM[m.Mask + i];
+            SQ_SM[m.Glm + i] = v;
         }
         c.sync();
     }
     // to_coords (modules.py:220-227) + clip_preserve(scale, 1e-4) (modules.py:206)
     SQ_DEV void set_coords(float w0, float w1, float w2, float w3, int r) const {
         const Smem& m = P.sm;
-        c.sm[m.Coords + 0 * R + r] = fmaxf(sigmoidf_(w0), 1e-4f);
-        c.sm[m.Coords + 1 * R + r] = fmaxf(sigmoidf_(w1), 1e-4f);
-        c.sm[m.Coords + 2 * R + r] = tanhf(w2);
-        c.sm[m.Coords + 3 * R + r] = tanhf(w3);
+        SQ_SM[m.Coords + 0 * R + r] = fmaxf(sigmoidf_(w0), 1e-4f);
+        SQ_SM[m.Coords + 1 * R + r] = fmaxf(sigmoidf_(w1), 1e-4f);
+        SQ_SM[m.Coords + 2 * R + r] = tanhf(w2);
+        SQ_SM[m.Coords + 3 * R + r] = tanhf(w3);
     }
     SQ_DEV void encode_glimpse(int last_layer) const {
         lin(L_ENC1); lin(L_ENC2); lin(last_layer);
@@ -516,9 +682,9 @@ struct Block {
     // snt.GRU gate algebra (Appendix B) around the two dense calls: Gr <- r*h, then state update.
     SQ_DEV void gru_mul_r(int state_off, int s) const {
         const Smem& m = P.sm;
-        for (int i = c.tid; i < P.nh * R; i += c.nthreads) {
+        for (int i = c.tid(); i < P.nh * R; i += c.nthreads()) {
             int f = i / R, r = i % R;
-            c.sm[m.Gr + i] *= c.sm[state_off + f * LDS() + s * R + r];
+            SQ_SM[m.Gr + i] *= SQ_SM[state_off + f * LDS() + s * R + r];
         }
         c.sync();
     }
@@ -532,17 +698,17 @@ struct Block {
         lin(L_PGRU_ZR, s);
         gru_mul_r(m.Pst, s);
         lin(L_PGRU_C, s);
-        for (int i = c.tid; i < nh * R; i += c.nthreads) {
+        for (int i = c.tid(); i < nh * R; i += c.nthreads()) {
             int f = i / R, r = i % R;
-            float& h = c.sm[m.Pst + f * LDS() + s * R + r];
-            float z = c.sm[m.Gz + i];
-            h = (1.f - z) * h + z * c.sm[m.Gc + i];
+            float& h = SQ_SM[m.Pst + f * LDS() + s * R + r];
+            float z = SQ_SM[m.Gz + i];
+            h = (1.f - z) * h + z * SQ_SM[m.Gc + i];
         }
         c.sync();
         lin(L_PLIN, s);
         // stats post-processing: rows 0 logit | 1..4 where_loc | 5..4+nw what_loc | where_scale(4) | what_scale(nw)
         const int nstat = 2 * (4 + nw) + 1;
-        for (int i = c.tid; i < nstat * R; i += c.nthreads) {
+        for (int i = c.tid(); i < nstat * R; i += c.nthreads()) {
             int f = i / R, r = i % R;
             float v = pri(f, s, r);
             const float ptm1 = Z(nw + 4, s, r);
@@ -576,22 +742,22 @@ struct Block {
         lin(L_WBMK1, s);
         lin(L_WB2);
         if (masked) lin(L_MK2);
-        for (int r = c.tid; r < R; r += c.nthreads)
-            set_coords(Z(nw + 0, s, r) + c.sm[m.Wb + 0 * R + r], Z(nw + 1, s, r) + c.sm[m.Wb + 1 * R + r],
-                       Z(nw + 2, s, r) + c.sm[m.Wb + 2 * R + r], Z(nw + 3, s, r) + c.sm[m.Wb + 3 * R + r], r);
+        for (int r = c.tid(); r < R; r += c.nthreads())
+            set_coords(Z(nw + 0, s, r) + SQ_SM[m.Wb + 0 * R + r], Z(nw + 1, s, r) + SQ_SM[m.Wb + 1 * R + r],
+                       Z(nw + 2, s, r) + SQ_SM[m.Wb + 2 * R + r], Z(nw + 3, s, r) + SQ_SM[m.Wb + 3 * R + r], r);
         c.sync();
         extract_glimpse(masked);
         encode_glimpse(L_ENC3_LOC);                               // -> Loc1 (core.py:292-293)
         lin(L_PRNN, s);                                           // core.py:295-302 -> Hrnn[1]
         lin(L_PT1, s); lin(L_PT2); lin(L_PT3);                    // core.py:323-324 -> Tp
         // where ~ MVN_TriL(where_tm1 + us*loc, L) (core.py:326-330; modules.py:535-545)
-        for (int r = c.tid; r < R; r += c.nthreads) {
+        for (int r = c.tid(); r < R; r += c.nthreads()) {
             float loc[4], sc[4], eps[4], L[4][4], wh[4];
             const float so = prm(P.po.p_scale_offset);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                loc[i] = Z(nw + i, s, r) + P.cfg.where_update_scale * c.sm[m.Tp + i * R + r];
-                sc[i] = softplusf_(c.sm[m.Tp + (4 + i) * R + r] + so - 1.f) + 1e-2f;
+                loc[i] = Z(nw + i, s, r) + P.cfg.where_update_scale * SQ_SM[m.Tp + i * R + r];
+                sc[i] = softplusf_(SQ_SM[m.Tp + (4 + i) * R + r] + so - 1.f) + 1e-2f;
                 eps[i] = J.eps_where[nidx(t, r, s) * 4 + i];
             }
             tril_from_scale(sc, L);
@@ -614,18 +780,18 @@ struct Block {
         lin(L_TGRU_ZR, s);
         gru_mul_r(m.Tst, s);
         lin(L_TGRU_C, s);
-        for (int i = c.tid; i < nh * R; i += c.nthreads) {
+        for (int i = c.tid(); i < nh * R; i += c.nthreads()) {
             int f = i / R, r = i % R;
-            float h = c.sm[m.Tst + f * LDS() + s * R + r], z = c.sm[m.Gz + i];
-            c.sm[m.Gc + i] = (1.f - z) * h + z * c.sm[m.Gc + i];
+            float h = SQ_SM[m.Tst + f * LDS() + s * R + r], z = SQ_SM[m.Gz + i];
+            SQ_SM[m.Gc + i] = (1.f - z) * h + z * SQ_SM[m.Gc + i];
         }
         c.sync();
         lin(L_PHEADS);                                            // core.py:343-349 -> Tg, Gt
-        for (int i = c.tid; i < nw * R; i += c.nthreads) {        // core.py:351-357
+        for (int i = c.tid(); i < nw * R; i += c.nthreads()) {        // core.py:351-357
             int j = i / R, r = i % R;
-            float fg = c.sm[m.Gt + i], ig = c.sm[m.Gt + nw * R + i], tg = c.sm[m.Gt + 2 * nw * R + i];
-            float loc2 = c.sm[m.Enc + i], sc2 = c.sm[m.Enc + nw * R + i];
-            float loct = c.sm[m.Tg + i], sct = c.sm[m.Tg + nw * R + i];
+            float fg = SQ_SM[m.Gt + i], ig = SQ_SM[m.Gt + nw * R + i], tg = SQ_SM[m.Gt + 2 * nw * R + i];
+            float loc2 = SQ_SM[m.Enc + i], sc2 = SQ_SM[m.Enc + nw * R + i];
+            float loct = SQ_SM[m.Tg + i], sct = SQ_SM[m.Tg + nw * R + i];
             float wl = fg * Z(j, s, r) + (1.f - ig) * loc2 + (1.f - tg) * loct;
             float ws = (1.f - ig) * sc2 + (1.f - tg) * sct;
             float what = wl + ws * J.eps_what[nidx(t, r, s) * nw + j];
@@ -635,9 +801,9 @@ struct Block {
         }
         c.sync();
         lin(L_PST1, s); lin(L_PST2);                              // modules.py:506-513
-        for (int r = c.tid; r < R; r += c.nthreads) {             // core.py:141-144
+        for (int r = c.tid(); r < R; r += c.nthreads()) {             // core.py:141-144
             const float ptm1 = Z(nw + 4, s, r);
-            float logit = ptm1 * c.sm[m.Lg + r] + (ptm1 - 1.f) * 88.f;
+            float logit = ptm1 * SQ_SM[m.Lg + r] + (ptm1 - 1.f) * 88.f;
             float prob = sigmoidf_(logit);
             float pres = (J.u_pres[nidx(t, r, s)] < prob ? 1.f : 0.f) * ptm1;
             rec(m.PropOut, e, F.logit, r) = logit;
@@ -646,16 +812,16 @@ struct Block {
         }
         c.sync();
         // log-probs under q and p (sqair_modules.py:290-317): one warp per row, lanes over dims
-        for (int r = c.warp; r < R; r += c.nwarps) {
+        for (int r = c.warp(); r < R; r += c.nwarps()) {
             float qw = 0.f, pw = 0.f;
-            for (int j = c.lane; j < nw; j += c.nlanes) {
+            for (int j = c.lane(); j < nw; j += c.nlanes()) {
                 float x = rec(m.PropOut, e, F.what + j, r);
                 qw += normal_lp(x, rec(m.PropOut, e, F.what_loc + j, r), rec(m.PropOut, e, F.what_scale + j, r));
                 pw += normal_lp(x, pri(5 + j, s, r), pri(9 + nw + j, s, r));
             }
             qw = warp_sum(qw);
             pw = warp_sum(pw);
-            if (c.lane == 0) {
+            if (c.lane() == 0) {
                 float x[4], loc[4], sc[4], L[4][4], y[4];
                 float pwh = 0.f;
 #pragma unroll
@@ -692,10 +858,10 @@ struct Block {
             }
         }
         // commit the slot: temporal state, RNN hidden
-        for (int i = c.tid; i < nh * R; i += c.nthreads) {
+        for (int i = c.tid(); i < nh * R; i += c.nthreads()) {
             int f = i / R, r = i % R;
-            c.sm[m.Tst + f * LDS() + s * R + r] = c.sm[m.Gc + i];
-            c.sm[m.Hrnn + i] = c.sm[m.Hrnn + nh * R + i];
+            SQ_SM[m.Tst + f * LDS() + s * R + r] = SQ_SM[m.Gc + i];
+            SQ_SM[m.Hrnn + i] = SQ_SM[m.Hrnn + nh * R + i];
         }
         c.sync();
     }
@@ -725,13 +891,13 @@ struct Block {
         const int nh = P.nh, nw = P.nw, e = s + 1, ns2 = P.NS + s;
         lin(L_DRNN, s);
         lin(L_DT1); lin(L_DT2); lin(L_DT3);
-        for (int r = c.tid; r < R; r += c.nthreads) {             // core.py:220-227
+        for (int r = c.tid(); r < R; r += c.nthreads()) {             // core.py:220-227
             const float so = prm(P.po.d_scale_offset);
             float wh[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                float loc = c.sm[m.Tp + i * R + r];
-                float sc = softplusf_(c.sm[m.Tp + (4 + i) * R + r] + so) + 1e-2f;
+                float loc = SQ_SM[m.Tp + i * R + r];
+                float sc = softplusf_(SQ_SM[m.Tp + (4 + i) * R + r] + so) + 1e-2f;
                 wh[i] = loc + sc * J.eps_where[nidx(t, r, ns2) * 4 + i];
                 rec(m.DiscOut, e, F.where + i, r) = wh[i];
                 rec(m.DiscOut, e, F.where_loc + i, r) = loc;
@@ -739,21 +905,24 @@ struct Block {
             }
             set_coords(wh[0], wh[1], wh[2], wh[3], r);
         }
+        // the new hidden state becomes the next slot's old one.  Done here (not at the end of the slot) so that no
+        // element-wise stage reads Hrnn[1] right before the next L_DRNN writes it from a peer block.
+        for (int i = c.tid(); i < nh * R; i += c.nthreads()) SQ_SM[m.Hrnn + i] = SQ_SM[m.Hrnn + nh * R + i];
         c.sync();
         extract_glimpse(false);                                   // discovery passes no mask (core.py:217)
         encode_glimpse(L_ENC3);
-        for (int i = c.tid; i < nw * R; i += c.nthreads) {        // core.py:216-218
+        for (int i = c.tid(); i < nw * R; i += c.nthreads()) {        // core.py:216-218
             int j = i / R, r = i % R;
-            float wl = c.sm[m.Enc + i], ws = c.sm[m.Enc + nw * R + i];
+            float wl = SQ_SM[m.Enc + i], ws = SQ_SM[m.Enc + nw * R + i];
             rec(m.DiscOut, e, F.what + j, r) = wl + ws * J.eps_what[nidx(t, r, ns2) * nw + j];
             rec(m.DiscOut, e, F.what_loc + j, r) = wl;
             rec(m.DiscOut, e, F.what_scale + j, r) = ws;
         }
         c.sync();
         lin(L_DST1, s); lin(L_DST2);
-        for (int r = c.tid; r < R; r += c.nthreads) {
+        for (int r = c.tid(); r < R; r += c.nthreads()) {
             const float pkm1 = rec(m.DiscOut, s, F.pres, r);      // entry 0 holds the initial 1 (core.py:153)
-            float logit = pkm1 * c.sm[m.Lg + r] + (pkm1 - 1.f) * 88.f;
+            float logit = pkm1 * SQ_SM[m.Lg + r] + (pkm1 - 1.f) * 88.f;
             float prob = sigmoidf_(logit);
             float pres = (J.u_pres[nidx(t, r, ns2)] < prob ? 1.f : 0.f) * pkm1;
             rec(m.DiscOut, e, F.logit, r) = logit;
@@ -761,16 +930,16 @@ struct Block {
             rec(m.DiscOut, e, F.pres, r) = pres;
         }
         c.sync();
-        for (int r = c.warp; r < R; r += c.nwarps) {
+        for (int r = c.warp(); r < R; r += c.nwarps()) {
             float qw = 0.f, pw = 0.f;
-            for (int j = c.lane; j < nw; j += c.nlanes) {
+            for (int j = c.lane(); j < nw; j += c.nlanes()) {
                 float x = rec(m.DiscOut, e, F.what + j, r);
                 qw += normal_lp(x, rec(m.DiscOut, e, F.what_loc + j, r), rec(m.DiscOut, e, F.what_scale + j, r));
                 pw += normal_lp(x, 0.f, 1.f);
             }
             qw = warp_sum(qw);
             pw = warp_sum(pw);
-            if (c.lane == 0) {
+            if (c.lane() == 0) {
                 float qwh = 0.f;
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -783,7 +952,6 @@ struct Block {
                 rowacc(RA_NDISC, r) += pres;
             }
         }
-        for (int i = c.tid; i < nh * R; i += c.nthreads) c.sm[m.Hrnn + i] = c.sm[m.Hrnn + nh * R + i];
         c.sync();
     }
 
@@ -795,26 +963,26 @@ struct Block {
         const int NS = P.NS;
         if (P.cfg.rec_where_prior) {
             // previous-sample inputs of the autoregressive prior: init_sample, then where_{s-1}
-            for (int i = c.tid; i < 4 * LDS(); i += c.nthreads) {
+            for (int i = c.tid(); i < 4 * LDS(); i += c.nthreads()) {
                 int f = i / LDS(), s = (i / R) % NS, r = i % R;
-                c.sm[m.RnPrev0 + i] = (s == 0) ? prm(P.po.rn_init_sample + f) : rec(m.DiscOut, s, F.where + f, r);
+                SQ_SM[m.RnPrev0 + i] = (s == 0) ? prm(P.po.rn_init_sample + f) : rec(m.DiscOut, s, F.where + f, r);
             }
             c.sync();
             lin(L_RN1);
             for (int s = 0; s < NS; ++s) {
                 lin(L_RN2, s); lin(L_RN3);
-                for (int r = c.tid; r < R; r += c.nthreads) {
+                for (int r = c.tid(); r < R; r += c.nthreads()) {
                     float a = 0.f;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        a += normal_lp(rec(m.DiscOut, s + 1, F.where + i, r), c.sm[m.Rns + i * R + r],
-                                       c.sm[m.Rns + (4 + i) * R + r]);
+                        a += normal_lp(rec(m.DiscOut, s + 1, F.where + i, r), SQ_SM[m.Rns + i * R + r],
+                                       SQ_SM[m.Rns + (4 + i) * R + r]);
                     lp(LP_DPWHERE, s, r) = a * rec(m.DiscOut, s + 1, F.pres, r);
                 }
                 c.sync();
             }
         } else {
-            for (int i = c.tid; i < LDS(); i += c.nthreads) {
+            for (int i = c.tid(); i < LDS(); i += c.nthreads()) {
                 int s = i / R, r = i % R;
                 float a = 0.f;
 #pragma unroll
@@ -825,7 +993,7 @@ struct Block {
             c.sync();
         }
         if (P.cfg.disc_prior_type == SQAIR_DISC_PRIOR_CAT) { lin(L_SP1); lin(L_SP2); }
-        for (int r = c.tid; r < R; r += c.nthreads) {
+        for (int r = c.tid(); r < R; r += c.nthreads()) {
             const int num = (int)rowacc(RA_NDISC, r);
             // p(N): Categorical(elu(bias + (t>0) tbias + MLP(E[n_prop]))) (sqair_modules.py:208-221)
             float pnum;
@@ -833,7 +1001,7 @@ struct Block {
                 float lg[MAX_SLOTS + 1], mx = -INFINITY;
                 for (int k = 0; k <= NS; ++k) {
                     float v = prm(P.po.step_prior_bias + k) + (t == 0 ? 0.f : 1.f) * prm(P.po.step_prior_tbias + k);
-                    v = eluf_(v + c.sm[m.Spl + k * R + r]);
+                    v = eluf_(v + SQ_SM[m.Spl + k * R + r]);
                     lg[k] = v;
                     mx = fmaxf(mx, v);
                 }
@@ -857,7 +1025,7 @@ struct Block {
             float qsel = 0.f;
             for (int k = 0; k <= NS; ++k) {
                 float v = (float)(mod[k] / tot);
-                c.sm[m.Spl + k * R + r] = v;                      // Spl now holds disc_prob
+                SQ_SM[m.Spl + k * R + r] = v;                      // Spl now holds disc_prob
                 if (k == num) qsel = v;
             }
             rowacc(RA_QNUM, r) = logf(fminf(fmaxf(qsel, 1e-16f), 1.f));
@@ -874,7 +1042,7 @@ struct Block {
         const RecF& F = P.rec;
         const int NS = P.NS, nw = P.nw, nh = P.nh;
         const sqair_outputs& o = J.out;
-        for (int r = c.tid; r < R; r += c.nthreads) {
+        for (int r = c.tid(); r < R; r += c.nthreads()) {
             // stable partition of the 2n candidates, present first
             int order[2 * MAX_SLOTS], cnt = 0;
             for (int k = 0; k < 2 * NS; ++k) {
@@ -887,21 +1055,21 @@ struct Block {
             }
             // ids (index.py:198-221)
             float ids[2 * MAX_SLOTS];
-            float last = c.sm[m.LastId + r], inc = 0.f;
+            float last = SQ_SM[m.LastId + r], inc = 0.f;
             for (int k = 0; k < NS; ++k) {
                 float pp = rec(m.PropOut, k + 1, F.pres, r);
-                ids[k] = c.sm[m.Ids + k * R + r] * pp - (1.f - pp);
+                ids[k] = SQ_SM[m.Ids + k * R + r] * pp - (1.f - pp);
             }
             for (int k = 0; k < NS; ++k) {
                 float dp = rec(m.DiscOut, k + 1, F.pres, r);
                 inc += dp;
                 ids[NS + k] = (inc + last) * dp - (1.f - dp);
             }
-            c.sm[m.LastId + r] = last + inc;
+            SQ_SM[m.LastId + r] = last + inc;
             float nsteps = 0.f;
             for (int j = 0; j < NS; ++j) {
-                c.sm[m.Perm + j * R + r] = (float)order[j];
-                c.sm[m.Ids + j * R + r] = ids[order[j]];
+                SQ_SM[m.Perm + j * R + r] = (float)order[j];
+                SQ_SM[m.Ids + j * R + r] = ids[order[j]];
                 int k = order[j];
                 nsteps += k < NS ? rec(m.PropOut, k + 1, F.pres, r) : rec(m.DiscOut, k - NS + 1, F.pres, r);
             }
@@ -910,9 +1078,9 @@ struct Block {
         c.sync();
         // new z_t and the 9 compacted heads
         const size_t trow = (size_t)t * P.rows;
-        for (int i = c.tid; i < F.size * LDS(); i += c.nthreads) {
+        for (int i = c.tid(); i < F.size * LDS(); i += c.nthreads()) {
             const int r = i % R, j = (i / R) % NS, f = i / LDS();
-            const int k = (int)c.sm[m.Perm + j * R + r];
+            const int k = (int)SQ_SM[m.Perm + j * R + r];
             const float v = k < NS ? rec(m.PropOut, k + 1, f, r) : rec(m.DiscOut, k - NS + 1, f, r);
             float* dst = nullptr;
             int ff = 0, width = 1;
@@ -925,21 +1093,21 @@ struct Block {
             else if (f < F.prob) { dst = o.where_scale; ff = f - F.where_scale; width = 4; }
             else if (f == F.prob) { dst = o.presence_prob; }
             else { Z(nw + 5, j, r) = v; dst = o.presence_logit; }
-            if (dst && c.rank == 0 && valid_row(r)) dst[((trow + grow_of(r)) * NS + j) * width + ff] = v;
+            if (dst && c.rank() == 0 && valid_row(r)) dst[((trow + grow_of(r)) * NS + j) * width + ff] = v;
         }
         // GRU states travel with their slots; discovered objects start from the trainable initial states
-        for (int i = c.tid; i < nh * R; i += c.nthreads) {
+        for (int i = c.tid(); i < nh * R; i += c.nthreads()) {
             const int f = i / R, r = i % R;
             float tv[MAX_SLOTS], pv[MAX_SLOTS];
             const float t0 = prm(P.po.temporal_h0 + f), p0 = prm(P.po.prior_h0 + f);
             for (int j = 0; j < NS; ++j) {
-                const int k = (int)c.sm[m.Perm + j * R + r];
-                tv[j] = k < NS ? c.sm[m.Tst + f * LDS() + k * R + r] : t0;
-                pv[j] = k < NS ? c.sm[m.Pst + f * LDS() + k * R + r] : p0;
+                const int k = (int)SQ_SM[m.Perm + j * R + r];
+                tv[j] = k < NS ? SQ_SM[m.Tst + f * LDS() + k * R + r] : t0;
+                pv[j] = k < NS ? SQ_SM[m.Pst + f * LDS() + k * R + r] : p0;
             }
             for (int j = 0; j < NS; ++j) {
-                c.sm[m.Tst + f * LDS() + j * R + r] = tv[j];
-                c.sm[m.Pst + f * LDS() + j * R + r] = pv[j];
+                SQ_SM[m.Tst + f * LDS() + j * R + r] = tv[j];
+                SQ_SM[m.Pst + f * LDS() + j * R + r] = pv[j];
             }
         }
         c.sync();
@@ -962,18 +1130,18 @@ struct Block {
     // ------------------------------------------------------------------------------------------
     SQ_DEV void decode_and_score(int t) const {
         const Smem& m = P.sm;
-        const int NS = P.NS, nw = P.nw, G = P.cfg.G, W = P.cfg.W, H = P.cfg.H, g = P.g, PX = P.P;
+        const int NS = P.NS, nw = P.nw, G = P.cfg.G, W = P.cfg.W, H = P.cfg.H, g = P.g, PX = P.PX;
         const sqair_outputs& o = J.out;
         const size_t trow = (size_t)t * P.rows;
         for (int s = 0; s < NS; ++s) { lin(L_DEC1, s); lin(L_DEC2); lin(L_DEC3, s); }
-        if (o.glimpse && c.rank == 0)
-            for (int i = c.tid; i < R * NS * g; i += c.nthreads) {
+        if (o.glimpse && c.rank() == 0)
+            for (int i = c.tid(); i < R * NS * g; i += c.nthreads()) {
                 const int px = i % g, s = (i / g) % NS, r = i / (g * NS);
-                if (valid_row(r)) o.glimpse[((trow + grow_of(r)) * NS + s) * g + px] = c.sm[m.Dgl + px * LDS() + s * R + r];
+                if (valid_row(r)) o.glimpse[((trow + grow_of(r)) * NS + s) * g + px] = SQ_SM[m.Dgl + px * LDS() + s * R + r];
             }
         // inverse-transformer coordinates of every slot (Pri is dead by now and reused as a table)
-        float* cc = c.sm + m.Pri;    // [4][NS][R]
-        for (int i = c.tid; i < LDS(); i += c.nthreads) {
+        float* cc = SQ_SM + m.Pri;    // [4][NS][R]
+        for (int i = c.tid(); i < LDS(); i += c.nthreads()) {
             const int s = i / R, r = i % R;
             cc[0 * LDS() + i] = fmaxf(sigmoidf_(Z(nw + 0, s, r)), 1e-4f);
             cc[1 * LDS() + i] = fmaxf(sigmoidf_(Z(nw + 1, s, r)), 1e-4f);
@@ -989,11 +1157,11 @@ struct Block {
 #pragma unroll
         for (int r = 0; r < R; ++r) ll[r] = 0.f;
         // every block of the cluster composes its share of the pixels
-        const int px_per = (PX + c.ncta - 1) / c.ncta;
-        const int px0 = c.rank * px_per, px1 = (px0 + px_per < PX) ? (px0 + px_per) : PX;
+        const int px_per = (PX + c.ncta() - 1) / c.ncta();
+        const int px0 = c.rank() * px_per, px1 = (px0 + px_per < PX) ? (px0 + px_per) : PX;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            for (int px = px0 + c.tid; px < px1; px += c.nthreads) {
+            for (int px = px0 + c.tid(); px < ((J.debug_flags & 4) ? 0 : px1); px += c.nthreads()) {
                 const int iy = px / W, ix = px % W;
                 const float u = lin11(ix, W), v = lin11(iy, H);
                 float canvas = 0.f, nz = 0.f;
@@ -1004,7 +1172,7 @@ struct Block {
                     const float tx = cc[2 * LDS() + s * R + r], ty = cc[3 * LDS() + s * R + r];
                     const float xg = hg * ((u - tx) / sx) + hg;
                     const float yg = hg * ((v - ty) / sy) + hg;
-                    const float* gl = c.sm + m.Dgl + s * R + r;
+                    const float* gl = SQ_SM + m.Dgl + s * R + r;
                     const int lds = LDS();
                     canvas += pres * bilinear_zero_pad(xg, yg, G, G, [&](int gx, int gy) { return gl[(gy * G + gx) * lds]; });
                     nz += pres * bilinear_zero_pad(xg, yg, G, G, [&](int, int) { return 1.f; });
@@ -1017,28 +1185,28 @@ struct Block {
             }
         }
         // block reduction of the R partial sums, then the cluster's partial sums meet in every block
-        float* red = c.sm + m.Red;
+        float* red = SQ_SM + m.Red;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             float v = warp_sum(ll[r]);
-            if (c.lane == 0) red[c.warp * R + r] = v;
+            if (c.lane() == 0) red[c.warp() * R + r] = v;
         }
         c.sync();
-        for (int r = c.tid; r < R; r += c.nthreads) {
+        for (int r = c.tid(); r < R; r += c.nthreads()) {
             float a = 0.f;
-            for (int w = 0; w < c.nwarps; ++w) a += red[w * R + r];
-            if (c.ncta > 1) {
-                for (int q = 0; q < c.ncta; ++q) store_peer(c, m.RowAcc + (8 + c.rank) * R + r, q, a);
+            for (int w = 0; w < c.nwarps(); ++w) a += red[w * R + r];
+            if (c.ncta() > 1) {
+                for (int q = 0; q < c.ncta(); ++q) store_peer(c, m.RowAcc + (8 + c.rank()) * R + r, q, a);
             } else {
                 rowacc(RA_LL, r) = a;
             }
         }
-        if (c.ncta > 1) {
+        if (c.ncta() > 1) {
             cluster_arrive(c);
             cluster_wait(c);
-            for (int r = c.tid; r < R; r += c.nthreads) {
+            for (int r = c.tid(); r < R; r += c.nthreads()) {
                 float a = 0.f;
-                for (int q = 0; q < c.ncta; ++q) a += rowacc(8 + q, r);
+                for (int q = 0; q < c.ncta(); ++q) a += rowacc(8 + q, r);
                 rowacc(RA_LL, r) = a;
             }
         }
@@ -1052,12 +1220,12 @@ struct Block {
         const int NS = P.NS;
         const sqair_outputs& o = J.out;
         const size_t trow = (size_t)t * P.rows;
-        if (c.rank != 0) { c.sync(); return; }                  // replicas hold identical values
-        for (int i = c.tid; i < LDS(); i += c.nthreads) {
+        if (c.rank() != 0 || (J.debug_flags & 32)) { c.sync(); return; }                  // replicas hold identical values
+        for (int i = c.tid(); i < LDS(); i += c.nthreads()) {
             const int s = i / R, r = i % R;
             if (!valid_row(r)) continue;
             const size_t b = (trow + grow_of(r)) * NS + s;
-            if (o.obj_id) o.obj_id[b] = c.sm[m.Ids + s * R + r];
+            if (o.obj_id) o.obj_id[b] = SQ_SM[m.Ids + s * R + r];
             if (o.disc_what_log_prob) o.disc_what_log_prob[b] = lp(LP_DQWHAT, s, r);
             if (o.disc_where_log_prob) o.disc_where_log_prob[b] = lp(LP_DQWHERE, s, r);
             if (o.disc_what_prior_log_prob) o.disc_what_prior_log_prob[b] = lp(LP_DPWHAT, s, r);
@@ -1071,11 +1239,11 @@ struct Block {
             if (o.disc_pres) o.disc_pres[b] = rec(m.DiscOut, s + 1, F.pres, r);
         }
         if (o.disc_prob)
-            for (int i = c.tid; i < (NS + 1) * R; i += c.nthreads) {
+            for (int i = c.tid(); i < (NS + 1) * R; i += c.nthreads()) {
                 const int k = i / R, r = i % R;
-                if (valid_row(r)) o.disc_prob[(trow + grow_of(r)) * (NS + 1) + k] = c.sm[m.Spl + i];
+                if (valid_row(r)) o.disc_prob[(trow + grow_of(r)) * (NS + 1) + k] = SQ_SM[m.Spl + i];
             }
-        for (int r = c.tid; r < R; r += c.nthreads) {
+        for (int r = c.tid(); r < R; r += c.nthreads()) {
             if (!valid_row(r)) continue;
             // q, p in the reference's summation order: sum_s(what_s + where_s) + discrete term, disc + prop
             float pq = 0.f, pp = 0.f, dq = 0.f, dp = 0.f;
@@ -1116,28 +1284,28 @@ struct Block {
         const Smem& m = P.sm;
         const int NS = P.NS, nh = P.nh;
 #pragma unroll
-        for (int r = 0; r < R; ++r) imgrow[r] = J.obs + ((size_t)t * P.cfg.B + grow[r] / P.cfg.K) * P.P;
-        for (int i = c.tid; i < 16 * R; i += c.nthreads) c.sm[m.RowAcc + i] = 0.f;
-        for (int i = c.tid; i < nh * R; i += c.nthreads) {
-            c.sm[m.Hrnn + i] = prm(P.po.prop_h0 + i / R);          // propagate.py:170 / core.py:130
-            c.sm[m.DIn + nh * R + i] = 0.f;                         // conditioning accumulator
+        for (int r = 0; r < R; ++r) imgrow[r] = J.obs + ((size_t)t * P.cfg.B + grow[r] / P.cfg.K) * P.PX;
+        for (int i = c.tid(); i < 16 * R; i += c.nthreads()) SQ_SM[m.RowAcc + i] = 0.f;
+        for (int i = c.tid(); i < nh * R; i += c.nthreads()) {
+            SQ_SM[m.Hrnn + i] = prm(P.po.prop_h0 + i / R);          // propagate.py:170 / core.py:130
+            SQ_SM[m.DIn + nh * R + i] = 0.f;                         // conditioning accumulator
         }
         c.sync();
         for (int s = 0; s < NS; ++s) prop_slot(t, s);
         // latent summary: sum_s pres_s * MLP([what_s, where_s]) (sqair_modules.py:368-385,501)
         for (int s = 0; s < NS; ++s) {
             lin(L_LAT1, s); lin(L_LAT2);
-            for (int i = c.tid; i < nh * R; i += c.nthreads)
-                c.sm[m.DIn + nh * R + i] += c.sm[m.A1 + i] * rec(m.PropOut, s + 1, P.rec.pres, i % R);
+            for (int i = c.tid(); i < nh * R; i += c.nthreads())
+                SQ_SM[m.DIn + nh * R + i] += SQ_SM[m.A1 + i] * rec(m.PropOut, s + 1, P.rec.pres, i % R);
             c.sync();
         }
-        for (int r = c.tid; r < R; r += c.nthreads) {               // sqair_modules.py:505-507
+        for (int r = c.tid(); r < R; r += c.nthreads()) {               // sqair_modules.py:505-507
             float a = 0.f;
             for (int s = 0; s < NS; ++s) a += (sigmoidf_(pri(0, s, r)) - 0.5f) / (float)NS;
-            c.sm[m.Exp + r] = a;
+            SQ_SM[m.Exp + r] = a;
         }
         lin(L_IMG1); lin(L_IMG2);                                    // core.py:165, hoisted out of the slot loop
-        for (int i = c.tid; i < nh * R; i += c.nthreads) c.sm[m.Hrnn + i] = prm(P.po.disc_h0 + i / R);
+        for (int i = c.tid(); i < nh * R; i += c.nthreads()) SQ_SM[m.Hrnn + i] = prm(P.po.disc_h0 + i / R);
         c.sync();
         for (int s = 0; s < NS; ++s) disc_slot(t, s);
         disc_priors(t);
@@ -1147,7 +1315,7 @@ struct Block {
     }
 
     SQ_DEV void run() {
-        ring_init(c, P);
+        ring_init(c, J.prm);
         init_sequence();
         for (int t = 0; t < P.cfg.T; ++t) frame(t);
     }

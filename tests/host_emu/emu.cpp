@@ -26,7 +26,7 @@ static void pack_host(const Plan& plan, const std::vector<ParamEntry>& tab, cons
         for (int k = 0; k < pc.K; ++k)
             for (int n = 0; n < pc.N; ++n) {
                 const int vrow = pc.vrow0 + k, vcol = pc.vcol0 + n, panel = vcol / L.Nc;
-                packed[(size_t)L.w_off + (size_t)panel * L.Ktot * L.Nc + (size_t)vrow * L.Nc + (vcol - panel * L.Nc)] =
+                packed[(size_t)L.w_off + (size_t)panel * L.Ktot * L.Nc + (size_t)vrow * L.Nc + (vcol - panel * L.Nc)] +=
                     params[pc.src_off + (int64_t)k * pc.src_ld + n];
             }
     }
@@ -44,10 +44,10 @@ static void run_clusters(const Plan& plan, const Job& job) {
         cb.n = C;
         auto body = [&](int rank) {
             Ctx c{};
-            c.tid = 0; c.nthreads = 1; c.lane = 0; c.nlanes = 1; c.warp = 0; c.nwarps = 1;
-            c.sm = peers[rank]; c.rank = rank; c.ncta = C;
-            c.peers = peers.data(); c.cb = &cb; c.cb_gen = 0;
-            Block<R> blk(c, plan, job, cl * R);
+            c.tid_ = 0; c.nthreads_ = 1; c.lane_ = 0; c.nlanes_ = 1; c.warp_ = 0; c.nwarps_ = 1; c.ncompute_ = 1;
+            c.sm = peers[rank]; c.rank_ = rank; c.ncta_ = C;
+            c.peers = peers.data(); c.cb = &cb; c.cb_gen = 0; c.plan = &plan;
+            Block<R> blk(c, job, cl * R);
             blk.run();
         };
         if (C == 1) {
@@ -82,7 +82,12 @@ extern "C" int emu_forward(const sqair_cfg* cfg, const float* params, const floa
     if (!e.empty()) { fprintf(stderr, "emu: %s\n", e.c_str()); return -1; }
     std::vector<float> packed(total, 0.f);
     pack_host(plan, tab, pieces, params, packed);
-    Job job{packed.data(), obs, eps_where, eps_what, u_pres, *out};
+    for (int r = 0; r < C; ++r) {
+        std::vector<uint32_t> ct;
+        chunk_table(plan, r, ct);
+        memcpy(packed.data() + plan.ctab_off + (size_t)r * plan.ctab_stride, ct.data(), ct.size() * sizeof(uint32_t));
+    }
+    Job job{packed.data(), obs, eps_where, eps_what, u_pres, *out, 0};
     switch (R) {
         case 1: run_clusters<1>(plan, job); break;
         case 2: run_clusters<2>(plan, job); break;
