@@ -38,16 +38,30 @@ static int cuda_fail(cudaError_t e, const char* what) {
 // ---------------------------------------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(NT_LAUNCH) sqair_sequence_kernel(const __grid_constant__ Job job) {
-    const Plan& plan = c_plan;
+    const PlanHdr& plan = c_plan;
     Ctx c;
 #ifdef SQAIR_PROFILE
     for (int i = 0; i < 8; ++i) c.prof[i] = 0;
     c.t_last = clock64();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int i = 0; i < L_COUNT; ++i) g_trace[0][i] = g_trace[1][i] = g_trace[2][i] = 0;
+        g_trace_last = clock64();
+    }
 #endif
     Block<R> blk(c, job, (int)(blockIdx.x / plan.C) * R);
     blk.run();
     if (plan.C > 1) { cluster_arrive(c); cluster_wait(c); }      // no block exits while peers may still write to it
 #ifdef SQAIR_PROFILE
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        long long tin = 0, tgap = 0, n = 0;
+        for (int i = 0; i < L_COUNT; ++i) {
+            if (g_trace[2][i] == 0) continue;
+            printf("[trace] layer %2d calls %5lld  in-dense %8.0f cyc/call  gap-before %8.0f cyc/call\n", i, g_trace[2][i],
+                   (double)g_trace[0][i] / g_trace[2][i], (double)g_trace[1][i] / g_trace[2][i]);
+            tin += g_trace[0][i]; tgap += g_trace[1][i]; n += g_trace[2][i];
+        }
+        printf("[trace] total calls %lld  in-dense %lld cyc  gaps %lld cyc\n", n, tin, tgap);
+    }
     if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 32 * 7)) {
         printf("[profile tid %d] cycles: wait_full %lld  accum %lld  partials+sync %lld  finish+stores %lld  barrierB %lld  between-dense %lld | fin:redsum %lld  fin:bias+act %lld\n",
                (int)threadIdx.x, c.prof[0], c.prof[1], c.prof[2], c.prof[3], c.prof[4], c.prof[5], c.prof[6], c.prof[7]);
@@ -62,17 +76,18 @@ static const int kSmemLimit = 232448;    // 227 KB opt-in shared memory per bloc
 // The plan lives in __constant__ memory (descriptor reads are constant-bank loads).  It is re-uploaded only
 // when it changes; an upload waits for the previous launch, which may still be reading the old plan.
 static std::mutex g_plan_mutex;
-static Plan g_plan_uploaded;
+static PlanHdr g_plan_uploaded;
 static bool g_plan_valid = false;
 static cudaEvent_t g_last_launch = nullptr;
 
 static int upload_plan(const Plan& plan, cudaStream_t st) {
-    if (g_plan_valid && memcmp(&g_plan_uploaded, &plan, sizeof(Plan)) == 0) return SQAIR_OK;
+    const PlanHdr& hdr = plan;
+    if (g_plan_valid && memcmp(&g_plan_uploaded, &hdr, sizeof(PlanHdr)) == 0) return SQAIR_OK;
     if (!g_last_launch) CUDA_TRY(cudaEventCreateWithFlags(&g_last_launch, cudaEventDisableTiming));
     else CUDA_TRY(cudaEventSynchronize(g_last_launch));
-    CUDA_TRY(cudaMemcpyToSymbolAsync(c_plan, &plan, sizeof(Plan), 0, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_plan, &hdr, sizeof(PlanHdr), 0, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));         // the host copy of `plan` may be a temporary
-    g_plan_uploaded = plan;
+    g_plan_uploaded = hdr;
     g_plan_valid = true;
     return SQAIR_OK;
 }
@@ -150,25 +165,34 @@ static std::string choose_shape(const sqair_cfg& c, const std::vector<ParamEntry
 static std::string choose_shape_uncached(const sqair_cfg& c, const std::vector<ParamEntry>& tab, Shape& out) {
     const int rows = c.B * c.K;
     const int fR = env_int("SQAIR_ROWS_PER_CTA"), fC = env_int("SQAIR_CLUSTER");
-    const double W = 44e6, bw_sm = 100e9, bw_l2 = 8e12, mac_row = 11e6, fma = 128 * 1.9e9 * 0.5;
+    int stage_kb = env_int("SQAIR_STAGE_KB");
+    const int f_nstage = env_int("SQAIR_NSTAGE");
+    if (!stage_kb) stage_kb = 32;
+    // Cost model fitted to the B200 measurements in profiles/: a dense call has a fixed cost (barriers, bookkeeping,
+    // copy latency) and streams its weight panel at ring speed; one frame is `calls` dense calls.
+    const double W = 44e6, ring_bw = 50e9, fixed = 3.3e-6, mac_row = 11e6, fma = 128 * 1.9e9 * 0.25;
+    const double calls = 38.0 * c.n + 1.0;
     double best = 1e30;
     std::string err = "configuration does not fit shared memory";
+    out.R = 0;
     for (int C : kClusterChoices) {
         if (fC && C != fC) continue;
         for (int R : kRowChoices) {
             if (fR && R != fR) continue;
             if (R > rows && R != 1) continue;
+            // deepest ring that fits (at least 2 chunks of the maximum size)
             Shape s;
-            int stage_kb = env_int("SQAIR_STAGE_KB"), nstage = env_int("SQAIR_NSTAGE");
-            if (!stage_kb) stage_kb = 16;
-            if (!nstage) nstage = 3;
-            std::string e = build_plan(c, R, C, s.plan, tab, s.pieces, &s.packed_total, stage_kb * 256, nstage);
-            if (!e.empty()) { err = e; continue; }
-            if (s.plan.sm.total * (int)sizeof(float) > kSmemLimit) continue;
+            bool ok = false;
+            for (int nstage = f_nstage ? f_nstage : 4; nstage >= (f_nstage ? f_nstage : 2); --nstage) {
+                std::string e = build_plan(c, R, C, s.plan, tab, s.pieces, &s.packed_total, stage_kb * 256, nstage);
+                if (!e.empty()) { err = e; break; }
+                if (s.plan.sm.total * (int)sizeof(float) <= kSmemLimit) { ok = true; break; }
+            }
+            if (!ok) continue;
             const int ncl = (rows + R - 1) / R;
             const int max_blocks = C <= 2 ? 148 : (C == 8 ? 128 : 132);
-            double waves = (double)((ncl * C + max_blocks - 1) / max_blocks);
-            double t = waves * (W / C / bw_sm + R * mac_row / C / fma) + ncl * W / bw_l2 + (C > 1 ? 40e-6 : 0.0);
+            const double waves = (double)((ncl * C + max_blocks - 1) / max_blocks);
+            const double t = waves * (calls * fixed + W / C / ring_bw + R * mac_row / C / fma + (C > 1 ? calls * 0.3e-6 : 0.0));
             if (t < best) { best = t; s.R = R; s.C = C; out = s; }
         }
     }

@@ -36,7 +36,8 @@ constexpr int MAX_KS = 16;       // max k-slices of a dense layer
 constexpr int MAX_SLOTS = 8;
 constexpr int MAXC = 8;          // max cluster size (portable limit)
 constexpr int MAXSEQ = 400;      // dense calls per frame
-constexpr int MAX_NSTAGE = 12;   // max weight-ring stages
+constexpr int MAX_NSTAGE = 12;   // ring size in units of the maximum chunk size
+constexpr int NBAR = 16;         // chunks in flight (mbarrier slots; power of two)
 constexpr int MAXPIECE = 24;      // GEMV pieces (chunk rows x segment) per dense layer
 constexpr int DESC_WORDS = 288;  // >= sizeof(Layer) / 4, multiple of 4, <= NT_LAUNCH (one word per thread when staging)
 
@@ -108,8 +109,9 @@ struct RecF {
 struct Smem {
     int Ctl;      // [16] ints: ring position / call counters shared by the block (device only)
     int Desc;     // [2][DESC_WORDS] staged descriptors of the current / next dense call
-    int Bar;      // 2*nstage mbarriers (8 bytes each): full[nstage], empty[nstage]
-    int Ring;     // nstage * stage_floats weight stages (128-byte aligned)
+    int Bar;      // 2*NBAR mbarriers (8 bytes each): full[NBAR], empty[NBAR]
+    int Roff;     // [NBAR] ring offset (floats) of the chunk in each barrier slot, written by the producer
+    int Ring;     // weight ring: nstage * stage_floats floats, variable-size chunks (128-byte aligned)
     int Z;        // [nw+6][NS][R]: what, where(4), pres, plogit     (latents of the previous frame)
     int Ids;      // [NS][R]
     int LastId;   // [R]
@@ -158,17 +160,22 @@ struct POff {
     int cholesky;
 };
 
-struct Plan {
+// Everything the device program needs except the layer table (which is staged from global memory one call
+// ahead): small enough to stay resident in the constant cache.
+struct PlanHdr {
     sqair_cfg cfg;
     int R, C, NS, rows, nw, nh, g, PX, LDS;  // LDS = NS*R; C = cluster size; PX = H*W
     int nseq;                                 // dense calls per frame
     int ltab_off;                             // packed-parameter offset of the layer table (L_COUNT x DESC_WORDS words)
-    int ctab_off, ctab_stride, ctab_n[MAXC];  // per-rank chunk tables {offset, floats} of one frame; entries per rank
+    int ctab_off, ctab_stride, ctab_n[MAXC];  // per-rank chunk tables {src offset, floats, ring offset, wait distance} of one frame
     RecF rec;
     Smem sm;
     POff po;
-    Layer L[L_COUNT];
     unsigned char seq[MAXSEQ];                // layer ids in program order (one frame)
+};
+
+struct Plan : PlanHdr {
+    Layer L[L_COUNT];
 };
 
 // ------------------------------------------------------------------------------------------
@@ -485,26 +492,59 @@ inline std::vector<int> frame_sequence(const sqair_cfg& c) {
 }
 
 // Weight chunks of one frame for block `rank` of the cluster, in consumption order: for every dense call with a
-// panel for this rank, consecutive blocks of <= rpc rows of the panel (chunks span segment boundaries).
-inline void chunk_table(const Plan& p, int rank, std::vector<uint32_t>& tab) {
+// panel for this rank, consecutive blocks of <= rpc rows of the panel (chunks span segment boundaries).  Each entry
+// is {packed source offset, floats, ring offset, wait distance}: chunks are placed back to back in a circular
+// buffer of `ring_floats` floats (restarting at 0 every frame so that the layout is identical in every frame), and
+// before overwriting its region the producer must wait until chunk (j - distance) has been consumed -- the newest
+// older chunk that overlaps the region, or the previous user of the mbarrier slot, whichever is newer.
+inline std::string chunk_table(const Plan& p, int rank, std::vector<uint32_t>& tab) {
     tab.clear();
+    std::vector<int64_t> src;
+    std::vector<int> sz;
     for (int i = 0; i < p.nseq; ++i) {
         const Layer& L = p.L[p.seq[i]];
         if (L.split && rank >= L.npanel) continue;
         const int64_t base = (int64_t)L.w_off + (int64_t)(L.split ? rank : 0) * L.Ktot * L.Nc;
         for (int r0 = 0; r0 < L.Ktot; r0 += L.rpc) {
             const int rows = (L.Ktot - r0 < L.rpc) ? (L.Ktot - r0) : L.rpc;
-            tab.push_back((uint32_t)(base + (int64_t)r0 * L.Nc));
-            tab.push_back((uint32_t)(rows * L.Nc));
+            src.push_back(base + (int64_t)r0 * L.Nc);
+            sz.push_back(rows * L.Nc);
         }
     }
+    const int n = (int)sz.size();
+    const int ring = p.sm.nstage * p.sm.stage_floats;
+    if (n == 0) return "";
+    // two identical frames: the second one gives the steady-state dependencies across the frame boundary
+    std::vector<int> pos(2 * n), len(2 * n);
+    for (int j = 0, cur = 0; j < 2 * n; ++j) {
+        if (j == n) cur = 0;
+        const int need = (sz[j % n] + 31) / 32 * 32;
+        if (need > ring) return "ring smaller than one chunk";
+        if (cur + need > ring) cur = 0;
+        pos[j] = cur; len[j] = need;
+        cur += need;
+    }
+    for (int j = n; j < 2 * n; ++j) {
+        int dist = NBAR;                                   // previous user of the barrier slot
+        for (int d = 1; d < NBAR && d <= j; ++d) {
+            const int o = j - d;
+            if (pos[o] < pos[j] + len[j] && pos[j] < pos[o] + len[o]) { dist = d; break; }
+        }
+        // an overlapping chunk older than NBAR is implied by the slot wait; but the region must not be reused while a
+        // chunk newer than that is still unconsumed: scanning d < NBAR finds every such chunk
+        tab.push_back((uint32_t)src[j % n]);
+        tab.push_back((uint32_t)sz[j % n]);
+        tab.push_back((uint32_t)pos[j]);
+        tab.push_back((uint32_t)dist);
+    }
+    return "";
 }
 
 // Builds the plan for R rows per cluster of C blocks.  Returns "" on success, else an error message.
 // `pieces` receives the packing table; *packed_total the floats of the packed parameter buffer.
 inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const std::vector<ParamEntry>& tab,
                               std::vector<Piece>& pieces, int64_t* packed_total, int stage_floats = 4096, int nstage = 3) {
-    memset(&p, 0, sizeof(p));
+    memset((void*)&p, 0, sizeof(p));
     pieces.clear();
     p.cfg = c;
     const int NS = c.n, nw = c.n_what, nh = c.n_hidden, g = c.G * c.G, P = c.H * c.W, s = nh / 2;
@@ -520,7 +560,8 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
     m.nstage = nstage;
     if (nstage < 2 || nstage > MAX_NSTAGE) return "ring stages must be in [2, 12]";
     const int LDS = NS * R, LDE = (NS + 1) * R;
-    m.Bar = B.alloc(2 * 2 * nstage, 4);                 // 8-byte barriers
+    m.Bar = B.alloc(2 * 2 * NBAR, 4);                   // 8-byte barriers
+    m.Roff = B.alloc(NBAR);
     m.Ctl = B.alloc(16);
     m.Desc = B.alloc(2 * DESC_WORDS);
     m.Ring = B.alloc(nstage * stage_floats, 32);
@@ -859,8 +900,9 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
         int mx = 0;
         std::vector<uint32_t> t;
         for (int r = 0; r < C; ++r) {
-            chunk_table(p, r, t);
-            p.ctab_n[r] = (int)t.size() / 2;
+            std::string e2 = chunk_table(p, r, t);
+            if (!e2.empty()) return e2;
+            p.ctab_n[r] = (int)t.size() / 4;
             if ((int)t.size() > mx) mx = (int)t.size();
         }
         p.ctab_off = (int)((B.wcursor + 31) / 32 * 32);

@@ -39,7 +39,7 @@ namespace sq {
 #define SQ_PLAN_OF(ctx) (*(ctx).plan)
 #else
 extern __shared__ __align__(128) float g_smem[];
-__constant__ Plan c_plan;
+__constant__ PlanHdr c_plan;
 #define SQ_SM g_smem
 #define SQ_PLAN c_plan
 #define SQ_PLAN_OF(ctx) c_plan
@@ -150,7 +150,12 @@ SQ_DEV void st_cluster_f32(uint32_t local_addr, int rank, float v) {
 }
 #endif
 
-enum { CTL_CONS = 0, CTL_STAGE, CTL_PHASE, CTL_CALL, CTL_DESC, CTL_ISSUED, CTL_PT, CTL_PI, CTL_POFF, CTL_PNFL };
+#if defined(SQAIR_PROFILE) && !defined(SQAIR_HOST_EMU)
+__device__ long long g_trace[3][L_COUNT];      // per layer id: cycles inside dense, cycles since previous dense exit, calls
+__device__ long long g_trace_last;
+#endif
+
+enum { CTL_CONS = 0, CTL_CALL, CTL_DESC, CTL_ISSUED, CTL_PT, CTL_PI };
 
 // cluster barrier, split phase: arrive (release) ... wait (acquire)
 SQ_DEV void cluster_arrive(Ctx& c) {
@@ -261,64 +266,63 @@ SQ_DEV const float* panel_ptr(const Layer& L, const float* prm, int rank) {
 }
 
 #ifndef SQAIR_HOST_EMU
-// Producer cursor, copied out of Ctx into registers for the duration of a dense call.
-struct ProdCur {
-    int issued, p_t, p_i, p_n;
-    uint32_t p_off, p_nfl;
-    const float* p_tab;
-};
-// issue the next chunk of this block's flat chunk table (one frame's chunks, repeated every frame)
-SQ_DEV void prod_issue(ProdCur& q, const float* prm, uint32_t bar, uint32_t ring, int ns, int stage_bytes) {
-    const int stage = q.issued % ns;
-    mbar_expect_tx(bar + 8u * stage, q.p_nfl * 4u);
-    bulk_g2s(ring + (uint32_t)(stage * stage_bytes), prm + q.p_off, q.p_nfl * 4u, bar + 8u * stage);
-    ++q.issued;
-    if (++q.p_i >= q.p_n) { q.p_i = 0; ++q.p_t; }
-    // fetch the following entry now; it is needed only at the next issue
-    const uint2 e = __ldg(reinterpret_cast<const uint2*>(q.p_tab) + q.p_i);
-    q.p_off = e.x; q.p_nfl = e.y;
-}
-// Producer warp, during one dense call: keep every free stage refilled (chunks of this and the following
-// layers, in program order) until the compute warps have consumed the last chunk of this layer.
+// Producer warp, during one dense call: keep the byte-granular weight ring full -- chunks of this and the
+// following layers, in program order -- until the compute warps have consumed the last chunk of this layer.
+// Chunk j uses mbarrier slot j % NBAR; its ring offset and the chunk whose consumption frees its region come from
+// the host-built table (sqair_core.h: chunk_table).
 SQ_DEV void prod_run(Ctx& c, const float* prm, bool work, int last_chunk) {
-    const Plan& P = SQ_PLAN;
+    const auto& P = SQ_PLAN;
     if (c.lane() == 0) {
         int* ctl = reinterpret_cast<int*>(SQ_SM + P.sm.Ctl);
-        ProdCur q{ctl[CTL_ISSUED], ctl[CTL_PT], ctl[CTL_PI], P.ctab_n[c.rank()], (uint32_t)ctl[CTL_POFF], (uint32_t)ctl[CTL_PNFL],
-                  prm + P.ctab_off + c.rank() * P.ctab_stride};
+        int issued = ctl[CTL_ISSUED], p_t = ctl[CTL_PT], p_i = ctl[CTL_PI];
+        const int p_n = P.ctab_n[c.rank()], T = P.cfg.T;
+        const uint4* tab = reinterpret_cast<const uint4*>(prm + P.ctab_off + c.rank() * P.ctab_stride);
         const uint32_t bar = smem_u32(SQ_SM + P.sm.Bar), ring = smem_u32(SQ_SM + P.sm.Ring);
-        const int ns = P.sm.nstage, T = P.cfg.T, stage_bytes = P.sm.stage_floats * 4;
-        const uint32_t ebar = bar + 8u * ns;
-        while (true) {
-            while (q.p_t < T && q.p_n > 0 && mbar_test_wait(ebar + 8u * (q.issued % ns), ((q.issued / ns) & 1) ^ 1))
-                prod_issue(q, prm, bar, ring, ns, stage_bytes);
-            // done once the layer's last chunk has been issued AND released by every compute warp (the parity probe
-            // alone would also succeed before that stage was even refilled for this chunk)
-            if (!work || (q.issued > last_chunk && mbar_test_wait(ebar + 8u * (last_chunk % ns), (last_chunk / ns) & 1))) break;
+        const uint32_t ebar = bar + 8u * NBAR;
+        int* roff = reinterpret_cast<int*>(SQ_SM + P.sm.Roff);
+        // table entries are fetched four chunks ahead so that their L2 latency is off the issue path
+        auto wrap = [&](int i) { while (i >= p_n) i -= p_n; return i; };
+        uint4 e0 = make_uint4(0, 0, 0, 1), e1 = e0, e2 = e0, e3 = e0;
+        if (p_n > 0) {
+            e0 = __ldg(tab + p_i); e1 = __ldg(tab + wrap(p_i + 1)); e2 = __ldg(tab + wrap(p_i + 2)); e3 = __ldg(tab + wrap(p_i + 3));
         }
-        ctl[CTL_ISSUED] = q.issued; ctl[CTL_PT] = q.p_t; ctl[CTL_PI] = q.p_i; ctl[CTL_POFF] = (int)q.p_off; ctl[CTL_PNFL] = (int)q.p_nfl;
+        while (true) {
+            while (p_t < T && p_n > 0) {
+                const int m = issued - (int)e0.w;           // chunk whose consumption frees this chunk's region and slot
+                if (m >= 0 && !mbar_test_wait(ebar + 8u * (m & (NBAR - 1)), (m / NBAR) & 1)) break;
+                const int slot = issued & (NBAR - 1);
+                roff[slot] = (int)e0.z;
+                mbar_expect_tx(bar + 8u * slot, e0.y * 4u);
+                bulk_g2s(ring + e0.z * 4u, prm + e0.x, e0.y * 4u, bar + 8u * slot);
+                ++issued;
+                if (++p_i >= p_n) { p_i = 0; ++p_t; }
+                e0 = e1; e1 = e2; e2 = e3;
+                e3 = __ldg(tab + wrap(p_i + 3));
+            }
+            // done once the layer's last chunk has been issued AND released by every compute warp
+            if (!work || (issued > last_chunk && mbar_test_wait(ebar + 8u * (last_chunk & (NBAR - 1)), (last_chunk / NBAR) & 1))) break;
+        }
+        ctl[CTL_ISSUED] = issued; ctl[CTL_PT] = p_t; ctl[CTL_PI] = p_i;
     }
     __syncwarp();
 }
 #endif
 
 SQ_DEV void ring_init(Ctx& c, const float* prm) {
-    const Plan& P = SQ_PLAN;
+    const auto& P = SQ_PLAN;
 #ifdef SQAIR_HOST_EMU
     c.cons = 0;
     c.call_idx = 0;
 #else
     if (c.tid() == 0) {
         const uint32_t bar = smem_u32(SQ_SM + P.sm.Bar);
-        for (int i = 0; i < P.sm.nstage; ++i) {
+        for (int i = 0; i < NBAR; ++i) {
             mbar_init(bar + 8u * i, 1);                                   // full: one expect_tx arrival + bytes
-            mbar_init(bar + 8u * (P.sm.nstage + i), c.ncompute() / 32);   // empty: one arrival per compute warp
+            mbar_init(bar + 8u * (NBAR + i), c.ncompute() / 32);          // empty: one arrival per compute warp
         }
         fence_barrier_init();
         int* ctl = reinterpret_cast<int*>(SQ_SM + P.sm.Ctl);
         for (int i = 0; i < 16; ++i) ctl[i] = 0;
-        const uint2 e = __ldg(reinterpret_cast<const uint2*>(prm + P.ctab_off + c.rank() * P.ctab_stride));
-        ctl[CTL_POFF] = (int)e.x; ctl[CTL_PNFL] = (int)e.y;
     }
     if (c.tid() < DESC_WORDS) SQ_SM[P.sm.Desc + c.tid()] = SQ_LDG(prm + P.ltab_off + (int)P.seq[0] * DESC_WORDS + c.tid());
     c.sync();
@@ -417,7 +421,7 @@ SQ_DEV void chunk_accum(const float* w, int Nc, int col, int k_first, int k_step
 template <int R>
 SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot,
                     const float* const* imgrow, int dbg) {
-    const Plan& P = SQ_PLAN;
+    const auto& P = SQ_PLAN;
 #ifdef SQAIR_HOST_EMU
     const Layer& L = P.L[layer_id];
     if (P.seq[c.call_idx] != layer_id) {
@@ -430,7 +434,7 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
 #else
     // block-wide counters (shared memory): ring position, call index, descriptor slot
     int* ctl = reinterpret_cast<int*>(SQ_SM + P.sm.Ctl);
-    int cons = ctl[CTL_CONS], stage = ctl[CTL_STAGE], phase = ctl[CTL_PHASE], call_idx = ctl[CTL_CALL];
+    int cons = ctl[CTL_CONS], call_idx = ctl[CTL_CALL];
     const int desc_cur = ctl[CTL_DESC];
     if (++call_idx >= P.nseq) call_idx = 0;
     // the descriptor of this call was staged in shared memory during the previous call; start fetching the next one
@@ -439,6 +443,14 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
     if (c.tid() < DESC_WORDS) next_desc_word = SQ_LDG(prm + P.ltab_off + (int)P.seq[call_idx] * DESC_WORDS + c.tid());
 #endif
     SQ_TICK(c, 5);                               // time since the previous dense call (element-wise stages)
+#if defined(SQAIR_PROFILE) && !defined(SQAIR_HOST_EMU)
+    long long t_enter = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        t_enter = clock64();
+        g_trace[1][layer_id] += t_enter - g_trace_last;
+        g_trace[2][layer_id] += 1;
+    }
+#endif
     const bool exchange = L.split && c.ncta() > 1;
     const bool work = layer_has_work(L, c.rank());
     const int Nc = L.Nc, Gc = Nc >> 2;
@@ -466,7 +478,7 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
                 if (pc.flags & PIECE_FIRST) {
                     chunk_row0 = row0;
                     const int rows = (L.Ktot - row0 < L.rpc) ? (L.Ktot - row0) : L.rpc;
-                    const uint32_t* te = reinterpret_cast<const uint32_t*>(prm + P.ctab_off + c.rank() * P.ctab_stride) + 2 * (c.cons % P.ctab_n[c.rank()]);
+                    const uint32_t* te = reinterpret_cast<const uint32_t*>(prm + P.ctab_off + c.rank() * P.ctab_stride) + 4 * (c.cons % P.ctab_n[c.rank()]);
                     if (te[0] != (uint32_t)(panel + (size_t)row0 * Nc - prm) || te[1] != (uint32_t)(rows * Nc)) {
                         fprintf(stderr, "emu: chunk table mismatch at chunk %d (layer %d)\n", c.cons, layer_id);
                         abort();
@@ -495,7 +507,6 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
         if (c.tid() >= c.ncompute()) {
             if (!(dbg & 2)) prod_run(c, prm, true, cons + nchunk - 1);
             cons += nchunk;
-            for (int q = 0; q < nchunk; ++q) if (++stage == P.sm.nstage) { stage = 0; phase ^= 1; }
         } else {
             const int sl = c.tid() / Gc, g = c.tid() - sl * Gc;
             const bool active = sl < ks, lane0 = c.lane() == 0;
@@ -505,25 +516,29 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
 #pragma unroll
                 for (int r = 0; r < R; ++r) acc[j][r] = 0.f;
             const uint32_t bar = smem_u32(SQ_SM + P.sm.Bar);
-            const int ns = P.sm.nstage, npiece = L.npiece, stage_floats = P.sm.stage_floats;
+            const int npiece = L.npiece;
             const float* ring = SQ_SM + P.sm.Ring;
+            const int* roffs = reinterpret_cast<const int*>(SQ_SM + P.sm.Roff);
+            const float* wst = ring;
             for (int pi = 0; pi < npiece; ++pi) {
                 const GemvPiece pc = L.piece[pi];
                 const bool image = (pc.flags & PIECE_IMAGE) != 0;
                 int xoff = image ? pc.x_off : (pc.x_off + slot * pc.x_sstride);
                 const int xadv = image ? pc.n : pc.n * pc.ld;
                 for (int rep = 0; rep < pc.rep; ++rep) {
-                    if ((pc.flags & PIECE_FIRST) && !(dbg & 2)) mbar_wait(bar + 8u * stage, phase);
+                    if ((pc.flags & PIECE_FIRST) && !(dbg & 2)) {
+                        const int slot = cons & (NBAR - 1);
+                        mbar_wait(bar + 8u * slot, (cons / NBAR) & 1);
+                        wst = ring + roffs[slot];
+                    }
                     SQ_TICK(c, 0);
                     if (active && sl < pc.n && !(dbg & 1))
-                        chunk_accum<R>(ring + stage * stage_floats + pc.w_rel, Nc, g * 4, sl, ks, pc.n, image, xoff, pc.ld, SQ_SM,
-                                       imgrow, acc);
+                        chunk_accum<R>(wst + pc.w_rel, Nc, g * 4, sl, ks, pc.n, image, xoff, pc.ld, SQ_SM, imgrow, acc);
                     xoff += xadv;
                     if (pc.flags & PIECE_LAST) {
                         __syncwarp();
-                        if (lane0 && !(dbg & 2)) mbar_arrive(bar + 8u * (ns + stage));
+                        if (lane0 && !(dbg & 2)) mbar_arrive(bar + 8u * (NBAR + (cons & (NBAR - 1))));
                         ++cons;
-                        if (++stage == ns) { stage = 0; phase ^= 1; }
                     }
                     SQ_TICK(c, 1);
                 }
@@ -569,13 +584,20 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
 #ifndef SQAIR_HOST_EMU
     if (c.tid() < DESC_WORDS) SQ_SM[P.sm.Desc + (desc_cur ^ 1) * DESC_WORDS + c.tid()] = next_desc_word;
     if (c.tid() == 0) {      // every thread computed the same values; readers are behind the barrier that follows
-        ctl[CTL_CONS] = cons; ctl[CTL_STAGE] = stage; ctl[CTL_PHASE] = phase; ctl[CTL_CALL] = call_idx; ctl[CTL_DESC] = desc_cur ^ 1;
+        ctl[CTL_CONS] = cons; ctl[CTL_CALL] = call_idx; ctl[CTL_DESC] = desc_cur ^ 1;
     }
 #endif
     SQ_TICK(c, 3);
     if (exchange) { cluster_arrive(c); cluster_wait(c); }     // phase B: all slices have landed everywhere
     else c.sync();
     SQ_TICK(c, 4);
+#if defined(SQAIR_PROFILE) && !defined(SQAIR_HOST_EMU)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const long long t_exit = clock64();
+        g_trace[0][layer_id] += t_exit - t_enter;
+        g_trace_last = t_exit;
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -584,7 +606,11 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
 template <int R>
 struct Block {
     Ctx& c;
+#ifdef SQAIR_HOST_EMU
     const Plan& P;
+#else
+    const PlanHdr& P;
+#endif
     const Job& J;            // the __grid_constant__ kernel parameter (constant-bank loads)
     int row0;                       // first global row of this block
     const float* imgrow[R];         // frame of each row for the current t
