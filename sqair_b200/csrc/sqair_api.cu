@@ -200,6 +200,17 @@ static std::string choose_shape_uncached(const sqair_cfg& c, const std::vector<P
     return "";
 }
 
+// The packed layout depends on the launch shape (cluster size, ring chunk size).  sqair_pack_params records the
+// layout tag of every buffer it fills; sqair_forward refuses a buffer that was packed for a different shape.
+struct LayoutTag {
+    int C, stage_floats, nstage;
+    int64_t packed_total;
+    bool operator==(const LayoutTag& o) const { return C == o.C && stage_floats == o.stage_floats && nstage == o.nstage && packed_total == o.packed_total; }
+};
+static std::mutex g_tag_mutex;
+static std::vector<std::pair<const void*, LayoutTag>> g_tags;
+static LayoutTag tag_of(const Shape& sh) { return LayoutTag{sh.C, sh.plan.sm.stage_floats, sh.plan.sm.nstage, sh.packed_total}; }
+
 // ---------------------------------------------------------------------------------------------
 // auxiliary kernels
 // ---------------------------------------------------------------------------------------------
@@ -544,6 +555,15 @@ int sqair_pack_params(const sqair_cfg* cfg, const float* params, float* packed, 
         CUDA_TRY(cudaStreamSynchronize(st));
     }
     CUDA_TRY(cudaStreamSynchronize(st));
+    {
+        std::lock_guard<std::mutex> lock(g_tag_mutex);
+        bool found = false;
+        for (auto& kv : g_tags) if (kv.first == packed) { kv.second = tag_of(sh); found = true; }
+        if (!found) {
+            if (g_tags.size() >= 64) g_tags.erase(g_tags.begin());
+            g_tags.emplace_back((const void*)packed, tag_of(sh));
+        }
+    }
     return SQAIR_OK;
 }
 
@@ -569,6 +589,13 @@ int sqair_forward(const sqair_cfg* cfg, const float* packed_params, const float*
     Shape sh;
     e = choose_shape(*cfg, tab, sh);
     if (!e.empty()) return fail(SQAIR_EUNSUPPORTED, e);
+    {
+        std::lock_guard<std::mutex> lock(g_tag_mutex);
+        for (auto& kv : g_tags)
+            if (kv.first == packed_params && !(kv.second == tag_of(sh)))
+                return fail(SQAIR_EINVAL, "packed_params were packed for a different launch shape (cluster size / ring); "
+                                          "call sqair_pack_params with the configuration of this call");
+    }
     Job job{packed_params, obs, eps_where, eps_what, u_pres, *out, env_int("SQAIR_DEBUG_FLAGS")};
     cudaStream_t st = (cudaStream_t)stream;
     switch (sh.R) {

@@ -69,7 +69,7 @@ class ParamStore(object):
         self.cfg, self.device = cfg, device
         self.table = table(cfg)
         self.flat = torch.from_numpy(initial_values(cfg, seed, spec)).to(device)
-        self._packed, self._version, self._packed_version = None, 0, -1
+        self._version, self._packed = 0, {}
 
     def state_dict(self):
         return OrderedDict((n, self.flat[o:o + int(np.prod(s))].reshape(s)) for n, (s, o) in self.table.items())
@@ -83,9 +83,14 @@ class ParamStore(object):
         self.flat.copy_(torch.as_tensor(flat, dtype=torch.float32).reshape(-1))
         self._version += 1
 
-    def packed(self):
-        """Kernel-side copy, re-packed only after the parameters changed."""
-        if self._packed_version != self._version:
-            self._packed = ops.pack_params(self.cfg, self.flat)
-            self._packed_version = self._version
-        return self._packed
+    def packed(self, cfg=None):
+        """Kernel-side copy for a call with configuration `cfg` (the packed layout depends on the launch shape the
+        library picks for the call: cluster size and ring chunking); re-packed only after the parameters changed."""
+        cfg = cfg or self.cfg
+        s = _capi.query_sizes(cfg)
+        key = (s.cluster_size, s.packed_floats, cfg.n)
+        hit = self._packed.get(key)
+        if hit is None or hit[0] != self._version:
+            hit = (self._version, ops.pack_params(cfg, self.flat))
+            self._packed[key] = hit
+        return hit[1]

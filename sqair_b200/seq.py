@@ -98,7 +98,7 @@ class SequentialAIR(object):
             noise = ops.fill_noise(cfg, seed, row_offset, device=obs.device)
         if kernel_events is not None:
             kernel_events[0].record()
-        out = ops.forward(cfg, store.packed(), obs, noise, outputs)
+        out = ops.forward(cfg, store.packed(cfg), obs, noise, outputs)
         if kernel_events is not None:
             kernel_events[1].record()
         return AttrDict(out)

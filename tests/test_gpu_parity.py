@@ -118,10 +118,11 @@ def test_sharded_rows_reproduce_unsharded_run():
     full = ops.forward(ccfg, packed, obs, ops.fill_noise(ccfg, 99, 0, device=dev))
     half = O.Cfg(T=3, B=2, K=3, n=2)
     hcfg = TL.capi_cfg(half)
+    packed_h = ops.pack_params(hcfg, flat)          # the packed layout follows the launch shape of the call
     parts = []
     for s in range(2):
         o = obs[:, 2 * s:2 * s + 2].contiguous()
-        parts.append(ops.forward(hcfg, packed, o, ops.fill_noise(hcfg, 99, s * half.rows, device=dev)))
+        parts.append(ops.forward(hcfg, packed_h, o, ops.fill_noise(hcfg, 99, s * half.rows, device=dev)))
     torch.cuda.synchronize()
     for k in full:
         cat = torch.cat([p[k] for p in parts], 1)
