@@ -253,7 +253,7 @@ def run_cuda(args):
                                   kernel='sqair_sequence_kernel', kernel_ms=kern_ms, algorithmic_bytes=alg,
                                   note='latency-bound dependent chain of small dense layers; see DESIGN.md'),
                     elbo_iwae=float(model.last_scalars[1]))
-        line['cpu_baseline'] = cpu_baseline_sample() if world == 1 else None
+        line['cpu_baseline'] = cpu_baseline_sample() if (world == 1 and not args.no_cpu_baseline) else None
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -265,6 +265,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU oracle sample (profiling runs)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

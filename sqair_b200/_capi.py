@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libsqair_b200.so')
+LIB_PATH = os.environ.get('SQAIR_LIB') or os.path.join(_HERE, 'csrc', 'libsqair_b200.so')   # SQAIR_LIB: instrumented build (tuning only)
 
 OUTPUT_NAMES = (
     'what what_loc what_scale where where_loc where_scale presence_prob presence presence_logit '
