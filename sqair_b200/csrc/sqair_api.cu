@@ -2,7 +2,7 @@
 //
 // The hot path is ONE persistent kernel per call: `sqair_sequence_kernel<R>` runs the whole
 // T-frame Discover/Propagate recursion for R rows per thread block with all recurrent state in
-// shared memory (sqair_device.cuh).  Small auxiliary kernels: parameter packing, counter-based
+// shared memory and every dense layer on the tensor cores (sqair_device.cuh).  Small auxiliary kernels: parameter packing, counter-based
 // noise, the particle objective, and stand-alone entry points for the two bandwidth-shaped ops
 // (glimpse sampler, canvas compose + likelihood).
 #include <cuda_runtime.h>
@@ -62,15 +62,15 @@ __global__ void __launch_bounds__(NT_LAUNCH) sqair_sequence_kernel(const __grid_
         }
         printf("[trace] total calls %lld  in-dense %lld cyc  gaps %lld cyc\n", n, tin, tgap);
     }
-    if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 32 * 7)) {
-        printf("[profile tid %d] cycles: wait_full %lld  accum %lld  partials+sync %lld  finish+stores %lld  barrierB %lld  between-dense %lld | fin:redsum %lld  fin:bias+act %lld\n",
-               (int)threadIdx.x, c.prof[0], c.prof[1], c.prof[2], c.prof[3], c.prof[4], c.prof[5], c.prof[6], c.prof[7]);
+    if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 32 * 11)) {
+        printf("[profile tid %d] cycles: mma %lld  partials+sync %lld  finish+stores %lld  barrierB %lld  between-dense %lld\n",
+               (int)threadIdx.x, c.prof[1], c.prof[2], c.prof[3], c.prof[4], c.prof[5]);
     }
 #endif
 }
 
-static const int kRowChoices[] = {1, 2, 3, 4, 5};
-static const int kClusterChoices[] = {1, 2, 3, 4, 8};
+static const int kRowChoices[] = {1, 2, 3, 4, 5, 6};
+static const int kClusterChoices[] = {1, 2, 3, 4, 5, 6, 7, 8};
 static const int kSmemLimit = 232448;    // 227 KB opt-in shared memory per block on sm_100
 
 // The plan lives in __constant__ memory (descriptor reads are constant-bank loads).  It is re-uploaded only
@@ -140,7 +140,7 @@ static std::string choose_shape_uncached(const sqair_cfg& c, const std::vector<P
 // environment variables, so the last few results are cached (building ~25 candidate plans costs ~1 ms of host time).
 struct ShapeKey {
     sqair_cfg cfg;
-    int env[4];
+    int env[2];
     bool operator==(const ShapeKey& o) const { return memcmp(this, &o, sizeof(ShapeKey)) == 0; }
 };
 static std::mutex g_shape_mutex;
@@ -151,7 +151,6 @@ static std::string choose_shape(const sqair_cfg& c, const std::vector<ParamEntry
     memset(&key, 0, sizeof(key));
     key.cfg = c;
     key.env[0] = env_int("SQAIR_ROWS_PER_CTA"); key.env[1] = env_int("SQAIR_CLUSTER");
-    key.env[2] = env_int("SQAIR_STAGE_KB"); key.env[3] = env_int("SQAIR_NSTAGE");
     std::lock_guard<std::mutex> lock(g_shape_mutex);
     for (auto& kv : g_shape_cache)
         if (kv.first == key) { out = *kv.second; return ""; }
@@ -162,15 +161,20 @@ static std::string choose_shape(const sqair_cfg& c, const std::vector<ParamEntry
     return "";
 }
 
+// Blocks of a cluster of size C that can be resident at once (GPCs hold 16-18 SMs; measured on B200 with
+// cudaOccupancyMaxActiveClusters at 220 KB of shared memory per block).
+static int max_resident_blocks(int C) {
+    static const int tab[9] = {0, 148, 148, 132, 132, 120, 120, 112, 128};
+    return tab[C];
+}
+
 static std::string choose_shape_uncached(const sqair_cfg& c, const std::vector<ParamEntry>& tab, Shape& out) {
     const int rows = c.B * c.K;
     const int fR = env_int("SQAIR_ROWS_PER_CTA"), fC = env_int("SQAIR_CLUSTER");
-    int stage_kb = env_int("SQAIR_STAGE_KB");
-    const int f_nstage = env_int("SQAIR_NSTAGE");
-    if (!stage_kb) stage_kb = 32;
-    // Cost model fitted to the B200 measurements in profiles/: a dense call has a fixed cost (barriers, bookkeeping,
-    // copy latency) and streams its weight panel at ring speed; one frame is `calls` dense calls.
-    const double W = 44e6, ring_bw = 50e9, fixed = 3.3e-6, mac_row = 11e6, fma = 128 * 1.9e9 * 0.25;
+    // Cost model (B200 measurements in profiles/): a dense call has a fixed cost (barriers, descriptor, first-load
+    // latency) and streams its weight panel through the tensor-core loop at `stream_bw` per block; a frame is
+    // `calls` dense calls and touches W bytes of weights (the glimpse encoder runs three times per slot).
+    const double W = 11.1e6 * c.n * 4.0, stream_bw = 60e9, fixed = 1.5e-6;
     const double calls = 38.0 * c.n + 1.0;
     double best = 1e30;
     std::string err = "configuration does not fit shared memory";
@@ -180,19 +184,14 @@ static std::string choose_shape_uncached(const sqair_cfg& c, const std::vector<P
         for (int R : kRowChoices) {
             if (fR && R != fR) continue;
             if (R > rows && R != 1) continue;
-            // deepest ring that fits (at least 2 chunks of the maximum size)
             Shape s;
-            bool ok = false;
-            for (int nstage = f_nstage ? f_nstage : 4; nstage >= (f_nstage ? f_nstage : 2); --nstage) {
-                std::string e = build_plan(c, R, C, s.plan, tab, s.pieces, &s.packed_total, stage_kb * 256, nstage);
-                if (!e.empty()) { err = e; break; }
-                if (s.plan.sm.total * (int)sizeof(float) <= kSmemLimit) { ok = true; break; }
-            }
-            if (!ok) continue;
+            std::string e = build_plan(c, R, C, s.plan, tab, s.pieces, &s.packed_total);
+            if (!e.empty()) { err = e; continue; }
+            if (s.plan.sm.total * (int)sizeof(float) > kSmemLimit) continue;
             const int ncl = (rows + R - 1) / R;
-            const int max_blocks = C <= 2 ? 148 : (C == 8 ? 128 : 132);
+            const int max_blocks = max_resident_blocks(C);
             const double waves = (double)((ncl * C + max_blocks - 1) / max_blocks);
-            const double t = waves * (calls * fixed + W / C / ring_bw + R * mac_row / C / fma + (C > 1 ? calls * 0.3e-6 : 0.0));
+            const double t = waves * (calls * fixed + W / C / stream_bw + (C > 1 ? calls * 0.4e-6 : 0.0));
             if (t < best) { best = t; s.R = R; s.C = C; out = s; }
         }
     }
@@ -200,16 +199,16 @@ static std::string choose_shape_uncached(const sqair_cfg& c, const std::vector<P
     return "";
 }
 
-// The packed layout depends on the launch shape (cluster size, ring chunk size).  sqair_pack_params records the
+// The packed layout depends on the launch shape (cluster size).  sqair_pack_params records the
 // layout tag of every buffer it fills; sqair_forward refuses a buffer that was packed for a different shape.
 struct LayoutTag {
-    int C, stage_floats, nstage;
+    int C;
     int64_t packed_total;
-    bool operator==(const LayoutTag& o) const { return C == o.C && stage_floats == o.stage_floats && nstage == o.nstage && packed_total == o.packed_total; }
+    bool operator==(const LayoutTag& o) const { return C == o.C && packed_total == o.packed_total; }
 };
 static std::mutex g_tag_mutex;
 static std::vector<std::pair<const void*, LayoutTag>> g_tags;
-static LayoutTag tag_of(const Shape& sh) { return LayoutTag{sh.C, sh.plan.sm.stage_floats, sh.plan.sm.nstage, sh.packed_total}; }
+static LayoutTag tag_of(const Shape& sh) { return LayoutTag{sh.C, sh.packed_total}; }
 
 // ---------------------------------------------------------------------------------------------
 // auxiliary kernels
@@ -231,9 +230,9 @@ __global__ void pack_kernel(const __grid_constant__ PackTab tab, const float* __
     }
 }
 
-// canonical matrices -> per-layer column panels [Ktot][Nc] (virtual matrix of each dense layer)
+// canonical matrices -> per-layer column panels in MMA fragment order (sqair_core.h: frag_off)
 struct PieceDev {
-    int vrow0, vcol0, K, N, src_off, src_ld, w_off, Ktot, Nc;
+    int vrow0, vcol0, K, N, src_off, src_ld, w_off, ksteps, Nc, panel_floats;
 };
 struct PieceTab {
     int n;
@@ -248,7 +247,8 @@ __global__ void pack_panels_kernel(const __grid_constant__ PieceTab tab, const f
         const int k = i / pc.N, n = i - k * pc.N;
         const int vrow = pc.vrow0 + k, vcol = pc.vcol0 + n, panel = vcol / pc.Nc;
         // accumulate (the buffer was zeroed): a bias row may be the sum of two bias vectors
-        atomicAdd(&dst[(size_t)pc.w_off + (size_t)panel * pc.Ktot * pc.Nc + (size_t)vrow * pc.Nc + (vcol - panel * pc.Nc)],
+        const int cc = vcol - panel * pc.Nc;
+        atomicAdd(&dst[(size_t)pc.w_off + (size_t)panel * pc.panel_floats + frag_off(pc.ksteps, cc >> 4, vrow >> 3, cc & 15, vrow & 7)],
                   src[(size_t)pc.src_off + (size_t)k * pc.src_ld + n]);
     }
 }
@@ -533,7 +533,7 @@ int sqair_pack_params(const sqair_cfg* cfg, const float* params, float* packed, 
     for (size_t i = 0; i < sh.pieces.size(); ++i) {
         const Piece& p = sh.pieces[i];
         const Layer& L = sh.plan.L[p.layer];
-        qt.p[i] = PieceDev{p.vrow0, p.vcol0, p.K, p.N, (int)p.src_off, p.src_ld, L.w_off, L.Ktot, L.Nc};
+        qt.p[i] = PieceDev{p.vrow0, p.vcol0, p.K, p.N, (int)p.src_off, p.src_ld, L.w_off, L.ksteps, L.Nc, L.panel_floats};
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int total = (int)(tab.back().offset + tab.back().count);
@@ -546,14 +546,6 @@ int sqair_pack_params(const sqair_cfg* cfg, const float* params, float* packed, 
     std::vector<int32_t> ltab((size_t)L_COUNT * DESC_WORDS, 0);
     for (int i = 0; i < L_COUNT; ++i) memcpy(&ltab[(size_t)i * DESC_WORDS], &sh.plan.L[i], sizeof(Layer));
     CUDA_TRY(cudaMemcpyAsync(packed + sh.plan.ltab_off, ltab.data(), ltab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    for (int r = 0; r < sh.C; ++r) {
-        std::vector<uint32_t> ct;
-        chunk_table(sh.plan, r, ct);
-        if (!ct.empty())
-            CUDA_TRY(cudaMemcpyAsync(packed + sh.plan.ctab_off + (size_t)r * sh.plan.ctab_stride, ct.data(), ct.size() * sizeof(uint32_t),
-                                     cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-    }
     CUDA_TRY(cudaStreamSynchronize(st));
     {
         std::lock_guard<std::mutex> lock(g_tag_mutex);
@@ -593,7 +585,7 @@ int sqair_forward(const sqair_cfg* cfg, const float* packed_params, const float*
         std::lock_guard<std::mutex> lock(g_tag_mutex);
         for (auto& kv : g_tags)
             if (kv.first == packed_params && !(kv.second == tag_of(sh)))
-                return fail(SQAIR_EINVAL, "packed_params were packed for a different launch shape (cluster size / ring); "
+                return fail(SQAIR_EINVAL, "packed_params were packed for a different launch shape (cluster size); "
                                           "call sqair_pack_params with the configuration of this call");
     }
     Job job{packed_params, obs, eps_where, eps_what, u_pres, *out, env_int("SQAIR_DEBUG_FLAGS")};
@@ -604,6 +596,7 @@ int sqair_forward(const sqair_cfg* cfg, const float* packed_params, const float*
         case 3: return launch_sequence<3>(sh.plan, job, st);
         case 4: return launch_sequence<4>(sh.plan, job, st);
         case 5: return launch_sequence<5>(sh.plan, job, st);
+        case 6: return launch_sequence<6>(sh.plan, job, st);
     }
     return fail(SQAIR_EUNSUPPORTED, "unsupported rows per block");
 }

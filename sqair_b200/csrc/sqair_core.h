@@ -10,13 +10,15 @@
 // split by OUTPUT COLUMNS across the C blocks: block c multiplies the activations with its column
 // panel of the layer's weight matrix and writes its slice of the result into the shared memory of
 // all C blocks (distributed shared memory), so the next layer again finds the full vector locally.
-// Weights never sit in shared memory permanently: each block streams its panels from L2 through a
-// ring of stages filled by `cp.async.bulk` (TMA) copies that run ahead of the dependent chain --
-// the order of layers within a frame is static (`Plan::seq`), so the copies do not wait for data.
+// Weights never sit in shared memory: every weight is used exactly once per block and layer, so each warp
+// streams its tensor-core A fragments straight from L2 into registers (LDG.128 on a fragment-ordered copy of
+// the panel, several k-steps in flight) and multiplies them with the activations in shared memory by
+// mma.sync.m16n8k8 TF32 in three passes (hi*hi + lo*hi + hi*lo, fp32 accumulate: fp32-faithful results).
+// Out-features are the MMA M dimension, the block's rows the N dimension (R <= 8 rows ride for free).
 //
 // The schedule is data: a `Plan` holds one `Layer` descriptor per dense layer (packed weight
-// panels, input segments and output heads as shared-memory offsets) and is passed to the kernel as
-// a __grid_constant__ parameter.
+// panels, input segments and output heads as shared-memory offsets); the header lives in constant memory,
+// the layer table in global memory (staged into shared memory one call ahead).
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -26,28 +28,35 @@
 
 #include "../../include/sqair_b200.h"
 
+#ifdef __CUDACC__
+#define SQ_HD __host__ __device__ inline
+#else
+#define SQ_HD inline
+#endif
+
 namespace sq {
 
 constexpr int MAXSEG = 6;
 constexpr int MAXHEAD = 3;
-constexpr int NT = 256;          // compute threads per block
-constexpr int NT_LAUNCH = 288;   // + one producer warp that streams the weights
-constexpr int MAX_KS = 16;       // max k-slices of a dense layer
+constexpr int NT = 384;          // threads per block (12 warps)
+constexpr int NT_LAUNCH = NT;
+constexpr int NWARP = NT / 32;
+constexpr int MAX_KS = NWARP;    // max k-slices of a dense layer
 constexpr int MAX_SLOTS = 8;
 constexpr int MAXC = 8;          // max cluster size (portable limit)
 constexpr int MAXSEQ = 400;      // dense calls per frame
-constexpr int MAX_NSTAGE = 12;   // ring size in units of the maximum chunk size
-constexpr int NBAR = 16;         // chunks in flight (mbarrier slots; power of two)
-constexpr int MAXPIECE = 24;      // GEMV pieces (chunk rows x segment) per dense layer
-constexpr int DESC_WORDS = 288;  // >= sizeof(Layer) / 4, multiple of 4, <= NT_LAUNCH (one word per thread when staging)
+constexpr int MAXR = 8;          // rows per block: the N dimension of one m16n8k8 MMA
+constexpr int DESC_WORDS = 96;   // >= sizeof(Layer) / 4, multiple of 4, <= NT (one word per thread when staging)
 
 enum Act { ACT_NONE = 0, ACT_ELU = 1, ACT_SIGMOID = 2, ACT_TANH = 3, ACT_SOFTPLUS = 4 };
 enum SegKind { SEG_SMEM = 0, SEG_IMAGE = 1 };
 
 // One input segment: K consecutive rows of the layer's (virtual) weight matrix, multiplied with
 // x[k][r] = smem[x_off + slot*x_sstride + k*ld + r]  (or with the frame pixels for SEG_IMAGE).
+// In the packed weights every segment is padded with zero rows to a multiple of 8 rows (one MMA k-step never
+// straddles two segments); ks0 = index of the segment's first k-step.
 struct Seg {
-    int x_off, x_sstride, ld, K, kind;
+    int x_off, x_sstride, ld, K, kind, ks0;
 };
 
 // One output head: columns [col0, col0 + N) of the virtual matrix (col0 is a multiple of 4).
@@ -61,37 +70,30 @@ struct Head {
     int out_off, out_sstride, out_ld;
 };
 
-// One GEMV piece: `n` consecutive rows of one segment that sit in one ring chunk (repeated `rep` times for the
-// uniform full chunks of a long single segment).  Built on the host so that the device loop has no index logic.
-enum { PIECE_FIRST = 1, PIECE_LAST = 2, PIECE_IMAGE = 4 };
-struct GemvPiece {
-    int row0;        // first row in the layer's virtual matrix (used by the host emulator)
-    int w_rel;       // float offset of the piece inside its ring stage
-    int x_off;       // shared-memory offset of the piece's first input row (pixel index for PIECE_IMAGE)
-    int x_sstride;   // added per slot
-    int ld;          // floats between consecutive input rows
-    int n;           // rows
-    int flags;       // PIECE_FIRST: wait for the chunk before; PIECE_LAST: release the chunk after
-    int rep;         // repeat count; each repeat advances row0 by n, x_off by n*ld (pixel index by n)
-};
-
 struct Layer {
     int nseg, nhead;
     Seg seg[MAXSEG];
     Head head[MAXHEAD];
-    int Ktot;      // rows of the virtual matrix = sum of segment K
+    int Ktot;      // rows of the virtual matrix = sum of segment K (unpadded)
+    int ksteps;    // MMA k-steps = sum of ceil(K_seg / 8)
     int Ntot;      // columns of the virtual matrix (heads padded to multiples of 4)
     int split;     // 1: columns split across the cluster; 0: every block computes all columns (tiny layers)
-    int Nc;        // columns per panel (multiple of 4); a panel is stored [Ktot][Nc], row-major
+    int Nc;        // columns per panel (multiple of 16)
+    int nmt;       // Nc / 16: m-tiles per panel
     int npanel;    // panels with real columns (blocks with rank >= npanel idle in this layer); 1 if !split
-    int w_off;     // packed-parameter offset of panel 0; panel p at w_off + p*Ktot*Nc
-    int rpc;       // weight rows per ring chunk
-    int ks;        // k-slices of the thread mapping (thread = slice * Nc/4 + column group)
-    int gc_magic;  // ceil(2^32 / (Nc/4)): slice = umulhi(tid, gc_magic)
-    int nchunk;    // ring chunks per call
-    int npiece;
-    GemvPiece piece[MAXPIECE];
+    int w_off;     // packed-parameter offset of panel 0; panel p at w_off + p * panel_floats
+    int panel_floats;   // nmt * ksteps * 128
+    int ksplit;    // k-slices: work units = nmt * ksplit, dealt round-robin to the warps
+    int kper;      // k-steps per slice
 };
+
+// Fragment order of a panel: [m-tile][k-step][lane][4] floats = the A operand of mma.m16n8k8 (row-major 16x8 tile
+// A[m][k] = W[k-step*8 + k][m-tile*16 + m]): lane = (m%8)*4 + k%4 holds a0 = (m, k), a1 = (m+8, k), a2 = (m, k+4),
+// a3 = (m+8, k+4).  One LDG.128 per lane and k-step, 512 contiguous bytes per warp.
+SQ_HD int frag_off(int ksteps, int mt, int kstep, int m, int k) {
+    const int lane = (m & 7) * 4 + (k & 3), q = (m >> 3) + 2 * (k >> 2);
+    return ((mt * ksteps + kstep) * 32 + lane) * 4 + q;
+}
 
 enum LayerId {
     L_PGRU_ZR, L_PGRU_C, L_PLIN, L_WBMK1, L_WB2, L_MK2, L_ENC1, L_ENC2, L_ENC3_LOC, L_ENC3,
@@ -107,11 +109,8 @@ struct RecF {
 
 // Shared-memory layout (float offsets from the dynamic shared memory base).  [f][S][R] = feature-major.
 struct Smem {
-    int Ctl;      // [16] ints: ring position / call counters shared by the block (device only)
+    int Ctl;      // [16] ints: call counters shared by the block (device only)
     int Desc;     // [2][DESC_WORDS] staged descriptors of the current / next dense call
-    int Bar;      // 2*NBAR mbarriers (8 bytes each): full[NBAR], empty[NBAR]
-    int Roff;     // [NBAR] ring offset (floats) of the chunk in each barrier slot, written by the producer
-    int Ring;     // weight ring: nstage * stage_floats floats, variable-size chunks (128-byte aligned)
     int Z;        // [nw+6][NS][R]: what, where(4), pres, plogit     (latents of the previous frame)
     int Ids;      // [NS][R]
     int LastId;   // [R]
@@ -147,7 +146,7 @@ struct Smem {
     int RowAcc;   // [16][R] per-row scalars
     int Perm;     // [2NS][R] compaction order (as floats)
     int total;    // floats
-    int red_floats, stage_floats, nstage;
+    int red_floats;
 };
 
 // Packed-parameter offsets of everything that is not a dense-layer weight.
@@ -167,7 +166,6 @@ struct PlanHdr {
     int R, C, NS, rows, nw, nh, g, PX, LDS;  // LDS = NS*R; C = cluster size; PX = H*W
     int nseq;                                 // dense calls per frame
     int ltab_off;                             // packed-parameter offset of the layer table (L_COUNT x DESC_WORDS words)
-    int ctab_off, ctab_stride, ctab_n[MAXC];  // per-rank chunk tables {src offset, floats, ring offset, wait distance} of one frame
     RecF rec;
     Smem sm;
     POff po;
@@ -190,7 +188,7 @@ struct ParamEntry {
 
 // One rectangular piece of a layer's virtual weight matrix, copied from a canonical variable.
 struct Piece {
-    int layer, vrow0, vcol0, K, N;
+    int layer, vrow0, vcol0, K, N;   // vrow0 in the PADDED row space (k-step * 8 + k)
     int64_t src_off;     // canonical offset of element (row0, col0) of the source matrix
     int src_ld;
 };
@@ -333,7 +331,9 @@ struct PlanBuilder {
     int seg(Layer& l, int x_off, int ld, int K, int x_sstride = 0, int kind = SEG_SMEM) {
         Seg& s = l.seg[l.nseg];
         s.x_off = x_off; s.ld = ld; s.K = K; s.kind = kind; s.x_sstride = x_sstride;
+        s.ks0 = l.ksteps;
         l.Ktot += K;
+        l.ksteps += (K + 7) / 8;
         return l.nseg++;
     }
     // canonical offset of a bias vector (name + "/b" style variable given by packed offset lookup is not enough:
@@ -354,8 +354,7 @@ struct PlanBuilder {
         const ParamEntry* e = find(name);
         if (!e) return;
         const Layer& l = p.L[id];
-        int vr = 0;
-        for (int i = 0; i < s; ++i) vr += l.seg[i].K;
+        const int vr = l.seg[s].ks0 * 8;          // padded row space: every segment starts on a k-step
         Piece pc;
         pc.layer = id; pc.vrow0 = vr; pc.vcol0 = l.head[h].col0; pc.K = l.seg[s].K; pc.N = l.head[h].N;
         pc.src_ld = e->shape[1];
@@ -377,8 +376,8 @@ struct PlanBuilder {
         err = "bias offset not inside a variable";
         return 0;
     }
-    // Finalise a layer: fold the biases into the GEMV (one extra weight row against the constant-1 input),
-    // decide the column split, reserve the packed panels and build the GEMV piece table.
+    // Finalise a layer: fold the biases into the product (one extra weight row against the constant-1 input),
+    // decide the column split and the k-slicing, reserve the packed (fragment-ordered) panels.
     void finish(int id) {
         Layer& l = p.L[id];
         const int C = p.C;
@@ -386,7 +385,7 @@ struct PlanBuilder {
         for (int h = 0; h < l.nhead; ++h) any_bias |= (l.head[h].b_off >= 0 || l.head[h].b2_off >= 0);
         if (any_bias) {
             if (l.nseg >= MAXSEG) { err = "too many segments"; return; }
-            const int brow = l.Ktot;
+            const int brow = l.ksteps * 8;
             seg(l, p.sm.Ones, p.R, 1);
             for (int h = 0; h < l.nhead; ++h) {
                 int offs[2] = {l.head[h].b_off, l.head[h].b2_off};
@@ -404,69 +403,33 @@ struct PlanBuilder {
         int per = (l.Ntot + C - 1) / C;
         if (C > 1 && per >= 16) {
             l.split = 1;
-            l.Nc = round_up(per, 4);
+            l.Nc = round_up(per, 16);
             l.npanel = (l.Ntot + l.Nc - 1) / l.Nc;
         } else {
             l.split = 0;
-            l.Nc = l.Ntot;
+            l.Nc = round_up(l.Ntot, 16);
             l.npanel = 1;
         }
+        l.nmt = l.Nc / 16;
+        l.panel_floats = l.nmt * l.ksteps * 128;
         l.w_off = (int)wcursor;
-        wcursor += (int64_t)l.npanel * l.Ktot * l.Nc;
+        wcursor += (int64_t)l.npanel * l.panel_floats;
         wcursor = (wcursor + 31) / 32 * 32;
-        l.rpc = p.sm.stage_floats / l.Nc;
-        if (l.rpc < 1) { err = "layer too wide for a ring stage"; return; }
-        if (l.Nc / 4 > NT) { err = "layer too wide for the thread block"; return; }
-        const int Gc = l.Nc / 4;
-        l.ks = NT / Gc;
-        if (l.ks > MAX_KS) l.ks = MAX_KS;
-        l.gc_magic = (int)(((1ull << 32) + Gc - 1) / Gc);
-        l.nchunk = (l.Ktot + l.rpc - 1) / l.rpc;
-        // piece table
-        l.npiece = 0;
-        int si = 0, seg0 = 0;
-        for (int r0 = 0; r0 < l.Ktot; r0 += l.rpc) {
-            const int r1 = (r0 + l.rpc < l.Ktot) ? (r0 + l.rpc) : l.Ktot;
-            int lo = r0;
-            while (lo < r1) {
-                if (lo >= seg0 + l.seg[si].K) { seg0 += l.seg[si].K; ++si; continue; }
-                const Seg& S = l.seg[si];
-                const int hi = (seg0 + S.K < r1) ? (seg0 + S.K) : r1;
-                GemvPiece g;
-                g.row0 = lo; g.w_rel = (lo - r0) * l.Nc; g.n = hi - lo; g.rep = 1;
-                g.flags = (lo == r0 ? PIECE_FIRST : 0) | (hi == r1 ? PIECE_LAST : 0) | (S.kind == SEG_IMAGE ? PIECE_IMAGE : 0);
-                g.x_sstride = S.x_sstride; g.ld = S.ld;
-                g.x_off = (S.kind == SEG_IMAGE) ? (lo - seg0) : (S.x_off + (lo - seg0) * S.ld);
-                // merge with the previous piece when both are whole chunks of the same segment in sequence
-                bool merged = false;
-                if (l.npiece > 0) {
-                    GemvPiece& q = l.piece[l.npiece - 1];
-                    const int step = (S.kind == SEG_IMAGE) ? q.n : q.n * q.ld;
-                    if (q.flags == g.flags && (g.flags & PIECE_FIRST) && (g.flags & PIECE_LAST) && q.n == g.n && q.ld == g.ld &&
-                        q.x_sstride == g.x_sstride && q.w_rel == 0 && g.w_rel == 0 && g.row0 == q.row0 + q.rep * q.n &&
-                        g.x_off == q.x_off + q.rep * step) {
-                        ++q.rep;
-                        merged = true;
-                    }
-                }
-                if (!merged) {
-                    if (l.npiece >= MAXPIECE) { err = "too many GEMV pieces in a layer"; return; }
-                    l.piece[l.npiece++] = g;
-                }
-                lo = hi;
-            }
+        // k-slicing: minimise (units per warp) x (k-steps per unit), with a small charge per extra slice for the
+        // cross-warp reduction; slices of fewer than 2 k-steps are not worth it
+        int best = 1;
+        double best_cost = 1e30;
+        for (int ks = 1; ks <= MAX_KS; ++ks) {
+            const int kper = (l.ksteps + ks - 1) / ks;
+            if (ks > 1 && (kper < 2 || (ks - 1) * kper >= l.ksteps)) continue;
+            const int rounds = (l.nmt * ks + NWARP - 1) / NWARP;
+            const double cost = (double)rounds * (kper + 3) + 0.5 * ks;
+            if (cost < best_cost) { best_cost = cost; best = ks; }
         }
+        l.ksplit = best;
+        l.kper = (l.ksteps + best - 1) / best;
     }
 };
-
-// k-slices used by a block for a panel of Nc columns (4-column thread tiles, NT threads)
-inline int dense_ks(int Nc, int nthreads) {
-    int Gc = Nc / 4;
-    int ks = nthreads / Gc;
-    if (ks > MAX_KS) ks = MAX_KS;
-    if (ks < 1) ks = 1;
-    return ks;
-}
 
 // Dense calls of one frame in program order; must mirror Block::frame() in sqair_device.cuh (the
 // emulator asserts it on every call).
@@ -491,59 +454,10 @@ inline std::vector<int> frame_sequence(const sqair_cfg& c) {
     return q;
 }
 
-// Weight chunks of one frame for block `rank` of the cluster, in consumption order: for every dense call with a
-// panel for this rank, consecutive blocks of <= rpc rows of the panel (chunks span segment boundaries).  Each entry
-// is {packed source offset, floats, ring offset, wait distance}: chunks are placed back to back in a circular
-// buffer of `ring_floats` floats (restarting at 0 every frame so that the layout is identical in every frame), and
-// before overwriting its region the producer must wait until chunk (j - distance) has been consumed -- the newest
-// older chunk that overlaps the region, or the previous user of the mbarrier slot, whichever is newer.
-inline std::string chunk_table(const Plan& p, int rank, std::vector<uint32_t>& tab) {
-    tab.clear();
-    std::vector<int64_t> src;
-    std::vector<int> sz;
-    for (int i = 0; i < p.nseq; ++i) {
-        const Layer& L = p.L[p.seq[i]];
-        if (L.split && rank >= L.npanel) continue;
-        const int64_t base = (int64_t)L.w_off + (int64_t)(L.split ? rank : 0) * L.Ktot * L.Nc;
-        for (int r0 = 0; r0 < L.Ktot; r0 += L.rpc) {
-            const int rows = (L.Ktot - r0 < L.rpc) ? (L.Ktot - r0) : L.rpc;
-            src.push_back(base + (int64_t)r0 * L.Nc);
-            sz.push_back(rows * L.Nc);
-        }
-    }
-    const int n = (int)sz.size();
-    const int ring = p.sm.nstage * p.sm.stage_floats;
-    if (n == 0) return "";
-    // two identical frames: the second one gives the steady-state dependencies across the frame boundary
-    std::vector<int> pos(2 * n), len(2 * n);
-    for (int j = 0, cur = 0; j < 2 * n; ++j) {
-        if (j == n) cur = 0;
-        const int need = (sz[j % n] + 31) / 32 * 32;
-        if (need > ring) return "ring smaller than one chunk";
-        if (cur + need > ring) cur = 0;
-        pos[j] = cur; len[j] = need;
-        cur += need;
-    }
-    for (int j = n; j < 2 * n; ++j) {
-        int dist = NBAR;                                   // previous user of the barrier slot
-        for (int d = 1; d < NBAR && d <= j; ++d) {
-            const int o = j - d;
-            if (pos[o] < pos[j] + len[j] && pos[j] < pos[o] + len[o]) { dist = d; break; }
-        }
-        // an overlapping chunk older than NBAR is implied by the slot wait; but the region must not be reused while a
-        // chunk newer than that is still unconsumed: scanning d < NBAR finds every such chunk
-        tab.push_back((uint32_t)src[j % n]);
-        tab.push_back((uint32_t)sz[j % n]);
-        tab.push_back((uint32_t)pos[j]);
-        tab.push_back((uint32_t)dist);
-    }
-    return "";
-}
-
 // Builds the plan for R rows per cluster of C blocks.  Returns "" on success, else an error message.
 // `pieces` receives the packing table; *packed_total the floats of the packed parameter buffer.
 inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const std::vector<ParamEntry>& tab,
-                              std::vector<Piece>& pieces, int64_t* packed_total, int stage_floats = 4096, int nstage = 3) {
+                              std::vector<Piece>& pieces, int64_t* packed_total) {
     memset((void*)&p, 0, sizeof(p));
     pieces.clear();
     p.cfg = c;
@@ -556,15 +470,10 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
 
     PlanBuilder B(p, tab, pieces);
     Smem& m = p.sm;
-    m.stage_floats = stage_floats;
-    m.nstage = nstage;
-    if (nstage < 2 || nstage > MAX_NSTAGE) return "ring stages must be in [2, 12]";
+    if (R < 1 || R > MAXR) return "rows per block must be in [1, 8]";
     const int LDS = NS * R, LDE = (NS + 1) * R;
-    m.Bar = B.alloc(2 * 2 * NBAR, 4);                   // 8-byte barriers
-    m.Roff = B.alloc(NBAR);
     m.Ctl = B.alloc(16);
     m.Desc = B.alloc(2 * DESC_WORDS);
-    m.Ring = B.alloc(nstage * stage_floats, 32);
     m.Z = B.alloc((nw + 6) * LDS);
     m.Ids = B.alloc(LDS);
     m.LastId = B.alloc(R);
@@ -872,16 +781,17 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
         .head[0].scale_p_off = po.output_scale;
     B.finish(L_DEC3);
 
-    // reduction scratch: every k-slice parks its partial sums, [ks][Nc][R]
+    // reduction scratch: every k-slice parks its partial sums, [ksplit][Nc][R]
     int red = 0;
     for (int i = 0; i < L_COUNT; ++i) {
         if (p.L[i].nhead == 0) continue;
-        int r = dense_ks(p.L[i].Nc, NT) * p.L[i].Nc * R;
+        int r = p.L[i].ksplit * p.L[i].Nc * R;
         if (r > red) red = r;
     }
     if (red < 16 * R) red = 16 * R;                        // also used by the block reduction of the likelihood
     m.red_floats = red;
     m.Red = B.alloc(red);
+    B.alloc(8 * (NS + 1) * R + 64);                        // slack: B fragments over-read at most 7 feature rows
     m.total = B.cursor;
 
     std::vector<int> q = frame_sequence(c);
@@ -889,26 +799,9 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
     p.nseq = (int)q.size();
     for (size_t i = 0; i < q.size(); ++i) p.seq[i] = (unsigned char)q[i];
     static_assert(sizeof(Layer) <= DESC_WORDS * 4, "DESC_WORDS too small");
+    static_assert(DESC_WORDS <= NT, "descriptor staging uses one thread per word");
     p.ltab_off = (int)((B.wcursor + 31) / 32 * 32);
     B.wcursor = p.ltab_off + (int64_t)L_COUNT * DESC_WORDS;
-    // per-rank chunk tables
-    p.nseq = (int)frame_sequence(c).size();
-    {
-        std::vector<int> q2 = frame_sequence(c);
-        if ((int)q2.size() > MAXSEQ) return "too many dense calls per frame";
-        for (size_t i = 0; i < q2.size(); ++i) p.seq[i] = (unsigned char)q2[i];
-        int mx = 0;
-        std::vector<uint32_t> t;
-        for (int r = 0; r < C; ++r) {
-            std::string e2 = chunk_table(p, r, t);
-            if (!e2.empty()) return e2;
-            p.ctab_n[r] = (int)t.size() / 4;
-            if ((int)t.size() > mx) mx = (int)t.size();
-        }
-        p.ctab_off = (int)((B.wcursor + 31) / 32 * 32);
-        p.ctab_stride = (mx + 31) / 32 * 32;
-        B.wcursor = p.ctab_off + (int64_t)C * p.ctab_stride;
-    }
     if (packed_total) *packed_total = (B.wcursor + 31) / 32 * 32 + 32;
     return B.err;
 }

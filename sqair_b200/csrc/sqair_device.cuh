@@ -85,10 +85,9 @@ struct Ctx {
     SQ_DEV int rank() const { uint32_t r; asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return (int)r; }
     SQ_DEV int ncta() const { uint32_t r; asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return (int)r; }
 #endif
-    // Ring position / call counters.  Host emulation keeps them here; on the device they live in the shared-memory
-    // words Smem::Ctl (CTL_*), read once per dense call and written back by one thread, so that dense() never
+    // Call counters.  Host emulation keeps them here; on the device they live in the shared-memory words
+    // Smem::Ctl (CTL_*), read once per dense call and written back by one thread, so that dense() never
     // touches local memory.
-    int cons;                // weight chunks consumed so far by this block
     int call_idx;            // dense calls executed in the current frame
 #if defined(SQAIR_PROFILE)
     long long prof[8];       // cycle counters
@@ -102,51 +101,40 @@ struct Ctx {
 };
 
 #ifndef SQAIR_HOST_EMU
-// ---- PTX wrappers: mbarrier, bulk async copy (TMA), cluster barrier, distributed shared memory ----
+// ---- PTX wrappers: tensor-core MMA, streaming load, cluster barrier, distributed shared memory ----
 SQ_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-SQ_DEV void mbar_init(uint32_t bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-SQ_DEV void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-SQ_DEV void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-SQ_DEV bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// non-blocking probe (try_wait may suspend the thread for a system-dependent time when the phase is not complete)
-SQ_DEV bool mbar_test_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-SQ_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
-}
-SQ_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-SQ_DEV void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 SQ_DEV void cluster_arrive_() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 SQ_DEV void cluster_wait_() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-SQ_DEV uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 SQ_DEV void st_cluster_f32(uint32_t local_addr, int rank, float v) {
     uint32_t ra;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+// D = A(16x8, tf32) * B(8x8, tf32)
+SQ_DEV void mma_tf32_zero(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+// D += A(16x8, tf32) * B(8x8, tf32), fp32 accumulate
+SQ_DEV void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// weights are read once per block and layer: keep them out of L1
+SQ_DEV float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+// fp32 -> (hi, lo): hi = x truncated to the tf32 mantissa (so hi + r == x exactly), lo = r rounded to tf32
+SQ_DEV void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    const float r = x - __uint_as_float(hi);
+#ifdef SQAIR_TF32_TRUNC_LO
+    lo = __float_as_uint(r);                     // the tensor core ignores the low 13 bits
+#else
+    lo = __float_as_uint(r) + 0x1000u;           // round to nearest (ties away) before the tensor core drops the low 13 bits
+#endif
 }
 #endif
 
@@ -155,7 +143,7 @@ __device__ long long g_trace[3][L_COUNT];      // per layer id: cycles inside de
 __device__ long long g_trace_last;
 #endif
 
-enum { CTL_CONS = 0, CTL_CALL, CTL_DESC, CTL_ISSUED, CTL_PT, CTL_PI };
+enum { CTL_CALL = 0, CTL_DESC };
 
 // cluster barrier, split phase: arrive (release) ... wait (acquire)
 SQ_DEV void cluster_arrive(Ctx& c) {
@@ -251,76 +239,20 @@ struct Job {
     const float* eps_what;   // [T][rows][2n][nw]
     const float* u_pres;     // [T][rows][2n]
     sqair_outputs out;
-    int debug_flags;         // tuning experiments only: 1 = skip the GEMV math, 2 = skip the weight ring (garbage results)
+    int debug_flags;         // tuning experiments only: 1 = skip the MMA math (garbage results), 4/8/16/32/64 skip other stages
 };
 
-// ---------------------------------------------------------------------------------------------
-// Weight ring.  Chunks = consecutive row blocks (<= rpc rows, never straddling a segment) of this
-// block's panel of each layer, in program order (Plan::seq repeated every frame).  Thread 0 issues
-// `cp.async.bulk` copies into P.sm.nstage stages as far ahead as stages are free; all threads wait on the
-// stage's "full" mbarrier before reading and every warp arrives on its "empty" mbarrier afterwards.
-// ---------------------------------------------------------------------------------------------
 SQ_DEV bool layer_has_work(const Layer& L, int rank) { return !L.split || rank < L.npanel; }
 SQ_DEV const float* panel_ptr(const Layer& L, const float* prm, int rank) {
-    return prm + L.w_off + (size_t)(L.split ? rank : 0) * L.Ktot * L.Nc;
+    return prm + L.w_off + (size_t)(L.split ? rank : 0) * L.panel_floats;
 }
 
-#ifndef SQAIR_HOST_EMU
-// Producer warp, during one dense call: keep the byte-granular weight ring full -- chunks of this and the
-// following layers, in program order -- until the compute warps have consumed the last chunk of this layer.
-// Chunk j uses mbarrier slot j % NBAR; its ring offset and the chunk whose consumption frees its region come from
-// the host-built table (sqair_core.h: chunk_table).
-SQ_DEV void prod_run(Ctx& c, const float* prm, bool work, int last_chunk) {
-    const auto& P = SQ_PLAN;
-    if (c.lane() == 0) {
-        int* ctl = reinterpret_cast<int*>(SQ_SM + P.sm.Ctl);
-        int issued = ctl[CTL_ISSUED], p_t = ctl[CTL_PT], p_i = ctl[CTL_PI];
-        const int p_n = P.ctab_n[c.rank()], T = P.cfg.T;
-        const uint4* tab = reinterpret_cast<const uint4*>(prm + P.ctab_off + c.rank() * P.ctab_stride);
-        const uint32_t bar = smem_u32(SQ_SM + P.sm.Bar), ring = smem_u32(SQ_SM + P.sm.Ring);
-        const uint32_t ebar = bar + 8u * NBAR;
-        int* roff = reinterpret_cast<int*>(SQ_SM + P.sm.Roff);
-        // table entries are fetched four chunks ahead so that their L2 latency is off the issue path
-        auto wrap = [&](int i) { while (i >= p_n) i -= p_n; return i; };
-        uint4 e0 = make_uint4(0, 0, 0, 1), e1 = e0, e2 = e0, e3 = e0;
-        if (p_n > 0) {
-            e0 = __ldg(tab + p_i); e1 = __ldg(tab + wrap(p_i + 1)); e2 = __ldg(tab + wrap(p_i + 2)); e3 = __ldg(tab + wrap(p_i + 3));
-        }
-        while (true) {
-            while (p_t < T && p_n > 0) {
-                const int m = issued - (int)e0.w;           // chunk whose consumption frees this chunk's region and slot
-                if (m >= 0 && !mbar_test_wait(ebar + 8u * (m & (NBAR - 1)), (m / NBAR) & 1)) break;
-                const int slot = issued & (NBAR - 1);
-                roff[slot] = (int)e0.z;
-                mbar_expect_tx(bar + 8u * slot, e0.y * 4u);
-                bulk_g2s(ring + e0.z * 4u, prm + e0.x, e0.y * 4u, bar + 8u * slot);
-                ++issued;
-                if (++p_i >= p_n) { p_i = 0; ++p_t; }
-                e0 = e1; e1 = e2; e2 = e3;
-                e3 = __ldg(tab + wrap(p_i + 3));
-            }
-            // done once the layer's last chunk has been issued AND released by every compute warp
-            if (!work || (issued > last_chunk && mbar_test_wait(ebar + 8u * (last_chunk & (NBAR - 1)), (last_chunk / NBAR) & 1))) break;
-        }
-        ctl[CTL_ISSUED] = issued; ctl[CTL_PT] = p_t; ctl[CTL_PI] = p_i;
-    }
-    __syncwarp();
-}
-#endif
-
-SQ_DEV void ring_init(Ctx& c, const float* prm) {
+SQ_DEV void calls_init(Ctx& c, const float* prm) {
     const auto& P = SQ_PLAN;
 #ifdef SQAIR_HOST_EMU
-    c.cons = 0;
     c.call_idx = 0;
 #else
     if (c.tid() == 0) {
-        const uint32_t bar = smem_u32(SQ_SM + P.sm.Bar);
-        for (int i = 0; i < NBAR; ++i) {
-            mbar_init(bar + 8u * i, 1);                                   // full: one expect_tx arrival + bytes
-            mbar_init(bar + 8u * (NBAR + i), c.ncompute() / 32);          // empty: one arrival per compute warp
-        }
-        fence_barrier_init();
         int* ctl = reinterpret_cast<int*>(SQ_SM + P.sm.Ctl);
         for (int i = 0; i < 16; ++i) ctl[i] = 0;
     }
@@ -338,89 +270,96 @@ SQ_DEV int head_of(const Layer& L, int vc, int& j) {
     return -1;
 }
 
-// x[k][0..R) for one feature row (vector load when the row is 16-byte aligned: R == 4 and ld % 4 == 0)
-template <int R>
-SQ_DEV void load_x(const float* xp, bool vec, float (&x)[R]) {
-    if (R == 4 && vec) {
-        const float4 v = *reinterpret_cast<const float4*>(xp);
-        x[0] = v.x; x[1 % R] = v.y; x[2 % R] = v.z; x[3 % R] = v.w;
-    } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r) x[r] = xp[r];
-    }
-}
-template <int R>
-SQ_DEV void fma4(float (&acc)[4][R], const float4& w, const float (&x)[R]) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        acc[0][r] += w.x * x[r]; acc[1][r] += w.y * x[r]; acc[2][r] += w.z * x[r]; acc[3][r] += w.w * x[r];
-    }
+#ifndef SQAIR_HOST_EMU
+constexpr int MMA_U = 8;        // k-steps (LDG.128 per lane) in flight per warp
+
+// One k-step: acc += A * B in (almost) fp32: both operands are split into tf32 (hi, lo) and all four partial
+// products of the 8 k values are summed on the tensor core, smallest first, starting from zero; the k-step's sum
+// then joins the running sum with a round-to-nearest FADD.  (The tensor core truncates when it accumulates:
+// chaining one accumulator through hundreds of MMAs biases the result by ~1e-5 relative, ten times the fp32
+// FMA-chain error -- measured as canvas parity failures on the c2 workload.)
+SQ_DEV void mma_kstep(float (&acc)[4], const float4& a, float b0f, float b1f) {
+    uint32_t ah[4], al[4], b0h, b0l, b1h, b1l;
+    split_tf32(a.x, ah[0], al[0]); split_tf32(a.y, ah[1], al[1]);
+    split_tf32(a.z, ah[2], al[2]); split_tf32(a.w, ah[3], al[3]);
+    split_tf32(b0f, b0h, b0l); split_tf32(b1f, b1h, b1l);
+    float d[4];
+    mma_tf32_zero(d, al, b0l, b1l);
+    mma_tf32(d, al, b0h, b1h);
+    mma_tf32(d, ah, b0l, b1l);
+    mma_tf32(d, ah, b0h, b1h);
+    acc[0] += d[0]; acc[1] += d[1]; acc[2] += d[2]; acc[3] += d[3];
 }
 
-// Accumulate rows k_first, k_first + k_step, ... (< n) of a weight piece w[n][Nc] for the 4 columns starting at
-// col; xoff = shared-memory offset of the piece's first input row (pixel index for image pieces).  Four rows in flight.
-template <int R>
-SQ_DEV void chunk_accum(const float* w, int Nc, int col, int k_first, int k_step, int n, bool image, int xoff, int ld,
-                        const float* sm, const float* const* imgrow, float (&acc)[4][R]) {
-    const float* wp = w + k_first * Nc + col;
-    const int wstep = k_step * Nc;
-    int k = k_first;
-    const int krow0 = xoff;                     // image pieces: index of the piece's first pixel
-    if (!image) {
-        const int xstep = k_step * ld;
-        const float* xp = sm + xoff + k_first * ld;
-        const bool vec = (R == 4) && ((ld & 3) == 0) && ((xoff & 3) == 0);
-        for (; k + 3 * k_step < n; k += 4 * k_step) {
-            const float4 w0 = *reinterpret_cast<const float4*>(wp);
-            const float4 w1 = *reinterpret_cast<const float4*>(wp + wstep);
-            const float4 w2 = *reinterpret_cast<const float4*>(wp + 2 * wstep);
-            const float4 w3 = *reinterpret_cast<const float4*>(wp + 3 * wstep);
-            float x0[R], x1[R], x2[R], x3[R];
-            load_x<R>(xp, vec, x0); load_x<R>(xp + xstep, vec, x1); load_x<R>(xp + 2 * xstep, vec, x2); load_x<R>(xp + 3 * xstep, vec, x3);
-            fma4<R>(acc, w0, x0); fma4<R>(acc, w1, x1); fma4<R>(acc, w2, x2); fma4<R>(acc, w3, x3);
-            wp += 4 * wstep;
-            xp += 4 * xstep;
-        }
-        for (; k < n; k += k_step) {
-            const float4 w0 = *reinterpret_cast<const float4*>(wp);
-            float x0[R];
-            load_x<R>(xp, vec, x0);
-            fma4<R>(acc, w0, x0);
-            wp += wstep;
-            xp += xstep;
-        }
-    } else {    // SEG_IMAGE: x[k][r] = frame pixel k of the image of row r (global, read-only)
-        for (; k + k_step < n; k += 2 * k_step) {
-            const float4 w0 = *reinterpret_cast<const float4*>(wp);
-            const float4 w1 = *reinterpret_cast<const float4*>(wp + wstep);
-            float x0[R], x1[R];
+// One work unit: m-tile `mt` (16 output columns) x k-steps [k0, k1) of this block's panel.  The A fragments stream
+// from global memory (fragment order, 512 contiguous bytes per k-step, MMA_U k-steps in flight), the B fragments
+// (activations, x[k][row]) come from shared memory -- or from the frame for SEG_IMAGE.  The last k-step of a
+// segment may read up to 7 feature rows past the segment: the matching weight rows are zero and shared memory only
+// ever holds finite values (it is cleared at kernel start), so those products vanish.
+template <int R, bool IMAGE>
+SQ_DEV void mma_unit(const Layer& L, const float4* SQ_RESTRICT wp, int k0, int k1, int slot, const float* SQ_RESTRICT img_g,
+                     int lane, float (&acc)[4]) {
+    const int g = lane >> 2, t = lane & 3, gr = g < R ? g : R - 1;
+    float4 buf[MMA_U];
 #pragma unroll
-            for (int r = 0; r < R; ++r) { x0[r] = SQ_LDG(imgrow[r] + krow0 + k); x1[r] = SQ_LDG(imgrow[r] + krow0 + k + k_step); }
-            fma4<R>(acc, w0, x0); fma4<R>(acc, w1, x1);
-            wp += 2 * wstep;
+    for (int j = 0; j < MMA_U; ++j)
+        if (k0 + j < k1) buf[j] = ldg_stream(wp + j * 32);
+    wp += MMA_U * 32;
+    int si = 0;                                        // segment that holds k-step k0
+    while (si + 1 < L.nseg && L.seg[si + 1].ks0 <= k0) ++si;
+    int seg_end = 0, ld4 = 0, step = 0, K = 0, kloc = 0;
+    const float* xp = nullptr;
+    bool image = false;
+    auto enter_segment = [&](int ks) {
+        const Seg S = L.seg[si];
+        seg_end = (si + 1 < L.nseg) ? L.seg[si + 1].ks0 : L.ksteps;
+        image = S.kind == SEG_IMAGE;
+        K = S.K;
+        kloc = (ks - S.ks0) * 8 + t;
+        ld4 = 4 * S.ld; step = 8 * S.ld;
+        xp = SQ_SM + S.x_off + slot * S.x_sstride + gr + kloc * S.ld;
+    };
+    enter_segment(k0);
+    auto kstep = [&](int ks, float4& slot_buf, bool refill) {
+        const float4 a = slot_buf;
+        if (ks == seg_end) { ++si; enter_segment(ks); }
+        float b0f, b1f;
+        if (!IMAGE || !image) {
+            b0f = xp[0]; b1f = xp[ld4];
+            xp += step;
+        } else {
+            int ka = kloc, kb = kloc + 4;
+            if (kb >= K) { ka = ka < K ? ka : K - 1; kb = K - 1; }
+            b0f = SQ_LDG(img_g + ka); b1f = SQ_LDG(img_g + kb);
+            kloc += 8;
         }
-        for (; k < n; k += k_step) {
-            const float4 w0 = *reinterpret_cast<const float4*>(wp);
-            float x0[R];
+        mma_kstep(acc, a, b0f, b1f);
+        if (refill) slot_buf = ldg_stream(wp);         // issued after the MMAs that consumed this slot (both are volatile)
+        wp += 32;
+    };
+    int kk = k0;
+    for (; kk + 2 * MMA_U <= k1; kk += MMA_U) {        // steady state: every slot is refilled
 #pragma unroll
-            for (int r = 0; r < R; ++r) x0[r] = SQ_LDG(imgrow[r] + krow0 + k);
-            fma4<R>(acc, w0, x0);
-            wp += wstep;
-        }
+        for (int j = 0; j < MMA_U; ++j) kstep(kk + j, buf[j], true);
+    }
+    for (; kk < k1; kk += MMA_U) {                     // last one or two groups
+#pragma unroll
+        for (int j = 0; j < MMA_U; ++j)
+            if (kk + j < k1) kstep(kk + j, buf[j], kk + j + MMA_U < k1);
     }
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Dense layer (snt.Linear / Nonlinear, neural.py:34-47; VanillaRNN / GRU gate pre-activations):
 //   out[col][r] = act( sum_seg sum_k W[k][col] * x_seg[k][r] + b[col] (+ b2[col]) ) * scale + add
-// Block `rank` owns the virtual columns [rank*Nc, rank*Nc + Nc) when the layer is split.  Thread tile:
-// 4 adjacent columns x R rows; the rows of every weight chunk are dealt round-robin to `ks` k-slices
-// whose partial sums meet in shared memory; all threads then finish one output each (bias,
-// activation) and store it into every block of the cluster.
+// Block `rank` owns the virtual columns [rank*Nc, rank*Nc + Nc) when the layer is split.  Work units =
+// (m-tile of 16 columns) x (k-slice), dealt round-robin to the warps; the slices' partial sums meet in shared
+// memory; all threads then finish one output each (activation) and store it into every block of the cluster.
 // ---------------------------------------------------------------------------------------------
 template <int R>
 SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot,
-                    const float* const* imgrow, int dbg) {
+                    const float* const* imgrow, const float* SQ_RESTRICT img_g, int dbg) {
     const auto& P = SQ_PLAN;
 #ifdef SQAIR_HOST_EMU
     const Layer& L = P.L[layer_id];
@@ -428,19 +367,19 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
         fprintf(stderr, "emu: dense call %d is layer %d but Plan::seq says %d\n", c.call_idx, layer_id, P.seq[c.call_idx]);
         abort();
     }
-#endif
-#ifdef SQAIR_HOST_EMU
     if (++c.call_idx >= P.nseq) c.call_idx = 0;
+    (void)img_g;
 #else
-    // block-wide counters (shared memory): ring position, call index, descriptor slot
+    // block-wide counters (shared memory): call index, descriptor slot
     int* ctl = reinterpret_cast<int*>(SQ_SM + P.sm.Ctl);
-    int cons = ctl[CTL_CONS], call_idx = ctl[CTL_CALL];
+    int call_idx = ctl[CTL_CALL];
     const int desc_cur = ctl[CTL_DESC];
     if (++call_idx >= P.nseq) call_idx = 0;
     // the descriptor of this call was staged in shared memory during the previous call; start fetching the next one
     const Layer& L = *reinterpret_cast<const Layer*>(SQ_SM + P.sm.Desc + desc_cur * DESC_WORDS);
     float next_desc_word = 0.f;
     if (c.tid() < DESC_WORDS) next_desc_word = SQ_LDG(prm + P.ltab_off + (int)P.seq[call_idx] * DESC_WORDS + c.tid());
+    (void)imgrow;
 #endif
     SQ_TICK(c, 5);                               // time since the previous dense call (element-wise stages)
 #if defined(SQAIR_PROFILE) && !defined(SQAIR_HOST_EMU)
@@ -453,7 +392,7 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
 #endif
     const bool exchange = L.split && c.ncta() > 1;
     const bool work = layer_has_work(L, c.rank());
-    const int Nc = L.Nc, Gc = Nc >> 2;
+    const int Nc = L.Nc;
     // Phase A ("nobody writes my buffers before I have entered this layer") is only needed if an element-wise
     // stage could still touch the output buffer of the dense call that follows it; the frame program never does
     // (audited in DESIGN.md), so it is compiled in only for debugging.
@@ -466,96 +405,47 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
     std::vector<float> redv;
 #endif
     if (work) {
-#ifdef SQAIR_HOST_EMU
-        // one sequential thread: all column groups, accumulators on the heap; walks the same piece table as the device
-        std::vector<float> accs((size_t)Gc * 4 * R, 0.f);
         const float* panel = panel_ptr(L, prm, c.rank());
-        int chunk_row0 = 0;
-        for (int pi = 0; pi < L.npiece; ++pi) {
-            const GemvPiece& pc = L.piece[pi];
-            for (int rep = 0; rep < pc.rep; ++rep) {
-                const int row0 = pc.row0 + rep * pc.n;
-                if (pc.flags & PIECE_FIRST) {
-                    chunk_row0 = row0;
-                    const int rows = (L.Ktot - row0 < L.rpc) ? (L.Ktot - row0) : L.rpc;
-                    const uint32_t* te = reinterpret_cast<const uint32_t*>(prm + P.ctab_off + c.rank() * P.ctab_stride) + 4 * (c.cons % P.ctab_n[c.rank()]);
-                    if (te[0] != (uint32_t)(panel + (size_t)row0 * Nc - prm) || te[1] != (uint32_t)(rows * Nc)) {
-                        fprintf(stderr, "emu: chunk table mismatch at chunk %d (layer %d)\n", c.cons, layer_id);
+#ifdef SQAIR_HOST_EMU
+        // one sequential thread: plain fp32 dot products over the same fragment-ordered panel and segment table
+        redv.assign((size_t)Nc * R, 0.f);
+        for (int col = 0; col < Nc; ++col)
+            for (int si = 0; si < L.nseg; ++si) {
+                const Seg& S = L.seg[si];
+                for (int k = 0; k < S.K; ++k) {
+                    const float w = panel[frag_off(L.ksteps, col >> 4, S.ks0 + (k >> 3), col & 15, k & 7)];
+                    for (int r = 0; r < R; ++r) {
+                        const float x = S.kind == SEG_IMAGE ? imgrow[r][k] : SQ_SM[S.x_off + slot * S.x_sstride + k * S.ld + r];
+                        redv[(size_t)col * R + r] += w * x;
+                    }
+                }
+                // the zero padding of the packed panel must really be zero
+                for (int k = S.K; k < (S.K + 7) / 8 * 8; ++k)
+                    if (panel[frag_off(L.ksteps, col >> 4, S.ks0 + (k >> 3), col & 15, k & 7)] != 0.f) {
+                        fprintf(stderr, "emu: non-zero padding weight (layer %d)\n", layer_id);
                         abort();
                     }
-                }
-                if (pc.w_rel != (row0 - chunk_row0) * Nc) { fprintf(stderr, "emu: bad piece w_rel (layer %d)\n", layer_id); abort(); }
-                const bool image = (pc.flags & PIECE_IMAGE) != 0;
-                const int xoff = image ? (pc.x_off + rep * pc.n) : (pc.x_off + slot * pc.x_sstride + rep * pc.n * pc.ld);
-                const float* w = panel + (size_t)row0 * Nc;
-                for (int g = 0; g < Gc; ++g) {
-                    float acc[4][R];
-                    for (int j = 0; j < 4; ++j) for (int r = 0; r < R; ++r) acc[j][r] = accs[((size_t)g * 4 + j) * R + r];
-                    chunk_accum<R>(w, Nc, g * 4, 0, 1, pc.n, image, xoff, pc.ld, SQ_SM, imgrow, acc);
-                    for (int j = 0; j < 4; ++j) for (int r = 0; r < R; ++r) accs[((size_t)g * 4 + j) * R + r] = acc[j][r];
-                }
-                if (pc.flags & PIECE_LAST) ++c.cons;
             }
-        }
-        redv.resize((size_t)Nc * R);
-        for (int g = 0; g < Gc; ++g)
-            for (int j = 0; j < 4; ++j) for (int r = 0; r < R; ++r) redv[(size_t)(g * 4 + j) * R + r] = accs[((size_t)g * 4 + j) * R + r];
         red = redv.data();
 #else
-        ks = L.ks;
-        const int nchunk = L.nchunk;
-        if (c.tid() >= c.ncompute()) {
-            if (!(dbg & 2)) prod_run(c, prm, true, cons + nchunk - 1);
-            cons += nchunk;
-        } else {
-            const int sl = c.tid() / Gc, g = c.tid() - sl * Gc;
-            const bool active = sl < ks, lane0 = c.lane() == 0;
-            float acc[4][R];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int r = 0; r < R; ++r) acc[j][r] = 0.f;
-            const uint32_t bar = smem_u32(SQ_SM + P.sm.Bar);
-            const int npiece = L.npiece;
-            const float* ring = SQ_SM + P.sm.Ring;
-            const int* roffs = reinterpret_cast<const int*>(SQ_SM + P.sm.Roff);
-            const float* wst = ring;
-            for (int pi = 0; pi < npiece; ++pi) {
-                const GemvPiece pc = L.piece[pi];
-                const bool image = (pc.flags & PIECE_IMAGE) != 0;
-                int xoff = image ? pc.x_off : (pc.x_off + slot * pc.x_sstride);
-                const int xadv = image ? pc.n : pc.n * pc.ld;
-                for (int rep = 0; rep < pc.rep; ++rep) {
-                    if ((pc.flags & PIECE_FIRST) && !(dbg & 2)) {
-                        const int slot = cons & (NBAR - 1);
-                        mbar_wait(bar + 8u * slot, (cons / NBAR) & 1);
-                        wst = ring + roffs[slot];
-                    }
-                    SQ_TICK(c, 0);
-                    if (active && sl < pc.n && !(dbg & 1))
-                        chunk_accum<R>(wst + pc.w_rel, Nc, g * 4, sl, ks, pc.n, image, xoff, pc.ld, SQ_SM, imgrow, acc);
-                    xoff += xadv;
-                    if (pc.flags & PIECE_LAST) {
-                        __syncwarp();
-                        if (lane0 && !(dbg & 2)) mbar_arrive(bar + 8u * (NBAR + (cons & (NBAR - 1))));
-                        ++cons;
-                    }
-                    SQ_TICK(c, 1);
-                }
-            }
-            if (active) {
-                float* rp = red + ((size_t)sl * Nc + g * 4) * R;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int r = 0; r < R; ++r) rp[j * R + r] = acc[j][r];
-            }
+        ks = L.ksplit;
+        const int nmt = L.nmt, kper = L.kper, ksteps = L.ksteps, nunits = nmt * ks;
+        const int lane = c.lane(), g = lane >> 2, t = lane & 3;
+        for (int u = c.warp(); u < ((dbg & 1) ? 0 : nunits); u += NWARP) {
+            const int sl = u / nmt, mt = u - sl * nmt;
+            const int k0 = sl * kper, k1 = (k0 + kper < ksteps) ? (k0 + kper) : ksteps;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const float4* wp = reinterpret_cast<const float4*>(panel) + ((size_t)mt * ksteps + k0) * 32 + lane;
+            if (L.seg[0].kind == SEG_IMAGE) mma_unit<R, true>(L, wp, k0, k1, slot, img_g, lane, acc);
+            else mma_unit<R, false>(L, wp, k0, k1, slot, img_g, lane, acc);
+            // C fragment: acc[0] = (col g, row 2t), acc[1] = (g, 2t+1), acc[2] = (g+8, 2t), acc[3] = (g+8, 2t+1)
+            float* rp = red + ((size_t)sl * Nc + mt * 16 + g) * R;
+            if (2 * t < R) { rp[2 * t] = acc[0]; rp[8 * R + 2 * t] = acc[2]; }
+            if (2 * t + 1 < R) { rp[2 * t + 1] = acc[1]; rp[8 * R + 2 * t + 1] = acc[3]; }
         }
+        SQ_TICK(c, 1);
 #endif
     }
-#ifndef SQAIR_HOST_EMU
-    else if (c.tid() >= c.ncompute() && !(dbg & 2)) prod_run(c, prm, false, 0);
-#endif
     c.sync();
     SQ_TICK(c, 2);
 #ifdef SQAIR_SAFE_EXCHANGE
@@ -571,7 +461,7 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
             const Head& H = L.head[h];
             float v = 0.f;
             for (int s2 = 0; s2 < ks; ++s2) v += red[((size_t)s2 * Nc + col) * R + r];
-            v = actf(H.act, v) * H.scale + H.add;                     // the bias arrived through the GEMV (constant-1 input)
+            v = actf(H.act, v) * H.scale + H.add;                     // the bias arrived through the product (constant-1 input)
             if (H.scale_p_off >= 0) v *= SQ_LDG(prm + H.scale_p_off);
             const int off = H.out_off + slot * H.out_sstride + j * H.out_ld + r;
             if (exchange) {
@@ -584,7 +474,7 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
 #ifndef SQAIR_HOST_EMU
     if (c.tid() < DESC_WORDS) SQ_SM[P.sm.Desc + (desc_cur ^ 1) * DESC_WORDS + c.tid()] = next_desc_word;
     if (c.tid() == 0) {      // every thread computed the same values; readers are behind the barrier that follows
-        ctl[CTL_CONS] = cons; ctl[CTL_CALL] = call_idx; ctl[CTL_DESC] = desc_cur ^ 1;
+        ctl[CTL_CALL] = call_idx; ctl[CTL_DESC] = desc_cur ^ 1;
     }
 #endif
     SQ_TICK(c, 3);
@@ -614,6 +504,7 @@ struct Block {
     const Job& J;            // the __grid_constant__ kernel parameter (constant-bank loads)
     int row0;                       // first global row of this block
     const float* imgrow[R];         // frame of each row for the current t
+    const float* img_g;             // frame of the row this lane feeds to the MMA B fragment (row min(lane / 4, R - 1))
     int grow[R];                    // global row (clamped) of each local row
     bool valid[R];
 
@@ -625,6 +516,7 @@ struct Block {
             grow[r] = valid[r] ? gr : P.rows - 1;
             imgrow[r] = nullptr;
         }
+        img_g = nullptr;
     }
     // accessors ------------------------------------------------------------------------------
     SQ_DEV float* sm() const { return SQ_SM; }
@@ -638,7 +530,7 @@ struct Block {
     SQ_DEV float prm(int off) const { return SQ_LDG(J.prm + off); }
     SQ_DEV void lin(int id, int slot = 0) const {
         if (J.debug_flags & 64) return;
-        dense<R>(c, J.prm, id, slot, imgrow, J.debug_flags);
+        dense<R>(c, J.prm, id, slot, imgrow, img_g, J.debug_flags);
     }
     SQ_DEV size_t nidx(int t, int r, int slot2) const {      // noise index of (t, row, slot in [0,2n))
         return ((size_t)t * P.rows + grow[r]) * (2 * P.NS) + slot2;
@@ -653,6 +545,12 @@ struct Block {
     SQ_DEV void init_sequence() const {
         const Smem& m = P.sm;
         const int nh = P.nh, nw = P.nw, NS = P.NS;
+#ifndef SQAIR_HOST_EMU
+        // every shared-memory word must be finite: the MMA B fragments may over-read into neighbouring buffers
+        // (against zero weights).  The staged descriptor and the counters written by calls_init() stay.
+        for (int i = m.Desc + 2 * DESC_WORDS + c.tid(); i < m.total; i += c.nthreads()) SQ_SM[i] = 0.f;
+        c.sync();
+#endif
         for (int i = c.tid(); i < (nw + 6) * LDS(); i += c.nthreads()) SQ_SM[m.Z + i] = 0.f;
         for (int i = c.tid(); i < LDS(); i += c.nthreads()) SQ_SM[m.Ids + i] = -1.f;
         for (int i = c.tid(); i < R; i += c.nthreads()) { SQ_SM[m.LastId + i] = -1.f; SQ_SM[m.Ones + i] = 1.f; }
@@ -1311,6 +1209,12 @@ struct Block {
         const int NS = P.NS, nh = P.nh;
 #pragma unroll
         for (int r = 0; r < R; ++r) imgrow[r] = J.obs + ((size_t)t * P.cfg.B + grow[r] / P.cfg.K) * P.PX;
+        {
+            const int g = c.lane() >> 2;
+            img_g = imgrow[R - 1];
+#pragma unroll
+            for (int r = 0; r < R - 1; ++r) if (g == r) img_g = imgrow[r];
+        }
         for (int i = c.tid(); i < 16 * R; i += c.nthreads()) SQ_SM[m.RowAcc + i] = 0.f;
         for (int i = c.tid(); i < nh * R; i += c.nthreads()) {
             SQ_SM[m.Hrnn + i] = prm(P.po.prop_h0 + i / R);          // propagate.py:170 / core.py:130
@@ -1341,7 +1245,7 @@ struct Block {
     }
 
     SQ_DEV void run() {
-        ring_init(c, J.prm);
+        calls_init(c, J.prm);
         init_sequence();
         for (int t = 0; t < P.cfg.T; ++t) frame(t);
     }

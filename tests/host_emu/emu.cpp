@@ -3,8 +3,8 @@
 // Compiles sqair_b200/csrc/sqair_device.cuh with SQAIR_HOST_EMU: every thread block becomes one
 // sequential host thread (tid 0 of 1), block barriers are no-ops, a cluster of C blocks becomes C
 // host threads that exchange layer outputs through each other's "shared memory" arrays and meet at
-// a split-phase barrier, and the weight ring is bypassed (chunks are read in place from the packed
-// buffer, in the same chunk order).  This lets the kernel's arithmetic, indexing, packing tables,
+// a split-phase barrier, and the tensor-core product is replaced by plain fp32 dot products over the
+// same fragment-ordered packed panels and segment tables.  This lets the kernel's arithmetic, indexing, packing tables,
 // column split and slot bookkeeping be checked against the oracle on a machine without a GPU.  It
 // is never loaded by the sqair_b200 package; the product path is the CUDA library only.
 #define SQAIR_HOST_EMU 1
@@ -25,8 +25,8 @@ static void pack_host(const Plan& plan, const std::vector<ParamEntry>& tab, cons
         const Layer& L = plan.L[pc.layer];
         for (int k = 0; k < pc.K; ++k)
             for (int n = 0; n < pc.N; ++n) {
-                const int vrow = pc.vrow0 + k, vcol = pc.vcol0 + n, panel = vcol / L.Nc;
-                packed[(size_t)L.w_off + (size_t)panel * L.Ktot * L.Nc + (size_t)vrow * L.Nc + (vcol - panel * L.Nc)] +=
+                const int vrow = pc.vrow0 + k, vcol = pc.vcol0 + n, panel = vcol / L.Nc, cc = vcol - panel * L.Nc;
+                packed[(size_t)L.w_off + (size_t)panel * L.panel_floats + frag_off(L.ksteps, cc >> 4, vrow >> 3, cc & 15, vrow & 7)] +=
                     params[pc.src_off + (int64_t)k * pc.src_ld + n];
             }
     }
@@ -82,11 +82,6 @@ extern "C" int emu_forward(const sqair_cfg* cfg, const float* params, const floa
     if (!e.empty()) { fprintf(stderr, "emu: %s\n", e.c_str()); return -1; }
     std::vector<float> packed(total, 0.f);
     pack_host(plan, tab, pieces, params, packed);
-    for (int r = 0; r < C; ++r) {
-        std::vector<uint32_t> ct;
-        chunk_table(plan, r, ct);
-        memcpy(packed.data() + plan.ctab_off + (size_t)r * plan.ctab_stride, ct.data(), ct.size() * sizeof(uint32_t));
-    }
     Job job{packed.data(), obs, eps_where, eps_what, u_pres, *out, 0};
     switch (R) {
         case 1: run_clusters<1>(plan, job); break;
@@ -94,6 +89,7 @@ extern "C" int emu_forward(const sqair_cfg* cfg, const float* params, const floa
         case 3: run_clusters<3>(plan, job); break;
         case 4: run_clusters<4>(plan, job); break;
         case 5: run_clusters<5>(plan, job); break;
+        case 6: run_clusters<6>(plan, job); break;
         default: fprintf(stderr, "emu: unsupported R=%d\n", R); return -2;
     }
     return 0;

@@ -16,16 +16,15 @@ def main():
     noise = ops.fill_noise(cfg, 7, 0, device=dev)
     outs = ops.alloc_outputs(cfg, dev)
     res = {}
-    shapes = [tuple(int(v) for v in x.split(':')) for x in os.environ.get('SWEEP', '4:3:16:4,3:2:32:3,3:2:16:6,2:2:32:4,2:1:32:4,2:1:16:8,1:1:32:4,4:4:16:3,3:4:32:3').split(',')]
-    for R, C, KB, NS in shapes:
-        os.environ['SQAIR_STAGE_KB'] = str(KB); os.environ['SQAIR_NSTAGE'] = str(NS)
+    shapes = [tuple(int(v) for v in x.split(':')) for x in os.environ.get('SWEEP', '4:3,5:4,6:5,6:4,4:2,3:2,2:1,6:2,5:3,4:4').split(',')]
+    for R, C in shapes:
         os.environ['SQAIR_ROWS_PER_CTA'] = str(R)
         os.environ['SQAIR_CLUSTER'] = str(C)
         try:
             s = _capi.query_sizes(cfg)
             packed = ops.pack_params(cfg, flat)
         except Exception as e:
-            print('R=%d C=%d %dKBx%d: %s' % (R, C, KB, NS, e)); continue
+            print('R=%d C=%d: %s' % (R, C, e)); continue
         for _ in range(3):
             ops.forward(cfg, packed, obs, noise, outs)
         torch.cuda.synchronize()
@@ -35,8 +34,8 @@ def main():
             ops.forward(cfg, packed, obs, noise, outs)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        res['%d:%d:%d:%d' % (R, C, KB, NS)] = ms
-        print('R=%d C=%d ring %dKBx%d ctas=%d smem=%d B: %.3f ms/step  %.0f frames/s' % (R, C, KB, NS, s.n_ctas, s.smem_bytes, ms, B * T / ms * 1e3), flush=True)
+        res['%d:%d' % (R, C)] = ms
+        print('R=%d C=%d ctas=%d smem=%d B: %.3f ms/step  %.0f frames/s' % (R, C, s.n_ctas, s.smem_bytes, ms, B * T / ms * 1e3), flush=True)
     os.environ.pop('SQAIR_ROWS_PER_CTA', None); os.environ.pop('SQAIR_CLUSTER', None)
     print(json.dumps(res))
 
