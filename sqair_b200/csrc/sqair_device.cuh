@@ -283,12 +283,12 @@ SQ_DEV void mma_kstep(float (&acc)[4], const float4& a, float b0f, float b1f) {
     split_tf32(a.x, ah[0], al[0]); split_tf32(a.y, ah[1], al[1]);
     split_tf32(a.z, ah[2], al[2]); split_tf32(a.w, ah[3], al[3]);
     split_tf32(b0f, b0h, b0l); split_tf32(b1f, b1h, b1l);
-    float d[4];
+    float d[4], e[4];                               // two independent chains (an MMA has ~21 cycles of latency)
     mma_tf32_zero(d, al, b0l, b1l);
+    mma_tf32_zero(e, ah, b0l, b1l);
     mma_tf32(d, al, b0h, b1h);
-    mma_tf32(d, ah, b0l, b1l);
-    mma_tf32(d, ah, b0h, b1h);
-    acc[0] += d[0]; acc[1] += d[1]; acc[2] += d[2]; acc[3] += d[3];
+    mma_tf32(e, ah, b0h, b1h);
+    acc[0] += d[0] + e[0]; acc[1] += d[1] + e[1]; acc[2] += d[2] + e[2]; acc[3] += d[3] + e[3];
 }
 
 // One work unit: m-tile `mt` (16 output columns) x k-steps [k0, k1) of this block's panel.  The A fragments stream
