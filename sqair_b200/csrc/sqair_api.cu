@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(NT_LAUNCH) sqair_sequence_kernel(const __grid_
         printf("[trace] total calls %lld  in-dense %lld cyc  gaps %lld cyc\n", n, tin, tgap);
     }
     if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 32 * 11)) {
-        printf("[profile tid %d] cycles: mma %lld  partials+sync %lld  finish+stores %lld  barrierB %lld  between-dense %lld\n",
-               (int)threadIdx.x, c.prof[1], c.prof[2], c.prof[3], c.prof[4], c.prof[5]);
+        printf("[profile tid %d] cycles: call-prologue %lld  mma-units %lld (%lld units, %lld k-steps)  partials+sync %lld  finish+stores %lld  barrierB %lld  between-dense %lld\n",
+               (int)threadIdx.x, c.prof[0], c.prof[1], c.prof[7], c.prof[6], c.prof[2], c.prof[3], c.prof[4], c.prof[5]);
     }
 #endif
 }
@@ -590,6 +590,9 @@ int sqair_forward(const sqair_cfg* cfg, const float* packed_params, const float*
     }
     Job job{packed_params, obs, eps_where, eps_what, u_pres, *out, env_int("SQAIR_DEBUG_FLAGS")};
     cudaStream_t st = (cudaStream_t)stream;
+#ifdef SQAIR_ONLY_R              // tuning builds: one instantiation compiles in seconds
+    if (sh.R == SQAIR_ONLY_R) return launch_sequence<SQAIR_ONLY_R>(sh.plan, job, st);
+#else
     switch (sh.R) {
         case 1: return launch_sequence<1>(sh.plan, job, st);
         case 2: return launch_sequence<2>(sh.plan, job, st);
@@ -598,6 +601,7 @@ int sqair_forward(const sqair_cfg* cfg, const float* packed_params, const float*
         case 5: return launch_sequence<5>(sh.plan, job, st);
         case 6: return launch_sequence<6>(sh.plan, job, st);
     }
+#endif
     return fail(SQAIR_EUNSUPPORTED, "unsupported rows per block");
 }
 

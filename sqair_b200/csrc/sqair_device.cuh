@@ -120,10 +120,10 @@ SQ_DEV void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// weights are read once per block and layer: keep them out of L1
+// plain read-only loads: when streaming they sustain 117 GB/s per SM, L1::no_allocate only 74 (tools/ldg_stream.cu)
 SQ_DEV float4 ldg_stream(const float4* p) {
     float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
 // fp32 -> (hi, lo): hi = x truncated to the tf32 mantissa (so hi + r == x exactly), lo = r rounded to tf32
@@ -271,7 +271,10 @@ SQ_DEV int head_of(const Layer& L, int vc, int& j) {
 }
 
 #ifndef SQAIR_HOST_EMU
-constexpr int MMA_U = 8;        // k-steps (LDG.128 per lane) in flight per warp
+#ifndef SQAIR_MMA_U
+#define SQAIR_MMA_U 4        // measured on c2: 4 -> 7.9 ms, 6 -> 8.0 ms, 8 -> 8.6 ms (register pressure), 2 -> 8.2 ms
+#endif
+constexpr int MMA_U = SQAIR_MMA_U;   // k-steps (LDG.128 per lane) in flight per warp
 
 // One k-step: acc += A * B in (almost) fp32: both operands are split into tf32 (hi, lo) and all four partial
 // products of the 8 k values are summed on the tensor core, smallest first, starting from zero; the k-step's sum
@@ -289,6 +292,26 @@ SQ_DEV void mma_kstep(float (&acc)[4], const float4& a, float b0f, float b1f) {
     mma_tf32(d, al, b0h, b1h);
     mma_tf32(e, ah, b0h, b1h);
     acc[0] += d[0] + e[0]; acc[1] += d[1] + e[1]; acc[2] += d[2] + e[2]; acc[3] += d[3] + e[3];
+}
+
+// Two k-steps at once: the splits and MMA chains of the pair are independent (more work per dependent-issue slot;
+// the loop is bound by in-order issue latency with 3 warps per scheduler).
+SQ_DEV void mma_kstep2(float (&acc)[4], const float4& a0, float p0, float p1, const float4& a1, float q0, float q1) {
+    uint32_t ah[4], al[4], ch[4], cl[4], p0h, p0l, p1h, p1l, q0h, q0l, q1h, q1l;
+    split_tf32(a0.x, ah[0], al[0]); split_tf32(a0.y, ah[1], al[1]); split_tf32(a0.z, ah[2], al[2]); split_tf32(a0.w, ah[3], al[3]);
+    split_tf32(a1.x, ch[0], cl[0]); split_tf32(a1.y, ch[1], cl[1]); split_tf32(a1.z, ch[2], cl[2]); split_tf32(a1.w, ch[3], cl[3]);
+    split_tf32(p0, p0h, p0l); split_tf32(p1, p1h, p1l); split_tf32(q0, q0h, q0l); split_tf32(q1, q1h, q1l);
+    float d[4], e[4];
+    mma_tf32_zero(d, al, p0l, p1l);
+    mma_tf32_zero(e, cl, q0l, q1l);
+    mma_tf32(d, al, p0h, p1h);
+    mma_tf32(e, cl, q0h, q1h);
+    mma_tf32(d, ah, p0l, p1l);
+    mma_tf32(e, ch, q0l, q1l);
+    mma_tf32(d, ah, p0h, p1h);
+    mma_tf32(e, ch, q0h, q1h);
+    acc[0] += d[0]; acc[1] += d[1]; acc[2] += d[2]; acc[3] += d[3];
+    acc[0] += e[0]; acc[1] += e[1]; acc[2] += e[2]; acc[3] += e[3];
 }
 
 // One work unit: m-tile `mt` (16 output columns) x k-steps [k0, k1) of this block's panel.  The A fragments stream
@@ -320,10 +343,9 @@ SQ_DEV void mma_unit(const Layer& L, const float4* SQ_RESTRICT wp, int k0, int k
         xp = SQ_SM + S.x_off + slot * S.x_sstride + gr + kloc * S.ld;
     };
     enter_segment(k0);
-    auto kstep = [&](int ks, float4& slot_buf, bool refill) {
-        const float4 a = slot_buf;
+    // B fragment of k-step ks (advances the segment cursor)
+    auto fetch_b = [&](int ks, float& b0f, float& b1f) {
         if (ks == seg_end) { ++si; enter_segment(ks); }
-        float b0f, b1f;
         if (!IMAGE || !image) {
             b0f = xp[0]; b1f = xp[ld4];
             xp += step;
@@ -333,14 +355,28 @@ SQ_DEV void mma_unit(const Layer& L, const float4* SQ_RESTRICT wp, int k0, int k
             b0f = SQ_LDG(img_g + ka); b1f = SQ_LDG(img_g + kb);
             kloc += 8;
         }
+    };
+    auto kstep = [&](int ks, float4& slot_buf, bool refill) {
+        const float4 a = slot_buf;
+        float b0f, b1f;
+        fetch_b(ks, b0f, b1f);
         mma_kstep(acc, a, b0f, b1f);
         if (refill) slot_buf = ldg_stream(wp);         // issued after the MMAs that consumed this slot (both are volatile)
         wp += 32;
     };
+    static_assert(MMA_U % 2 == 0, "k-steps are processed in pairs");
     int kk = k0;
-    for (; kk + 2 * MMA_U <= k1; kk += MMA_U) {        // steady state: every slot is refilled
+    for (; kk + 2 * MMA_U <= k1; kk += MMA_U) {        // steady state: pairs of k-steps, every slot is refilled
 #pragma unroll
-        for (int j = 0; j < MMA_U; ++j) kstep(kk + j, buf[j], true);
+        for (int j = 0; j < MMA_U; j += 2) {
+            float p0, p1, q0, q1;
+            fetch_b(kk + j, p0, p1);
+            fetch_b(kk + j + 1, q0, q1);
+            mma_kstep2(acc, buf[j], p0, p1, buf[j + 1], q0, q1);
+            buf[j] = ldg_stream(wp);
+            buf[j + 1] = ldg_stream(wp + 32);
+            wp += 64;
+        }
     }
     for (; kk < k1; kk += MMA_U) {                     // last one or two groups
 #pragma unroll
@@ -431,9 +467,13 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
         ks = L.ksplit;
         const int nmt = L.nmt, kper = L.kper, ksteps = L.ksteps, nunits = nmt * ks;
         const int lane = c.lane(), g = lane >> 2, t = lane & 3;
+        SQ_TICK(c, 0);                           // call prologue: counters, descriptor
         for (int u = c.warp(); u < ((dbg & 1) ? 0 : nunits); u += NWARP) {
             const int sl = u / nmt, mt = u - sl * nmt;
             const int k0 = sl * kper, k1 = (k0 + kper < ksteps) ? (k0 + kper) : ksteps;
+#if defined(SQAIR_PROFILE)
+            c.prof[6] += k1 - k0; c.prof[7] += 1;
+#endif
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             const float4* wp = reinterpret_cast<const float4*>(panel) + ((size_t)mt * ksteps + k0) * 32 + lane;
             if (L.seg[0].kind == SEG_IMAGE) mma_unit<R, true>(L, wp, k0, k1, slot, img_g, lane, acc);

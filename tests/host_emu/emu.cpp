@@ -94,3 +94,18 @@ extern "C" int emu_forward(const sqair_cfg* cfg, const float* params, const floa
     }
     return 0;
 }
+
+// plan dump for tuning scripts: per layer id {ksteps, Nc, nmt, ksplit, kper, npanel, split}
+extern "C" int emu_dump_plan(const sqair_cfg* cfg, int R, int C, int* out /* L_COUNT x 8 */) {
+    auto tab = param_table(*cfg);
+    static Plan plan;
+    std::vector<Piece> pieces;
+    int64_t total;
+    if (!build_plan(*cfg, R, C, plan, tab, pieces, &total).empty()) return -1;
+    for (int i = 0; i < L_COUNT; ++i) {
+        const Layer& L = plan.L[i];
+        int* o = out + 8 * i;
+        o[0] = L.ksteps; o[1] = L.Nc; o[2] = L.nmt; o[3] = L.ksplit; o[4] = L.kper; o[5] = L.npanel; o[6] = L.split; o[7] = L.Ntot;
+    }
+    return L_COUNT;
+}
