@@ -69,7 +69,7 @@ def test_forward_parity(name):
     assert not bad, '\n'.join(bad)
 
 
-@pytest.mark.parametrize('R,C', [(1, 1), (2, 1), (3, 2), (4, 2), (5, 4), (2, 4), (1, 8), (3, 8)])
+@pytest.mark.parametrize('R,C', [(1, 1), (2, 1), (3, 2), (4, 2), (5, 4), (2, 4), (1, 8), (3, 8), (6, 4), (6, 1), (4, 5), (2, 6), (3, 7)])
 def test_launch_shape_variants(R, C):
     """Every instantiation of the persistent kernel (rows per cluster R) and every cluster size C,
     including row counts that do not divide."""
@@ -90,6 +90,27 @@ def test_full_size_c2_parity():
     bad = TL.compare_outputs(got, want)
     assert not bad, '\n'.join(bad)
     assert 0.05 < want['presence'].mean() < 0.95     # both branches exercised
+
+
+def test_full_size_c4_parity():
+    """BASELINE configs[3]: 100x100 canvas, n=6 objects, B=16, K=10 (glimpse-bandwidth stress)."""
+    cfg = O.Cfg(T=10, B=16, K=10, n=6, H=100, W=100)
+    imgs, params, noise = TL.make_inputs(cfg)
+    want, obj = TL.run_oracle(cfg, imgs, params, noise)
+    got = run_cuda(cfg, imgs, params, noise)
+    bad = TL.compare_outputs(got, want)
+    assert not bad, '\n'.join(bad)
+
+
+def test_c5_long_rollout_parity():
+    """BASELINE configs[4]: seq_len=100 inference rollout, 2 objects, B=8, K=1.  One hundred frames of recurrence:
+    the integer-valued decisions must still agree exactly and the real outputs within tolerance."""
+    cfg = O.Cfg(T=100, B=8, K=1, n=2)
+    imgs, params, noise = TL.make_inputs(cfg)
+    want, obj = TL.run_oracle(cfg, imgs, params, noise)
+    got = run_cuda(cfg, imgs, params, noise)
+    bad = TL.compare_outputs(got, want)
+    assert not bad, '\n'.join(bad)
 
 
 def test_device_noise_matches_numpy_philox():

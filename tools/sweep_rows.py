@@ -16,10 +16,12 @@ def main():
     noise = ops.fill_noise(cfg, 7, 0, device=dev)
     outs = ops.alloc_outputs(cfg, dev)
     res = {}
-    shapes = [tuple(int(v) for v in x.split(':')) for x in os.environ.get('SWEEP', '4:3,5:4,6:5,6:4,4:2,3:2,2:1,6:2,5:3,4:4').split(',')]
+    shapes = [tuple(int(v) for v in x.split(':')) for x in os.environ.get('SWEEP', '4:3,5:4,6:5,6:4,4:2,3:2,2:1,6:2,5:3,4:4' if len(sys.argv) <= 5 else '0:0').split(',')]
     for R, C in shapes:
-        os.environ['SQAIR_ROWS_PER_CTA'] = str(R)
-        os.environ['SQAIR_CLUSTER'] = str(C)
+        os.environ.pop('SQAIR_ROWS_PER_CTA', None); os.environ.pop('SQAIR_CLUSTER', None)
+        if R:
+            os.environ['SQAIR_ROWS_PER_CTA'] = str(R)
+            os.environ['SQAIR_CLUSTER'] = str(C)
         try:
             s = _capi.query_sizes(cfg)
             packed = ops.pack_params(cfg, flat)
@@ -35,7 +37,7 @@ def main():
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         res['%d:%d' % (R, C)] = ms
-        print('R=%d C=%d ctas=%d smem=%d B: %.3f ms/step  %.0f frames/s' % (R, C, s.n_ctas, s.smem_bytes, ms, B * T / ms * 1e3), flush=True)
+        print('R=%d C=%d ctas=%d smem=%d B: %.3f ms/step  %.0f frames/s' % (s.rows_per_cta, s.cluster_size, s.n_ctas, s.smem_bytes, ms, B * T / ms * 1e3), flush=True)
     os.environ.pop('SQAIR_ROWS_PER_CTA', None); os.environ.pop('SQAIR_CLUSTER', None)
     print(json.dumps(res))
 
