@@ -140,7 +140,7 @@ static std::string choose_shape_uncached(const sqair_cfg& c, const std::vector<P
 // environment variables, so the last few results are cached (building ~25 candidate plans costs ~1 ms of host time).
 struct ShapeKey {
     sqair_cfg cfg;
-    int env[2];
+    int env[3];
     bool operator==(const ShapeKey& o) const { return memcmp(this, &o, sizeof(ShapeKey)) == 0; }
 };
 static std::mutex g_shape_mutex;
@@ -150,7 +150,7 @@ static std::string choose_shape(const sqair_cfg& c, const std::vector<ParamEntry
     ShapeKey key;
     memset(&key, 0, sizeof(key));
     key.cfg = c;
-    key.env[0] = env_int("SQAIR_ROWS_PER_CTA"); key.env[1] = env_int("SQAIR_CLUSTER");
+    key.env[0] = env_int("SQAIR_ROWS_PER_CTA"); key.env[1] = env_int("SQAIR_CLUSTER"); key.env[2] = env_int("SQAIR_NO_FRAME_STAGING");
     std::lock_guard<std::mutex> lock(g_shape_mutex);
     for (auto& kv : g_shape_cache)
         if (kv.first == key) { out = *kv.second; return ""; }
@@ -185,9 +185,13 @@ static std::string choose_shape_uncached(const sqair_cfg& c, const std::vector<P
             if (fR && R != fR) continue;
             if (R > rows && R != 1) continue;
             Shape s;
-            std::string e = build_plan(c, R, C, s.plan, tab, s.pieces, &s.packed_total);
-            if (!e.empty()) { err = e; continue; }
-            if (s.plan.sm.total * (int)sizeof(float) > kSmemLimit) continue;
+            bool ok = false;
+            for (int stage = env_int("SQAIR_NO_FRAME_STAGING") ? 0 : 1; stage >= 0 && !ok; --stage) {   // frames in shared memory if they fit
+                std::string e = build_plan(c, R, C, s.plan, tab, s.pieces, &s.packed_total, stage != 0);
+                if (!e.empty()) { err = e; break; }
+                ok = s.plan.sm.total * (int)sizeof(float) <= kSmemLimit;
+            }
+            if (!ok) continue;
             const int ncl = (rows + R - 1) / R;
             const int max_blocks = max_resident_blocks(C);
             const double waves = (double)((ncl * C + max_blocks - 1) / max_blocks);

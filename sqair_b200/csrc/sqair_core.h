@@ -145,6 +145,9 @@ struct Smem {
     int Red;      // k-slice partial sums
     int RowAcc;   // [16][R] per-row scalars
     int Perm;     // [2NS][R] compaction order (as floats)
+    int Img;      // [img_n][H*W] frames of this block's sequences, staged by TMA at frame start (img_n = 0: read from global)
+    int ImgBar;   // mbarrier (8 bytes) of the frame copy
+    int img_n;
     int total;    // floats
     int red_floats;
 };
@@ -457,7 +460,7 @@ inline std::vector<int> frame_sequence(const sqair_cfg& c) {
 // Builds the plan for R rows per cluster of C blocks.  Returns "" on success, else an error message.
 // `pieces` receives the packing table; *packed_total the floats of the packed parameter buffer.
 inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const std::vector<ParamEntry>& tab,
-                              std::vector<Piece>& pieces, int64_t* packed_total) {
+                              std::vector<Piece>& pieces, int64_t* packed_total, bool stage_frame = true) {
     memset((void*)&p, 0, sizeof(p));
     pieces.clear();
     p.cfg = c;
@@ -506,6 +509,19 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
     m.Coords = B.alloc(4 * R);
     m.RowAcc = B.alloc(16 * R);
     m.Perm = B.alloc(2 * NS * R);
+    // Frames in shared memory: the rows of a cluster belong to at most img_n consecutive sequences (row = b*K + k).
+    // A bulk copy needs 16-byte sizes and addresses, i.e. H*W a multiple of 4.
+    m.img_n = 0;
+    m.ImgBar = B.alloc(4, 4);
+    if (stage_frame && P % 4 == 0) {
+        const int rows = c.B * c.K;
+        for (int r0 = 0; r0 < rows; r0 += R) {
+            const int r1 = (r0 + R - 1 < rows - 1) ? (r0 + R - 1) : (rows - 1);
+            const int cnt = r1 / c.K - r0 / c.K + 1;
+            if (cnt > m.img_n) m.img_n = cnt;
+        }
+        m.Img = B.alloc(m.img_n * P, 4);
+    }
     m.Wb = B.alloc(4 * R);
     // per-slot scratch; the decoded glimpses alias it (it is dead once the slots are compacted)
     int scratch0 = B.cursor;

@@ -110,6 +110,27 @@ SQ_DEV void st_cluster_f32(uint32_t local_addr, int rank, float v) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
+// mbarrier + bulk asynchronous copy (TMA, cp.async.bulk): the frame copy at the start of every frame
+SQ_DEV void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+SQ_DEV void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+SQ_DEV bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+SQ_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+SQ_DEV void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // D = A(16x8, tf32) * B(8x8, tf32)
 SQ_DEV void mma_tf32_zero(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
@@ -352,7 +373,7 @@ SQ_DEV void mma_unit(const Layer& L, const float4* SQ_RESTRICT wp, int k0, int k
         } else {
             int ka = kloc, kb = kloc + 4;
             if (kb >= K) { ka = ka < K ? ka : K - 1; kb = K - 1; }
-            b0f = SQ_LDG(img_g + ka); b1f = SQ_LDG(img_g + kb);
+            b0f = img_g[ka]; b1f = img_g[kb];            // generic loads: the frame is in shared memory when staged
             kloc += 8;
         }
     };
@@ -545,6 +566,7 @@ struct Block {
     int row0;                       // first global row of this block
     const float* imgrow[R];         // frame of each row for the current t
     const float* img_g;             // frame of the row this lane feeds to the MMA B fragment (row min(lane / 4, R - 1))
+    uint32_t frame_parity;          // mbarrier phase of the current frame's TMA copy
     int grow[R];                    // global row (clamped) of each local row
     bool valid[R];
 
@@ -557,6 +579,7 @@ struct Block {
             imgrow[r] = nullptr;
         }
         img_g = nullptr;
+        frame_parity = 0;
     }
     // accessors ------------------------------------------------------------------------------
     SQ_DEV float* sm() const { return SQ_SM; }
@@ -590,6 +613,8 @@ struct Block {
         // (against zero weights).  The staged descriptor and the counters written by calls_init() stay.
         for (int i = m.Desc + 2 * DESC_WORDS + c.tid(); i < m.total; i += c.nthreads()) SQ_SM[i] = 0.f;
         c.sync();
+        if (c.tid() == 0) { mbar_init(smem_u32(SQ_SM + m.ImgBar), 1); fence_barrier_init(); }
+        c.sync();
 #endif
         for (int i = c.tid(); i < (nw + 6) * LDS(); i += c.nthreads()) SQ_SM[m.Z + i] = 0.f;
         for (int i = c.tid(); i < LDS(); i += c.nthreads()) SQ_SM[m.Ids + i] = -1.f;
@@ -611,11 +636,21 @@ struct Block {
         c.sync();
     }
 
+    // the frame's bulk copy has landed (returns at once when it already has; no-op when frames are read from global)
+    SQ_DEV void wait_frame() const {
+#ifndef SQAIR_HOST_EMU
+        if (P.sm.img_n > 0) {
+            const uint32_t bar = smem_u32(SQ_SM + P.sm.ImgBar);
+            while (!mbar_try_wait(bar, frame_parity)) {}
+        }
+#endif
+    }
     // forward spatial transformer (modules.py:165-172,204-218) at Coords -> Glm (* Mask)
     SQ_DEV void extract_glimpse(bool use_mask) const {
         const Smem& m = P.sm;
         const int G = P.cfg.G, W = P.cfg.W, H = P.cfg.H;
         const float hw = 0.5f * (float)(W - 1), hh = 0.5f * (float)(H - 1);
+        wait_frame();
         for (int i = c.tid(); i < ((J.debug_flags & 8) ? 0 : P.g * R); i += c.nthreads()) {
             const int r = i % R, j = i / R;
             const int gy = j / G, gx = j % G;
@@ -626,7 +661,7 @@ struct Block {
             const float* img = imgrow[0];
 #pragma unroll
             for (int q = 1; q < R; ++q) if (r == q) img = imgrow[q];
-            float v = bilinear_zero_pad(x, y, W, H, [&](int ix, int iy) { return SQ_LDG(img + iy * W + ix); });
+            float v = bilinear_zero_pad(x, y, W, H, [&](int ix, int iy) { return img[iy * W + ix]; });
             if (use_mask) v *= SQ_SM[m.Mask + i];
             SQ_SM[m.Glm + i] = v;
         }
@@ -1144,7 +1179,7 @@ struct Block {
                 const float mask = sigmoidf_(-10.f + nz * 20.f);                    // modules.py:462
                 canvas += prm(P.po.mean_img + px) * mask;                           // modules.py:465
                 const float std = mask * sf + (1.f - mask) * sb;                    // modules.py:453
-                ll[r] += normal_lp(SQ_LDG(imgrow[r] + px), canvas, std);
+                ll[r] += normal_lp(imgrow[r][px], canvas, std);
                 if (o.canvas && valid[r]) o.canvas[(trow + grow[r]) * PX + px] = canvas;
             }
         }
@@ -1249,6 +1284,23 @@ struct Block {
         const int NS = P.NS, nh = P.nh;
 #pragma unroll
         for (int r = 0; r < R; ++r) imgrow[r] = J.obs + ((size_t)t * P.cfg.B + grow[r] / P.cfg.K) * P.PX;
+#ifndef SQAIR_HOST_EMU
+        if (m.img_n > 0) {
+            // TMA: one bulk copy per sequence of this block's rows, completion on an mbarrier whose phase is the frame
+            // index; the first glimpse extraction of the frame waits for it (a few dense layers later).  Every thread is
+            // past the barrier that ended the previous frame, so nobody still reads the old frame.
+            const int b0 = grow[0] / P.cfg.K, nimg = grow[R - 1] / P.cfg.K - b0 + 1;
+            if (c.tid() == 0) {
+                const uint32_t bar = smem_u32(SQ_SM + m.ImgBar);
+                mbar_expect_tx(bar, (uint32_t)(nimg * P.PX) * 4u);
+                for (int i = 0; i < nimg; ++i)
+                    bulk_g2s(smem_u32(SQ_SM + m.Img + i * P.PX), J.obs + ((size_t)t * P.cfg.B + b0 + i) * P.PX, (uint32_t)P.PX * 4u, bar);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) imgrow[r] = SQ_SM + m.Img + (grow[r] / P.cfg.K - b0) * P.PX;
+            frame_parity = (uint32_t)(t & 1);
+        }
+#endif
         {
             const int g = c.lane() >> 2;
             img_g = imgrow[R - 1];
