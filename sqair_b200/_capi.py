@@ -74,20 +74,28 @@ def make_cfg(T, B, K, n, H, W, G=20, n_what=50, n_hidden=256, prior_type='rnn', 
 
 
 def output_shapes(cfg: SqairCfg):
-    """Shapes of the 38 outputs for a call with `cfg` (seq.py:121-177), leading [T, rows]."""
+    """Shapes of the 38 outputs for a call with `cfg` (seq.py:121-177), leading [T, rows].
+
+    The reference squeezes every per-frame output whose last axis has length 1 before writing it to its
+    TensorArray (seq.py:253-255).  presence / ids etc. are [rows, n, 1] there and come out as [rows, n]; the
+    per-slot log-probabilities are [rows, n] and therefore lose their slot axis when n_steps_per_image == 1.
+    The memory layout is unchanged, only the reported shape follows the quirk."""
     T, rows, n = cfg.T, cfg.B * cfg.K, cfg.n
     per_slot = {'what': (n, cfg.n_what), 'what_loc': (n, cfg.n_what), 'what_scale': (n, cfg.n_what),
                 'where': (n, 4), 'where_loc': (n, 4), 'where_scale': (n, 4),
                 'canvas': (cfg.H, cfg.W), 'glimpse': (n, cfg.G, cfg.G), 'disc_prob': (n + 1,)}
-    slot_vecs = ('presence_prob presence presence_logit obj_id disc_what_log_prob disc_where_log_prob '
-                 'disc_what_prior_log_prob disc_where_prior_log_prob prop_what_log_prob prop_where_log_prob '
-                 'prop_what_prior_log_prob prop_where_prior_log_prob prop_prob prop_pres disc_pres').split()
+    slot_vecs = 'presence_prob presence presence_logit obj_id prop_pres disc_pres'.split()
+    slot_scalars = ('disc_what_log_prob disc_where_log_prob disc_what_prior_log_prob disc_where_prior_log_prob '
+                    'prop_what_log_prob prop_where_log_prob prop_what_prior_log_prob prop_where_prior_log_prob '
+                    'prop_prob').split()
     shapes = {}
     for k in OUTPUT_NAMES:
         if k in per_slot:
             shapes[k] = (T, rows) + per_slot[k]
         elif k in slot_vecs:
             shapes[k] = (T, rows, n)
+        elif k in slot_scalars:
+            shapes[k] = (T, rows, n) if n > 1 else (T, rows)
         else:
             shapes[k] = (T, rows)
     return shapes

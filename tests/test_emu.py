@@ -15,6 +15,9 @@ CASES = [      # (config, rows per cluster, blocks per cluster)
     (dict(T=3, B=2, K=2, n=2, prior_type='guided', disc_prior_type='geom'), 3, 4),
     (dict(T=2, B=2, K=1, n=2, rec_where_prior=False, masked_glimpse=False), 2, 2),
     (dict(T=2, B=2, K=2, n=6, H=64, W=64), 4, 4),
+    (dict(T=3, B=3, K=2, n=1), 2, 2),          # one slot: the reference squeezes the slot axis of the per-slot log-probs
+    (dict(T=2, B=2, K=1, n=8), 6, 3),          # maximum slot count, largest rows-per-cluster instantiation
+    (dict(T=2, B=3, K=1, n=2, H=45, W=35), 1, 5),
 ]
 
 

@@ -56,6 +56,14 @@ CASES = {
     'guided_geom': dict(T=3, B=2, K=2, n=2, prior_type='guided', disc_prior_type='geom'),
     'no_rec_no_mask': dict(T=3, B=2, K=1, n=2, rec_where_prior=False, masked_glimpse=False),
     'c4_like_64px_n6': dict(T=2, B=2, K=2, n=6, H=64, W=64),
+    # edges: a single slot, the maximum slot count, one frame, one row, non-square canvases (one of them with
+    # H*W not a multiple of 4: frames are then read from global memory instead of the TMA-staged copy)
+    'one_slot': dict(T=3, B=3, K=2, n=1),
+    'max_slots_n8': dict(T=2, B=2, K=1, n=8),
+    'single_frame_single_row': dict(T=1, B=1, K=1, n=2),
+    'non_square_40x60': dict(T=2, B=2, K=2, n=2, H=40, W=60),
+    'odd_pixels_45x35': dict(T=2, B=3, K=1, n=2, H=45, W=35),
+    'seven_particles': dict(T=2, B=2, K=7, n=3),
 }
 
 
