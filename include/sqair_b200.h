@@ -131,6 +131,16 @@ int sqair_objective(const float* log_w_t, const float* disc_lp_t, int32_t T, int
                     float* log_weights, float* elbo_iwae_per_example, float* importance_weights,
                     float* scalars, void* stream);
 
+/* First stage of the backward pass of Model.make_target (model.py:150-158; targets.py:46-75): gradients of the
+ * VIMCO target `mean_{b,k}(-elbo_iwae_b - stop_gradient(log_w_bk - control_variate_bk) * log_prob_bk) / T` with
+ * respect to the summed log weight and the summed discrete log-probability of every row (the same value flows to
+ * each of the row's T per-frame terms):
+ *   d_log_weights [B,K]        = -softmax_k(log_w_b)_k / (B * T)
+ *   d_discrete_log_prob [B,K]  = -(log_w_bk - control_variate_bk) / (B * K * T)
+ * Either output may be NULL. */
+int sqair_objective_grad(const float* log_w_t, const float* disc_lp_t, int32_t T, int32_t B, int32_t K,
+                         float* d_log_weights, float* d_discrete_log_prob, void* stream);
+
 /* Per-op entry points (unit parity / roofline of the bandwidth-shaped pieces).
  * sqair_stn_glimpse: SpatialTransformer forward (modules.py:165-172,204-218): img [N,H,W],
  *   where-logits [N,4] -> glimpse [N,G,G].
@@ -139,10 +149,26 @@ int sqair_objective(const float* log_w_t, const float* disc_lp_t, int32_t T, int
  *   -> canvas [N,H,W], data_ll [N]. */
 int sqair_stn_glimpse(const float* img, const float* where, float* glimpse,
                       int32_t N, int32_t H, int32_t W, int32_t G, void* stream);
+/* Backward of sqair_stn_glimpse with respect to the where-logits (the frame is an input and gets no gradient,
+ * SURVEY Appendix F): d_glimpse [N,G,G] -> d_where [N,4].  Matches tf.contrib.resampler's warp gradient (bilinear
+ * weights differentiated, zero outside the frame) chained through AffineGridWarper, to_coords (sigmoid / tanh,
+ * modules.py:220-227) and the straight-through clip of the scale (ops.py:33-42, modules.py:206). */
+int sqair_stn_glimpse_grad(const float* img, const float* where, const float* d_glimpse, float* d_where,
+                           int32_t N, int32_t H, int32_t W, int32_t G, void* stream);
 int sqair_canvas_ll(const float* glimpse, const float* where, const float* presence, const float* mean_img,
                     const float* img, float* canvas, float* data_ll,
                     int32_t N, int32_t n, int32_t H, int32_t W, int32_t G, float output_std, float bg_std,
                     void* stream);
+
+/* Backward of sqair_canvas_ll (AIRDecoder._decode/_add_mean_image + the pixel likelihood, modules.py:435-467,
+ * seq.py:272-273) for an upstream gradient d_ll [N] on data_ll: gradients w.r.t. the decoded glimpses
+ * d_glimpse [N,n,G,G], the where-logits d_where [N,n,4] (inverse-warp gradient for both the glimpse and the
+ * all-ones occupancy map that feeds the mean-image mask) and the trainable mean image d_mean_img [H,W]
+ * (ACCUMULATED into the buffer: zero it first).  presence and the frame get no gradient. */
+int sqair_canvas_ll_grad(const float* glimpse, const float* where, const float* presence, const float* mean_img,
+                         const float* img, const float* d_ll, float* d_glimpse, float* d_where, float* d_mean_img,
+                         int32_t N, int32_t n, int32_t H, int32_t W, int32_t G, float output_std, float bg_std,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -394,6 +394,40 @@ __global__ void objective_kernel(const float* __restrict__ lw_t, const float* __
     }
 }
 
+// Gradient of the VIMCO target w.r.t. the rows' summed log weights and discrete log-probs (targets.py:46-75;
+// model.py:150-158): one thread per sample, K is small.
+__global__ void objective_grad_kernel(const float* __restrict__ lw_t, const float* __restrict__ lp_t, int T, int B, int K,
+                                      float* __restrict__ d_lw, float* __restrict__ d_lp) {
+    const float logK = logf((float)K);
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        auto lw = [&](int k) {
+            float a = 0.f;
+            for (int t = 0; t < T; ++t) a += lw_t[(size_t)t * B * K + b * K + k];
+            return a;
+        };
+        float S = 0.f, mx = -INFINITY;
+        for (int k = 0; k < K; ++k) { const float a = lw(k); S += a; mx = fmaxf(mx, a); }
+        float se = 0.f;
+        for (int k = 0; k < K; ++k) se += expf(lw(k) - mx);
+        const float lse = mx + logf(se);
+        for (int j = 0; j < K; ++j) {
+            const float lwj = lw(j);
+            if (d_lw) d_lw[b * K + j] = -expf(lwj - lse) / ((float)B * (float)T);
+            if (d_lp) {
+                // control variate: logsumexp_i(i == j ? mean_{i != j} lw_i : lw_i) - log K
+                const float abo = (S - lwj) / ((float)K - 1.f);
+                float m2 = abo;
+                for (int i = 0; i < K; ++i) if (i != j) m2 = fmaxf(m2, lw(i));
+                float s2 = expf(abo - m2);
+                for (int i = 0; i < K; ++i) if (i != j) s2 += expf(lw(i) - m2);
+                const float cv = m2 + logf(s2) - logK;
+                d_lp[b * K + j] = -(lwj - cv) / ((float)B * (float)K * (float)T);
+            }
+        }
+    }
+    (void)lp_t;
+}
+
 // SpatialTransformer forward (modules.py:165-172,204-218): one thread per glimpse texel.
 __global__ void stn_glimpse_kernel(const float* __restrict__ img, const float* __restrict__ where,
                                    float* __restrict__ glimpse, int N, int H, int W, int G) {
@@ -409,6 +443,59 @@ __global__ void stn_glimpse_kernel(const float* __restrict__ img, const float* _
         const float y = hh * (sy * lin11(gy, G) + ty) + hh;
         const float* im = img + (size_t)nidx * H * W;
         glimpse[i] = bilinear_zero_pad(x, y, W, H, [&](int ix, int iy) { return __ldg(im + iy * W + ix); });
+    }
+}
+
+// Backward of the glimpse sampler w.r.t. the where-logits: one block per glimpse, threads over texels, block reduction
+// of the four coordinate-space sums, chain rule through to_coords in thread 0.
+__global__ void stn_glimpse_grad_kernel(const float* __restrict__ img, const float* __restrict__ where,
+                                        const float* __restrict__ d_glimpse, float* __restrict__ d_where, int H, int W, int G) {
+    const int nidx = blockIdx.x;
+    const float* wl = where + (size_t)nidx * 4;
+    const float s0 = sigmoidf_(__ldg(wl)), s1 = sigmoidf_(__ldg(wl + 1));
+    const float sx = fmaxf(s0, 1e-4f), sy = fmaxf(s1, 1e-4f);
+    const float tx = tanhf(__ldg(wl + 2)), ty = tanhf(__ldg(wl + 3));
+    const float hw = 0.5f * (float)(W - 1), hh = 0.5f * (float)(H - 1);
+    const float* im = img + (size_t)nidx * H * W;
+    float a_sx = 0.f, a_sy = 0.f, a_tx = 0.f, a_ty = 0.f;
+    for (int i = threadIdx.x; i < G * G; i += blockDim.x) {
+        const int gx = i % G, gy = i / G;
+        const float u = lin11(gx, G), v = lin11(gy, G);
+        const float x = hw * (sx * u + tx) + hw, y = hh * (sy * v + ty) + hh;
+        if (!(x > -1.f && y > -1.f && x < (float)W && y < (float)H)) continue;      // sample is 0 there, so is its gradient
+        const float fx = floorf(x), fy = floorf(y);
+        const float dx = fx + 1.f - x, dy = fy + 1.f - y;
+        const int ifx = (int)fx, ify = (int)fy, icx = ifx + 1, icy = ify + 1;
+        const bool fx_ok = ifx >= 0 && ifx <= W - 1, cx_ok = icx >= 0 && icx <= W - 1;
+        const bool fy_ok = ify >= 0 && ify <= H - 1, cy_ok = icy >= 0 && icy <= H - 1;
+        const float v00 = (fx_ok && fy_ok) ? __ldg(im + ify * W + ifx) : 0.f;
+        const float v11 = (cx_ok && cy_ok) ? __ldg(im + icy * W + icx) : 0.f;
+        const float v01 = (fx_ok && cy_ok) ? __ldg(im + icy * W + ifx) : 0.f;
+        const float v10 = (cx_ok && fy_ok) ? __ldg(im + ify * W + icx) : 0.f;
+        const float gxv = dy * (v10 - v00) + (1.f - dy) * (v11 - v01);             // d sample / d x
+        const float gyv = dx * (v01 - v00) + (1.f - dx) * (v11 - v10);             // d sample / d y
+        const float dg = __ldg(d_glimpse + (size_t)nidx * G * G + i);
+        a_sx += dg * gxv * hw * u; a_tx += dg * gxv * hw;
+        a_sy += dg * gyv * hh * v; a_ty += dg * gyv * hh;
+    }
+    __shared__ float red[4][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc[4] = {a_sx, a_sy, a_tx, a_ty};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float r = warp_sum(acc[q]);
+        if (lane == 0) red[q][warp] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int q = 0; q < 4; ++q)
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t[q] += red[q][w];
+        float* o = d_where + (size_t)nidx * 4;
+        o[0] = t[0] * s0 * (1.f - s0);          // straight-through clip: the gradient ignores the 1e-4 floor
+        o[1] = t[1] * s1 * (1.f - s1);
+        o[2] = t[2] * (1.f - tx * tx);
+        o[3] = t[3] * (1.f - ty * ty);
     }
 }
 
@@ -462,6 +549,123 @@ __global__ void canvas_ll_kernel(const float* __restrict__ glimpse, const float*
         float a = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += red[w];
         data_ll[b] = a;
+    }
+}
+
+// bilinear sample with zero padding plus its derivatives w.r.t. the sample position; `w4`/`idx4` receive the four texel
+// weights / linear indices (-1 = outside) for the scatter of the data gradient.
+struct Bilin {
+    float val, ddx, ddy;
+    float w4[4];
+    int idx4[4];
+};
+template <class Fetch>
+__device__ __forceinline__ Bilin bilinear_zero_pad_grad(float x, float y, int w, int h, Fetch fetch) {
+    Bilin r;
+    r.val = r.ddx = r.ddy = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { r.w4[q] = 0.f; r.idx4[q] = -1; }
+    if (!(x > -1.f && y > -1.f && x < (float)w && y < (float)h)) return r;
+    const float fx = floorf(x), fy = floorf(y);
+    const float dx = fx + 1.f - x, dy = fy + 1.f - y;
+    const int ifx = (int)fx, ify = (int)fy, icx = ifx + 1, icy = ify + 1;
+    const bool fx_ok = ifx >= 0 && ifx <= w - 1, cx_ok = icx >= 0 && icx <= w - 1;
+    const bool fy_ok = ify >= 0 && ify <= h - 1, cy_ok = icy >= 0 && icy <= h - 1;
+    const float v00 = (fx_ok && fy_ok) ? fetch(ifx, ify) : 0.f;
+    const float v11 = (cx_ok && cy_ok) ? fetch(icx, icy) : 0.f;
+    const float v01 = (fx_ok && cy_ok) ? fetch(ifx, icy) : 0.f;
+    const float v10 = (cx_ok && fy_ok) ? fetch(icx, ify) : 0.f;
+    r.val = dx * dy * v00 + (1.f - dx) * (1.f - dy) * v11 + dx * (1.f - dy) * v01 + (1.f - dx) * dy * v10;
+    r.ddx = dy * (v10 - v00) + (1.f - dy) * (v11 - v01);
+    r.ddy = dx * (v01 - v00) + (1.f - dx) * (v11 - v10);
+    if (fx_ok && fy_ok) { r.w4[0] = dx * dy; r.idx4[0] = ify * w + ifx; }
+    if (cx_ok && cy_ok) { r.w4[1] = (1.f - dx) * (1.f - dy); r.idx4[1] = icy * w + icx; }
+    if (fx_ok && cy_ok) { r.w4[2] = dx * (1.f - dy); r.idx4[2] = icy * w + ifx; }
+    if (cx_ok && fy_ok) { r.w4[3] = (1.f - dx) * dy; r.idx4[3] = ify * w + icx; }
+    return r;
+}
+
+// Backward of canvas_ll_kernel.  One block per image; the n glimpses and their gradient accumulators live in shared
+// memory (the data gradient is a scatter-add: shared-memory atomics), the where-gradient sums are block-reduced.
+__global__ void canvas_ll_grad_kernel(const float* __restrict__ glimpse, const float* __restrict__ where,
+                                      const float* __restrict__ presence, const float* __restrict__ mean_img,
+                                      const float* __restrict__ img, const float* __restrict__ d_ll,
+                                      float* __restrict__ d_glimpse, float* __restrict__ d_where, float* __restrict__ d_mean_img,
+                                      int n, int H, int W, int G, float output_std, float bg_std) {
+    extern __shared__ float sg[];              // glimpses [n][g], gradient accumulators [n][g], coords [n][7], where sums [n][4]
+    const int b = blockIdx.x, g = G * G;
+    float* dgl = sg + n * g;
+    float* cc = dgl + n * g;
+    float* wsum = cc + n * 7;
+    for (int i = threadIdx.x; i < n * g; i += blockDim.x) { sg[i] = glimpse[(size_t)b * n * g + i]; dgl[i] = 0.f; }
+    for (int s = threadIdx.x; s < n; s += blockDim.x) {
+        const float* wl = where + ((size_t)b * n + s) * 4;
+        const float s0 = sigmoidf_(wl[0]), s1 = sigmoidf_(wl[1]);
+        cc[s * 7 + 0] = fmaxf(s0, 1e-4f);
+        cc[s * 7 + 1] = fmaxf(s1, 1e-4f);
+        cc[s * 7 + 2] = tanhf(wl[2]);
+        cc[s * 7 + 3] = tanhf(wl[3]);
+        cc[s * 7 + 4] = presence[(size_t)b * n + s];
+        cc[s * 7 + 5] = s0 * (1.f - s0);        // d sigmoid (straight-through clip: the 1e-4 floor is ignored)
+        cc[s * 7 + 6] = s1 * (1.f - s1);
+    }
+    for (int i = threadIdx.x; i < n * 4; i += blockDim.x) wsum[i] = 0.f;
+    __syncthreads();
+    const float hg = 0.5f * (float)(G - 1);
+    const float sf0 = sqrtf(output_std), sb0 = sqrtf(bg_std);
+    const float sf = sf0 * sf0, sb = sb0 * sb0;
+    const float up = d_ll[b];
+    for (int px = threadIdx.x; px < H * W; px += blockDim.x) {
+        const int iy = px / W, ix = px % W;
+        const float u = lin11(ix, W), v = lin11(iy, H);
+        // forward values of this pixel
+        float cv = 0.f, nz = 0.f;
+        for (int s = 0; s < n; ++s) {
+            const float pres = cc[s * 7 + 4];
+            if (pres == 0.f) continue;
+            const float xg = hg * ((u - cc[s * 7 + 2]) / cc[s * 7 + 0]) + hg;
+            const float yg = hg * ((v - cc[s * 7 + 3]) / cc[s * 7 + 1]) + hg;
+            const float* gl = sg + s * g;
+            cv += pres * bilinear_zero_pad(xg, yg, G, G, [&](int gx, int gy) { return gl[gy * G + gx]; });
+            nz += pres * bilinear_zero_pad(xg, yg, G, G, [&](int, int) { return 1.f; });
+        }
+        const float mask = sigmoidf_(-10.f + nz * 20.f);
+        const float mi = __ldg(mean_img + px);
+        cv += mi * mask;
+        const float std = mask * sf + (1.f - mask) * sb;
+        const float z = (__ldg(img + (size_t)b * H * W + px) - cv) / std;
+        // d ll / d canvas, d ll / d std  (tfd.Normal.log_prob)
+        const float d_cv = up * z / std;
+        const float d_std = up * (z * z - 1.f) / std;
+        const float d_mask = d_cv * mi + d_std * (sf - sb);
+        const float d_nz = d_mask * 20.f * mask * (1.f - mask);
+        atomicAdd(d_mean_img + px, d_cv * mask);
+        for (int s = 0; s < n; ++s) {
+            const float pres = cc[s * 7 + 4];
+            if (pres == 0.f) continue;
+            const float sx = cc[s * 7 + 0], sy = cc[s * 7 + 1], tx = cc[s * 7 + 2], ty = cc[s * 7 + 3];
+            const float xg = hg * ((u - tx) / sx) + hg, yg = hg * ((v - ty) / sy) + hg;
+            const float* gl = sg + s * g;
+            const Bilin bg = bilinear_zero_pad_grad(xg, yg, G, G, [&](int gx, int gy) { return gl[gy * G + gx]; });
+            const Bilin bo = bilinear_zero_pad_grad(xg, yg, G, G, [&](int, int) { return 1.f; });
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (bg.idx4[q] >= 0) atomicAdd(dgl + s * g + bg.idx4[q], d_cv * pres * bg.w4[q]);
+            // position gradients of both samplers, then the inverse warp x_g = hg ((u - tx) / sx) + hg
+            const float d_xg = pres * (d_cv * bg.ddx + d_nz * bo.ddx), d_yg = pres * (d_cv * bg.ddy + d_nz * bo.ddy);
+            atomicAdd(wsum + s * 4 + 0, d_xg * (-hg * (u - tx) / (sx * sx)));
+            atomicAdd(wsum + s * 4 + 1, d_yg * (-hg * (v - ty) / (sy * sy)));
+            atomicAdd(wsum + s * 4 + 2, d_xg * (-hg / sx));
+            atomicAdd(wsum + s * 4 + 3, d_yg * (-hg / sy));
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * g; i += blockDim.x) d_glimpse[(size_t)b * n * g + i] = dgl[i];
+    for (int i = threadIdx.x; i < n * 4; i += blockDim.x) {
+        const int s = i / 4, q = i % 4;
+        const float chain = q == 0 ? cc[s * 7 + 5] : q == 1 ? cc[s * 7 + 6] : q == 2 ? (1.f - cc[s * 7 + 2] * cc[s * 7 + 2])
+                                                                                     : (1.f - cc[s * 7 + 3] * cc[s * 7 + 3]);
+        d_where[((size_t)b * n + s) * 4 + q] = wsum[i] * chain;
     }
 }
 
@@ -618,6 +822,15 @@ int sqair_objective(const float* log_w_t, const float* disc_lp_t, int32_t T, int
     return SQAIR_OK;
 }
 
+int sqair_objective_grad(const float* log_w_t, const float* disc_lp_t, int32_t T, int32_t B, int32_t K, float* d_log_weights,
+                         float* d_discrete_log_prob, void* stream) {
+    if (!log_w_t || T < 1 || B < 1 || K < 1) return fail(SQAIR_EINVAL, "bad argument");
+    objective_grad_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(log_w_t, disc_lp_t, T, B, K, d_log_weights,
+                                                                               d_discrete_log_prob);
+    CUDA_TRY(cudaGetLastError());
+    return SQAIR_OK;
+}
+
 int sqair_stn_glimpse(const float* img, const float* where, float* glimpse, int32_t N, int32_t H, int32_t W, int32_t G,
                       void* stream) {
     if (!img || !where || !glimpse || N < 1 || H < 2 || W < 2 || G < 2) return fail(SQAIR_EINVAL, "bad argument");
@@ -625,6 +838,14 @@ int sqair_stn_glimpse(const float* img, const float* where, float* glimpse, int3
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     stn_glimpse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(img, where, glimpse, N, H, W, G);
+    CUDA_TRY(cudaGetLastError());
+    return SQAIR_OK;
+}
+
+int sqair_stn_glimpse_grad(const float* img, const float* where, const float* d_glimpse, float* d_where, int32_t N, int32_t H,
+                           int32_t W, int32_t G, void* stream) {
+    if (!img || !where || !d_glimpse || !d_where || N < 1 || H < 2 || W < 2 || G < 2) return fail(SQAIR_EINVAL, "bad argument");
+    stn_glimpse_grad_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(img, where, d_glimpse, d_where, H, W, G);
     CUDA_TRY(cudaGetLastError());
     return SQAIR_OK;
 }
@@ -639,6 +860,21 @@ int sqair_canvas_ll(const float* glimpse, const float* where, const float* prese
         CUDA_TRY(cudaFuncSetAttribute(canvas_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     canvas_ll_kernel<<<N, 256, smem, (cudaStream_t)stream>>>(glimpse, where, presence, mean_img, img, canvas, data_ll, n, H,
                                                              W, G, output_std, bg_std);
+    CUDA_TRY(cudaGetLastError());
+    return SQAIR_OK;
+}
+
+int sqair_canvas_ll_grad(const float* glimpse, const float* where, const float* presence, const float* mean_img,
+                         const float* img, const float* d_ll, float* d_glimpse, float* d_where, float* d_mean_img, int32_t N,
+                         int32_t n, int32_t H, int32_t W, int32_t G, float output_std, float bg_std, void* stream) {
+    if (!glimpse || !where || !presence || !mean_img || !img || !d_ll || !d_glimpse || !d_where || !d_mean_img || N < 1 || n < 1)
+        return fail(SQAIR_EINVAL, "bad argument");
+    const int smem = (2 * n * G * G + n * 11) * (int)sizeof(float);
+    if (smem > kSmemLimit) return fail(SQAIR_EUNSUPPORTED, "glimpses do not fit shared memory");
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(canvas_ll_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    canvas_ll_grad_kernel<<<N, 256, smem, (cudaStream_t)stream>>>(glimpse, where, presence, mean_img, img, d_ll, d_glimpse,
+                                                                  d_where, d_mean_img, n, H, W, G, output_std, bg_std);
     CUDA_TRY(cudaGetLastError());
     return SQAIR_OK;
 }

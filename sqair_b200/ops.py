@@ -97,12 +97,33 @@ def objective(log_w_t: torch.Tensor, disc_lp_t: torch.Tensor, B: int, K: int):
     return dict(log_weights=lw, elbo_iwae_per_example=pe, importance_weights=iw, scalars=sc)
 
 
+def objective_grad(log_w_t: torch.Tensor, disc_lp_t: torch.Tensor, B: int, K: int):
+    """Gradients of the VIMCO target (model.py:150-158 / targets.py:62-75) w.r.t. the rows' summed log weights and
+    discrete log-probs, both [B,K]; every per-frame term of a row receives the row's value."""
+    _need_cuda(log_w_t, disc_lp_t)
+    T = log_w_t.shape[0]
+    d_lw = torch.empty(B, K, dtype=torch.float32, device=log_w_t.device)
+    d_lp = torch.empty(B, K, dtype=torch.float32, device=log_w_t.device)
+    check(_capi.lib().sqair_objective_grad(_ptr(log_w_t), _ptr(disc_lp_t), T, B, K, _ptr(d_lw), _ptr(d_lp), _stream()))
+    return d_lw, d_lp
+
+
 def stn_glimpse(img: torch.Tensor, where: torch.Tensor, G: int) -> torch.Tensor:
     """SpatialTransformer forward at where-logits (modules.py:165-172,204-227): [N,H,W],[N,4] -> [N,G,G]."""
     _need_cuda(img, where)
     N, H, W = img.shape
     out = torch.empty(N, G, G, dtype=torch.float32, device=img.device)
     check(_capi.lib().sqair_stn_glimpse(_ptr(img), _ptr(where), _ptr(out), N, H, W, G, _stream()))
+    return out
+
+
+def stn_glimpse_grad(img: torch.Tensor, where: torch.Tensor, d_glimpse: torch.Tensor) -> torch.Tensor:
+    """Backward of `stn_glimpse` w.r.t. the where-logits: [N,H,W], [N,4], [N,G,G] -> [N,4]."""
+    _need_cuda(img, where, d_glimpse)
+    N, H, W = img.shape
+    G = d_glimpse.shape[-1]
+    out = torch.empty(N, 4, dtype=torch.float32, device=img.device)
+    check(_capi.lib().sqair_stn_glimpse_grad(_ptr(img), _ptr(where), _ptr(d_glimpse), _ptr(out), N, H, W, G, _stream()))
     return out
 
 
@@ -117,3 +138,18 @@ def canvas_ll(glimpse, where, presence, mean_img, img, output_std=0.3, bg_std=No
                                       _ptr(canvas), _ptr(ll), N, n, H, W, G, float(output_std),
                                       float(output_std if bg_std is None else bg_std), _stream()))
     return canvas, ll
+
+
+def canvas_ll_grad(glimpse, where, presence, mean_img, img, d_ll, output_std=0.3, bg_std=None):
+    """Backward of `canvas_ll` for an upstream gradient `d_ll` [N] on the pixel log-likelihood: returns
+    (d_glimpse [N,n,G,G], d_where [N,n,4], d_mean_img [H,W])."""
+    _need_cuda(glimpse, where, presence, mean_img, img, d_ll)
+    N, n, G, _ = glimpse.shape
+    H, W = img.shape[1:]
+    d_gl = torch.empty_like(glimpse)
+    d_wh = torch.empty(N, n, 4, dtype=torch.float32, device=img.device)
+    d_mi = torch.zeros(H, W, dtype=torch.float32, device=img.device)
+    check(_capi.lib().sqair_canvas_ll_grad(_ptr(glimpse), _ptr(where), _ptr(presence), _ptr(mean_img), _ptr(img), _ptr(d_ll),
+                                           _ptr(d_gl), _ptr(d_wh), _ptr(d_mi), N, n, H, W, G, float(output_std),
+                                           float(output_std if bg_std is None else bg_std), _stream()))
+    return d_gl, d_wh, d_mi

@@ -211,3 +211,65 @@ def test_objective_op():
     np.testing.assert_allclose(sc[_capi.OBJ_ESS], O.ess(torch.softmax(lw, -1)).mean().item(), rtol=1e-4)
     np.testing.assert_allclose(sc[_capi.OBJ_VIMCO_TARGET], (O.vimco(lw, lp, O.iwae(lw)) / T).item(), rtol=1e-4)
     np.testing.assert_allclose(sc[_capi.OBJ_IWAE_TARGET], (-O.iwae(lw).mean() / T).item(), rtol=1e-5)
+
+
+def test_objective_grad_op():
+    """First stage of the backward pass: d(VIMCO target)/d(log weights, discrete log-probs) against torch autograd
+    on the oracle's objective (targets.py:46-75 semantics incl. the stop-gradient on the learning signal)."""
+    ops, dev = _gpu()
+    rng = np.random.default_rng(3)
+    T, B, K = 10, 32, 5
+    lw_t = (rng.standard_normal((T, B * K)) * 3 + 50).astype(np.float32)
+    lp_t = (rng.standard_normal((T, B * K))).astype(np.float32)
+    d_lw, d_lp = ops.objective_grad(torch.from_numpy(lw_t).to(dev), torch.from_numpy(lp_t).to(dev), B, K)
+    a = torch.from_numpy(lw_t).requires_grad_(True)
+    b = torch.from_numpy(lp_t).requires_grad_(True)
+    lw, lp = a.sum(0).reshape(B, K), b.sum(0).reshape(B, K)
+    (O.vimco(lw, lp, O.iwae(lw)) / T).backward()
+    for t in range(T):          # every frame of a row receives the row's gradient
+        np.testing.assert_allclose(d_lw.cpu().numpy().reshape(-1), a.grad[t].numpy(), rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(d_lp.cpu().numpy().reshape(-1), b.grad[t].numpy(), rtol=1e-4, atol=1e-8)
+
+
+def test_stn_glimpse_grad_op():
+    """Glimpse-sampler backward w.r.t. the where-logits against torch autograd through the oracle's transformer
+    (resampler warp gradient, modules.py:165-227).  Scales stay above the 1e-4 floor, where the oracle's clamp and
+    the reference's straight-through clip have the same gradient."""
+    ops, dev = _gpu()
+    rng = np.random.default_rng(4)
+    N, H, W, G = 53, 50, 50, 20
+    img = torch.from_numpy(rng.random((N, H, W), dtype=np.float32))
+    where = torch.from_numpy((rng.standard_normal((N, 4)) * 1.2).astype(np.float32)).requires_grad_(True)
+    dg = torch.from_numpy(rng.standard_normal((N, G, G)).astype(np.float32))
+    O.stn_forward(img, O.to_coords(where), G).backward(dg)
+    got = ops.stn_glimpse_grad(img.to(dev), where.detach().to(dev), dg.to(dev)).cpu().numpy()
+    want = where.grad.numpy()
+    np.testing.assert_allclose(got, want, rtol=2e-3, atol=2e-3 * np.abs(want).max())
+
+
+def test_canvas_ll_grad_op():
+    """Canvas composition + pixel likelihood backward (inverse-warp gradient w.r.t. data and warp, mean-image mask)
+    against torch autograd through the oracle's composition (modules.py:435-467; seq.py:272-273)."""
+    ops, dev = _gpu()
+    rng = np.random.default_rng(5)
+    N, n, H, W, G = 11, 3, 50, 50, 20
+    glimpse = torch.from_numpy((rng.random((N, n, G, G)) * 0.5).astype(np.float32)).requires_grad_(True)
+    where = torch.from_numpy((rng.standard_normal((N, n, 4)) * 0.8).astype(np.float32)).requires_grad_(True)
+    pres = torch.from_numpy((rng.random((N, n)) < 0.7).astype(np.float32))
+    mean_img = torch.from_numpy((rng.random((H, W)) * 0.2).astype(np.float32)).requires_grad_(True)
+    img = torch.from_numpy(rng.random((N, H, W), dtype=np.float32))
+    d_ll = torch.from_numpy(rng.standard_normal(N).astype(np.float32))
+    coords = O.to_coords(where).reshape(N * n, 4)
+    pr = pres.reshape(N, n, 1, 1)
+    canvas = (O.stn_inverse(glimpse.reshape(N * n, G, G), coords, H, W).reshape(N, n, H, W) * pr).sum(1)
+    nz = (O.stn_inverse(torch.ones(N * n, G, G), coords, H, W).reshape(N, n, H, W) * pr).sum(1)
+    mask = torch.sigmoid(-10. + nz * 20.)
+    canvas = canvas + mean_img[None] * mask
+    std = float(np.float32(np.sqrt(np.float32(0.3))) ** 2)
+    ll = O.normal_log_prob(img, canvas, mask * std + (1. - mask) * std).sum((1, 2))
+    ll.backward(d_ll)
+    d_gl, d_wh, d_mi = ops.canvas_ll_grad(glimpse.detach().to(dev), where.detach().to(dev), pres.to(dev),
+                                          mean_img.detach().to(dev), img.to(dev), d_ll.to(dev))
+    for got, want in ((d_gl, glimpse.grad), (d_wh, where.grad), (d_mi, mean_img.grad)):
+        w = want.numpy()
+        np.testing.assert_allclose(got.cpu().numpy(), w, rtol=2e-3, atol=2e-3 * np.abs(w).max())
