@@ -257,6 +257,22 @@ __global__ void pack_panels_kernel(const __grid_constant__ PieceTab tab, const f
     }
 }
 
+// plain fragment order (fp32 sums of the packed pieces) -> (hi, lo) fragment order read by the sequence kernel
+struct SplitTab {
+    int n;
+    int w1_off[L_COUNT], w_off[L_COUNT], floats[L_COUNT];      // floats = npanel * panel_floats / 2
+};
+__global__ void split_panels_kernel(const __grid_constant__ SplitTab tab, float* __restrict__ buf) {
+    const int l = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tab.floats[l]; i += gridDim.x * blockDim.x) {
+        float hi, lo;
+        split_weight(buf[(size_t)tab.w1_off[l] + i], hi, lo);
+        const size_t d = (size_t)tab.w_off[l] + (size_t)(i >> 7) * 256 + (i & 127);
+        buf[d] = hi;
+        buf[d + 128] = lo;
+    }
+}
+
 // Philox4x32-10 (Salmon et al. 2011), counter = (row, frame, slot, block), key = seed.
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t (&out)[4]) {
@@ -741,7 +757,7 @@ int sqair_pack_params(const sqair_cfg* cfg, const float* params, float* packed, 
     for (size_t i = 0; i < sh.pieces.size(); ++i) {
         const Piece& p = sh.pieces[i];
         const Layer& L = sh.plan.L[p.layer];
-        qt.p[i] = PieceDev{p.vrow0, p.vcol0, p.K, p.N, (int)p.src_off, p.src_ld, L.w_off, L.ksteps, L.Nc, L.panel_floats};
+        qt.p[i] = PieceDev{p.vrow0, p.vcol0, p.K, p.N, (int)p.src_off, p.src_ld, L.w1_off, L.ksteps, L.Nc, L.panel_floats / 2};
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int total = (int)(tab.back().offset + tab.back().count);
@@ -749,6 +765,16 @@ int sqair_pack_params(const sqair_cfg* cfg, const float* params, float* packed, 
     pack_kernel<<<592, 256, 0, st>>>(pt, params, packed, total);
     CUDA_TRY(cudaGetLastError());
     pack_panels_kernel<<<dim3(64, qt.n), 256, 0, st>>>(qt, params, packed);
+    CUDA_TRY(cudaGetLastError());
+    SplitTab stab;
+    memset(&stab, 0, sizeof(stab));
+    for (int i = 0; i < L_COUNT; ++i) {
+        const Layer& L = sh.plan.L[i];
+        if (L.nhead == 0) continue;
+        stab.w1_off[stab.n] = L.w1_off; stab.w_off[stab.n] = L.w_off; stab.floats[stab.n] = L.npanel * (L.panel_floats / 2);
+        ++stab.n;
+    }
+    split_panels_kernel<<<dim3(32, stab.n), 256, 0, st>>>(stab, packed);
     CUDA_TRY(cudaGetLastError());
     // layer table (staged into shared memory one call ahead by the kernel)
     std::vector<int32_t> ltab((size_t)L_COUNT * DESC_WORDS, 0);

@@ -38,7 +38,10 @@ namespace sq {
 
 constexpr int MAXSEG = 6;
 constexpr int MAXHEAD = 3;
-constexpr int NT = 384;          // threads per block (12 warps)
+#ifndef SQAIR_NT
+#define SQAIR_NT 384
+#endif
+constexpr int NT = SQAIR_NT;      // threads per block (12 warps)
 constexpr int NT_LAUNCH = NT;
 constexpr int NWARP = NT / 32;
 constexpr int MAX_KS = NWARP;    // max k-slices of a dense layer
@@ -81,15 +84,20 @@ struct Layer {
     int Nc;        // columns per panel (multiple of 16)
     int nmt;       // Nc / 16: m-tiles per panel
     int npanel;    // panels with real columns (blocks with rank >= npanel idle in this layer); 1 if !split
-    int w_off;     // packed-parameter offset of panel 0; panel p at w_off + p * panel_floats
-    int panel_floats;   // nmt * ksteps * 128
+    int w_off;     // packed-parameter offset of panel 0 in (hi, lo) fragment order; panel p at w_off + p * panel_floats
+    int panel_floats;   // nmt * ksteps * 256
+    int w1_off;    // staging copy of the panels in plain fragment order (fp32 sums, written by the pack kernels): panel p at
+                   // w1_off + p * panel_floats / 2; split_panels then derives the (hi, lo) copy the kernel reads
     int ksplit;    // k-slices: work units = nmt * ksplit, dealt round-robin to the warps
     int kper;      // k-steps per slice
 };
 
 // Fragment order of a panel: [m-tile][k-step][lane][4] floats = the A operand of mma.m16n8k8 (row-major 16x8 tile
 // A[m][k] = W[k-step*8 + k][m-tile*16 + m]): lane = (m%8)*4 + k%4 holds a0 = (m, k), a1 = (m+8, k), a2 = (m, k+4),
-// a3 = (m+8, k+4).  One LDG.128 per lane and k-step, 512 contiguous bytes per warp.
+// a3 = (m+8, k+4).  The copy the kernel reads stores every fragment twice, [m-tile][k-step][hi | lo][lane][4]: the tf32
+// split of the weights (split_weight below) is done once at pack time instead of in every block and k-step -- twice
+// the L2 traffic for 11 fewer issued instructions per k-step in a loop that is instruction-bound.  Two LDG.128 per
+// lane and k-step, 1 KB contiguous per warp.
 SQ_HD int frag_off(int ksteps, int mt, int kstep, int m, int k) {
     const int lane = (m & 7) * 4 + (k & 3), q = (m >> 3) + 2 * (k >> 2);
     return ((mt * ksteps + kstep) * 32 + lane) * 4 + q;
@@ -101,6 +109,18 @@ enum LayerId {
     L_LAT1, L_LAT2, L_IMG1, L_IMG2, L_DRNN, L_DT1, L_DT2, L_DT3, L_DST1, L_DST2,
     L_RN1, L_RN2, L_RN3, L_SP1, L_SP2, L_DEC1, L_DEC2, L_DEC3, L_COUNT
 };
+
+// fp32 -> (hi, lo), both exactly representable in tf32: hi = w truncated to 10 mantissa bits (so w - hi is exact), lo = the
+// remainder rounded to nearest.  hi + lo differs from w by <= 2^-22 |w|.
+SQ_HD void split_weight(float w, float& hi, float& lo) {
+    union { float f; uint32_t u; } a, b;
+    a.f = w;
+    a.u &= 0xffffe000u;
+    hi = a.f;
+    b.f = w - hi;
+    b.u = (b.u + 0x1000u) & 0xffffe000u;
+    lo = b.f;
+}
 
 // Feature offsets inside a PropOut / DiscOut entry (a "slot record").
 struct RecF {
@@ -414,7 +434,10 @@ struct PlanBuilder {
             l.npanel = 1;
         }
         l.nmt = l.Nc / 16;
-        l.panel_floats = l.nmt * l.ksteps * 128;
+        l.panel_floats = l.nmt * l.ksteps * 256;
+        l.w1_off = (int)wcursor;
+        wcursor += (int64_t)l.npanel * (l.panel_floats / 2);
+        wcursor = (wcursor + 31) / 32 * 32;
         l.w_off = (int)wcursor;
         wcursor += (int64_t)l.npanel * l.panel_floats;
         wcursor = (wcursor + 31) / 32 * 32;

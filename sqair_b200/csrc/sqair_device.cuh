@@ -147,7 +147,7 @@ SQ_DEV float4 ldg_stream(const float4* p) {
     asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
-// fp32 -> (hi, lo): hi = x truncated to the tf32 mantissa (so hi + r == x exactly), lo = r rounded to tf32
+// activations: fp32 -> (hi, lo): hi = x truncated to the tf32 mantissa (so hi + r == x exactly), lo = r rounded to tf32
 SQ_DEV void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
     hi = __float_as_uint(x) & 0xffffe000u;
     const float r = x - __uint_as_float(hi);
@@ -293,19 +293,33 @@ SQ_DEV int head_of(const Layer& L, int vc, int& j) {
 
 #ifndef SQAIR_HOST_EMU
 #ifndef SQAIR_MMA_U
-#define SQAIR_MMA_U 4        // measured on c2: 4 -> 7.9 ms, 6 -> 8.0 ms, 8 -> 8.6 ms (register pressure), 2 -> 8.2 ms
+#define SQAIR_MMA_U 2        // k-steps in flight (2 LDG.128 each)
 #endif
 constexpr int MMA_U = SQAIR_MMA_U;   // k-steps (LDG.128 per lane) in flight per warp
 
-// One k-step: acc += A * B in (almost) fp32: both operands are split into tf32 (hi, lo) and all four partial
-// products of the 8 k values are summed on the tensor core, smallest first, starting from zero; the k-step's sum
-// then joins the running sum with a round-to-nearest FADD.  (The tensor core truncates when it accumulates:
-// chaining one accumulator through hundreds of MMAs biases the result by ~1e-5 relative, ten times the fp32
-// FMA-chain error -- measured as canvas parity failures on the c2 workload.)
-SQ_DEV void mma_kstep(float (&acc)[4], const float4& a, float b0f, float b1f) {
+// A fragment of one k-step as stored: tf32 hi and lo parts of the four weights of this lane
+struct AFrag {
+    float4 hi, lo;
+};
+SQ_DEV AFrag ldg_afrag(const float4* p) {
+    AFrag a;
+    a.hi = ldg_stream(p);
+    a.lo = ldg_stream(p + 32);
+    return a;
+}
+SQ_DEV void afrag_bits(const AFrag& a, uint32_t (&ah)[4], uint32_t (&al)[4]) {
+    ah[0] = __float_as_uint(a.hi.x); ah[1] = __float_as_uint(a.hi.y); ah[2] = __float_as_uint(a.hi.z); ah[3] = __float_as_uint(a.hi.w);
+    al[0] = __float_as_uint(a.lo.x); al[1] = __float_as_uint(a.lo.y); al[2] = __float_as_uint(a.lo.z); al[3] = __float_as_uint(a.lo.w);
+}
+
+// One k-step: acc += A * B in (almost) fp32.  The weights arrive pre-split into tf32 (hi, lo) (pack time), the
+// activations are split here; all four partial products of the 8 k values are summed on the tensor core, smallest
+// first, starting from zero; the k-step's sum then joins the running sum with a round-to-nearest FADD.  (The tensor
+// core truncates when it accumulates: chaining one accumulator through hundreds of MMAs biases the result by ~1e-5
+// relative, ten times the fp32 FMA-chain error -- measured as canvas parity failures on the c2 workload.)
+SQ_DEV void mma_kstep(float (&acc)[4], const AFrag& a, float b0f, float b1f) {
     uint32_t ah[4], al[4], b0h, b0l, b1h, b1l;
-    split_tf32(a.x, ah[0], al[0]); split_tf32(a.y, ah[1], al[1]);
-    split_tf32(a.z, ah[2], al[2]); split_tf32(a.w, ah[3], al[3]);
+    afrag_bits(a, ah, al);
     split_tf32(b0f, b0h, b0l); split_tf32(b1f, b1h, b1l);
     float d[4], e[4];                               // two independent chains (an MMA has ~21 cycles of latency)
     mma_tf32_zero(d, al, b0l, b1l);
@@ -315,12 +329,12 @@ SQ_DEV void mma_kstep(float (&acc)[4], const float4& a, float b0f, float b1f) {
     acc[0] += d[0] + e[0]; acc[1] += d[1] + e[1]; acc[2] += d[2] + e[2]; acc[3] += d[3] + e[3];
 }
 
-// Two k-steps at once: the splits and MMA chains of the pair are independent (more work per dependent-issue slot;
-// the loop is bound by in-order issue latency with 3 warps per scheduler).
-SQ_DEV void mma_kstep2(float (&acc)[4], const float4& a0, float p0, float p1, const float4& a1, float q0, float q1) {
+// Two k-steps at once: the MMA chains of the pair are independent (more work per dependent-issue slot; the loop is
+// bound by in-order issue latency with 3 warps per scheduler).
+SQ_DEV void mma_kstep2(float (&acc)[4], const AFrag& a0, float p0, float p1, const AFrag& a1, float q0, float q1) {
     uint32_t ah[4], al[4], ch[4], cl[4], p0h, p0l, p1h, p1l, q0h, q0l, q1h, q1l;
-    split_tf32(a0.x, ah[0], al[0]); split_tf32(a0.y, ah[1], al[1]); split_tf32(a0.z, ah[2], al[2]); split_tf32(a0.w, ah[3], al[3]);
-    split_tf32(a1.x, ch[0], cl[0]); split_tf32(a1.y, ch[1], cl[1]); split_tf32(a1.z, ch[2], cl[2]); split_tf32(a1.w, ch[3], cl[3]);
+    afrag_bits(a0, ah, al);
+    afrag_bits(a1, ch, cl);
     split_tf32(p0, p0h, p0l); split_tf32(p1, p1h, p1l); split_tf32(q0, q0h, q0l); split_tf32(q1, q1h, q1l);
     float d[4], e[4];
     mma_tf32_zero(d, al, p0l, p1l);
@@ -344,11 +358,11 @@ template <int R, bool IMAGE>
 SQ_DEV void mma_unit(const Layer& L, const float4* SQ_RESTRICT wp, int k0, int k1, int slot, const float* SQ_RESTRICT img_g,
                      int lane, float (&acc)[4]) {
     const int g = lane >> 2, t = lane & 3, gr = g < R ? g : R - 1;
-    float4 buf[MMA_U];
+    AFrag buf[MMA_U];
 #pragma unroll
     for (int j = 0; j < MMA_U; ++j)
-        if (k0 + j < k1) buf[j] = ldg_stream(wp + j * 32);
-    wp += MMA_U * 32;
+        if (k0 + j < k1) buf[j] = ldg_afrag(wp + j * 64);
+    wp += MMA_U * 64;
     int si = 0;                                        // segment that holds k-step k0
     while (si + 1 < L.nseg && L.seg[si + 1].ks0 <= k0) ++si;
     int seg_end = 0, ld4 = 0, step = 0, K = 0, kloc = 0;
@@ -377,13 +391,13 @@ SQ_DEV void mma_unit(const Layer& L, const float4* SQ_RESTRICT wp, int k0, int k
             kloc += 8;
         }
     };
-    auto kstep = [&](int ks, float4& slot_buf, bool refill) {
-        const float4 a = slot_buf;
+    auto kstep = [&](int ks, AFrag& slot_buf, bool refill) {
+        const AFrag a = slot_buf;
         float b0f, b1f;
         fetch_b(ks, b0f, b1f);
         mma_kstep(acc, a, b0f, b1f);
-        if (refill) slot_buf = ldg_stream(wp);         // issued after the MMAs that consumed this slot (both are volatile)
-        wp += 32;
+        if (refill) slot_buf = ldg_afrag(wp);          // issued after the MMAs that consumed this slot (both are volatile)
+        wp += 64;
     };
     static_assert(MMA_U % 2 == 0, "k-steps are processed in pairs");
     int kk = k0;
@@ -394,9 +408,9 @@ SQ_DEV void mma_unit(const Layer& L, const float4* SQ_RESTRICT wp, int k0, int k
             fetch_b(kk + j, p0, p1);
             fetch_b(kk + j + 1, q0, q1);
             mma_kstep2(acc, buf[j], p0, p1, buf[j + 1], q0, q1);
-            buf[j] = ldg_stream(wp);
-            buf[j + 1] = ldg_stream(wp + 32);
-            wp += 64;
+            buf[j] = ldg_afrag(wp);
+            buf[j + 1] = ldg_afrag(wp + 64);
+            wp += 128;
         }
     }
     for (; kk < k1; kk += MMA_U) {                     // last one or two groups
@@ -470,7 +484,8 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
             for (int si = 0; si < L.nseg; ++si) {
                 const Seg& S = L.seg[si];
                 for (int k = 0; k < S.K; ++k) {
-                    const float w = panel[frag_off(L.ksteps, col >> 4, S.ks0 + (k >> 3), col & 15, k & 7)];
+                    const int fo = frag_off(L.ksteps, col >> 4, S.ks0 + (k >> 3), col & 15, k & 7);
+                    const float w = panel[(fo >> 7) * 256 + (fo & 127)] + panel[(fo >> 7) * 256 + 128 + (fo & 127)];   // hi + lo
                     for (int r = 0; r < R; ++r) {
                         const float x = S.kind == SEG_IMAGE ? imgrow[r][k] : SQ_SM[S.x_off + slot * S.x_sstride + k * S.ld + r];
                         redv[(size_t)col * R + r] += w * x;
@@ -478,7 +493,8 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
                 }
                 // the zero padding of the packed panel must really be zero
                 for (int k = S.K; k < (S.K + 7) / 8 * 8; ++k)
-                    if (panel[frag_off(L.ksteps, col >> 4, S.ks0 + (k >> 3), col & 15, k & 7)] != 0.f) {
+                    if (panel[(frag_off(L.ksteps, col >> 4, S.ks0 + (k >> 3), col & 15, k & 7) >> 7) * 256 +
+                              (frag_off(L.ksteps, col >> 4, S.ks0 + (k >> 3), col & 15, k & 7) & 127)] != 0.f) {
                         fprintf(stderr, "emu: non-zero padding weight (layer %d)\n", layer_id);
                         abort();
                     }
@@ -496,7 +512,7 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
             c.prof[6] += k1 - k0; c.prof[7] += 1;
 #endif
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            const float4* wp = reinterpret_cast<const float4*>(panel) + ((size_t)mt * ksteps + k0) * 32 + lane;
+            const float4* wp = reinterpret_cast<const float4*>(panel) + ((size_t)mt * ksteps + k0) * 64 + lane;
             if (L.seg[0].kind == SEG_IMAGE) mma_unit<R, true>(L, wp, k0, k1, slot, img_g, lane, acc);
             else mma_unit<R, false>(L, wp, k0, k1, slot, img_g, lane, acc);
             // C fragment: acc[0] = (col g, row 2t), acc[1] = (g, 2t+1), acc[2] = (g+8, 2t), acc[3] = (g+8, 2t+1)
@@ -554,15 +570,25 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
 // ---------------------------------------------------------------------------------------------
 // The per-block state machine
 // ---------------------------------------------------------------------------------------------
+#ifndef SQAIR_HOST_EMU
+#define P c_plan
+#endif
 template <int R>
 struct Block {
     Ctx& c;
 #ifdef SQAIR_HOST_EMU
     const Plan& P;
 #else
-    const PlanHdr& P;
+    // no member on the device: `P` is the __constant__ symbol itself (see the macro above the struct), so that every
+    // plan field is a constant-bank load; through a reference member the compiler emitted ~2 000 generic LD.E
 #endif
-    const Job& J;            // the __grid_constant__ kernel parameter (constant-bank loads)
+    const Job& J;            // the __grid_constant__ kernel parameter; only the output table is read through it
+    const float* prm_;       // hot fields of the job, copied once (through the reference they were generic loads)
+    const float* obs_;
+    const float* eps_where_;
+    const float* eps_what_;
+    const float* u_pres_;
+    int dbg_;
     int row0;                       // first global row of this block
     const float* imgrow[R];         // frame of each row for the current t
     const float* img_g;             // frame of the row this lane feeds to the MMA B fragment (row min(lane / 4, R - 1))
@@ -570,7 +596,12 @@ struct Block {
     int grow[R];                    // global row (clamped) of each local row
     bool valid[R];
 
+#ifdef SQAIR_HOST_EMU
     SQ_DEV Block(Ctx& c_, const Job& J_, int row0_) : c(c_), P(SQ_PLAN_OF(c_)), J(J_), row0(row0_) {
+#else
+    SQ_DEV Block(Ctx& c_, const Job& J_, int row0_) : c(c_), J(J_), row0(row0_) {
+#endif
+        prm_ = J_.prm; obs_ = J_.obs; eps_where_ = J_.eps_where; eps_what_ = J_.eps_what; u_pres_ = J_.u_pres; dbg_ = J_.debug_flags;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             int gr = row0 + r;
@@ -590,10 +621,14 @@ struct Block {
     SQ_DEV float& pri(int f, int s, int r) const { return SQ_SM[P.sm.Pri + f * LDS() + s * R + r]; }
     SQ_DEV float& lp(int k, int s, int r) const { return SQ_SM[P.sm.Lp + k * LDS() + s * R + r]; }
     SQ_DEV float& rowacc(int k, int r) const { return SQ_SM[P.sm.RowAcc + k * R + r]; }
-    SQ_DEV float prm(int off) const { return SQ_LDG(J.prm + off); }
+    SQ_DEV float prm(int off) const { return SQ_LDG(prm_ + off); }
     SQ_DEV void lin(int id, int slot = 0) const {
-        if (J.debug_flags & 64) return;
-        dense<R>(c, J.prm, id, slot, imgrow, img_g, J.debug_flags);
+        if (dbg_ & 64) return;
+#ifdef SQAIR_HOST_EMU
+        dense<R>(c, prm_, id, slot, imgrow, img_g, dbg_);
+#else
+        dense<R>(c, prm_, id, slot, nullptr, img_g, dbg_);      // passing the array would pin imgrow[] to local memory
+#endif
     }
     SQ_DEV size_t nidx(int t, int r, int slot2) const {      // noise index of (t, row, slot in [0,2n))
         return ((size_t)t * P.rows + grow[r]) * (2 * P.NS) + slot2;
@@ -651,7 +686,7 @@ struct Block {
         const int G = P.cfg.G, W = P.cfg.W, H = P.cfg.H;
         const float hw = 0.5f * (float)(W - 1), hh = 0.5f * (float)(H - 1);
         wait_frame();
-        for (int i = c.tid(); i < ((J.debug_flags & 8) ? 0 : P.g * R); i += c.nthreads()) {
+        for (int i = c.tid(); i < ((dbg_ & 8) ? 0 : P.g * R); i += c.nthreads()) {
             const int r = i % R, j = i / R;
             const int gy = j / G, gx = j % G;
             const float sx = SQ_SM[m.Coords + 0 * R + r], sy = SQ_SM[m.Coords + 1 * R + r];
@@ -757,7 +792,7 @@ struct Block {
             for (int i = 0; i < 4; ++i) {
                 loc[i] = Z(nw + i, s, r) + P.cfg.where_update_scale * SQ_SM[m.Tp + i * R + r];
                 sc[i] = softplusf_(SQ_SM[m.Tp + (4 + i) * R + r] + so - 1.f) + 1e-2f;
-                eps[i] = J.eps_where[nidx(t, r, s) * 4 + i];
+                eps[i] = eps_where_[nidx(t, r, s) * 4 + i];
             }
             tril_from_scale(sc, L);
 #pragma unroll
@@ -793,7 +828,7 @@ struct Block {
             float loct = SQ_SM[m.Tg + i], sct = SQ_SM[m.Tg + nw * R + i];
             float wl = fg * Z(j, s, r) + (1.f - ig) * loc2 + (1.f - tg) * loct;
             float ws = (1.f - ig) * sc2 + (1.f - tg) * sct;
-            float what = wl + ws * J.eps_what[nidx(t, r, s) * nw + j];
+            float what = wl + ws * eps_what_[nidx(t, r, s) * nw + j];
             rec(m.PropOut, e, F.what + j, r) = what;
             rec(m.PropOut, e, F.what_loc + j, r) = wl;
             rec(m.PropOut, e, F.what_scale + j, r) = ws;
@@ -804,7 +839,7 @@ struct Block {
             const float ptm1 = Z(nw + 4, s, r);
             float logit = ptm1 * SQ_SM[m.Lg + r] + (ptm1 - 1.f) * 88.f;
             float prob = sigmoidf_(logit);
-            float pres = (J.u_pres[nidx(t, r, s)] < prob ? 1.f : 0.f) * ptm1;
+            float pres = (u_pres_[nidx(t, r, s)] < prob ? 1.f : 0.f) * ptm1;
             rec(m.PropOut, e, F.logit, r) = logit;
             rec(m.PropOut, e, F.prob, r) = prob;
             rec(m.PropOut, e, F.pres, r) = pres;
@@ -897,7 +932,7 @@ struct Block {
             for (int i = 0; i < 4; ++i) {
                 float loc = SQ_SM[m.Tp + i * R + r];
                 float sc = softplusf_(SQ_SM[m.Tp + (4 + i) * R + r] + so) + 1e-2f;
-                wh[i] = loc + sc * J.eps_where[nidx(t, r, ns2) * 4 + i];
+                wh[i] = loc + sc * eps_where_[nidx(t, r, ns2) * 4 + i];
                 rec(m.DiscOut, e, F.where + i, r) = wh[i];
                 rec(m.DiscOut, e, F.where_loc + i, r) = loc;
                 rec(m.DiscOut, e, F.where_scale + i, r) = sc;
@@ -913,7 +948,7 @@ struct Block {
         for (int i = c.tid(); i < nw * R; i += c.nthreads()) {        // core.py:216-218
             int j = i / R, r = i % R;
             float wl = SQ_SM[m.Enc + i], ws = SQ_SM[m.Enc + nw * R + i];
-            rec(m.DiscOut, e, F.what + j, r) = wl + ws * J.eps_what[nidx(t, r, ns2) * nw + j];
+            rec(m.DiscOut, e, F.what + j, r) = wl + ws * eps_what_[nidx(t, r, ns2) * nw + j];
             rec(m.DiscOut, e, F.what_loc + j, r) = wl;
             rec(m.DiscOut, e, F.what_scale + j, r) = ws;
         }
@@ -923,7 +958,7 @@ struct Block {
             const float pkm1 = rec(m.DiscOut, s, F.pres, r);      // entry 0 holds the initial 1 (core.py:153)
             float logit = pkm1 * SQ_SM[m.Lg + r] + (pkm1 - 1.f) * 88.f;
             float prob = sigmoidf_(logit);
-            float pres = (J.u_pres[nidx(t, r, ns2)] < prob ? 1.f : 0.f) * pkm1;
+            float pres = (u_pres_[nidx(t, r, ns2)] < prob ? 1.f : 0.f) * pkm1;
             rec(m.DiscOut, e, F.logit, r) = logit;
             rec(m.DiscOut, e, F.prob, r) = prob;
             rec(m.DiscOut, e, F.pres, r) = pres;
@@ -1160,7 +1195,7 @@ struct Block {
         const int px0 = c.rank() * px_per, px1 = (px0 + px_per < PX) ? (px0 + px_per) : PX;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            for (int px = px0 + c.tid(); px < ((J.debug_flags & 4) ? 0 : px1); px += c.nthreads()) {
+            for (int px = px0 + c.tid(); px < ((dbg_ & 4) ? 0 : px1); px += c.nthreads()) {
                 const int iy = px / W, ix = px % W;
                 const float u = lin11(ix, W), v = lin11(iy, H);
                 float canvas = 0.f, nz = 0.f;
@@ -1219,7 +1254,7 @@ struct Block {
         const int NS = P.NS;
         const sqair_outputs& o = J.out;
         const size_t trow = (size_t)t * P.rows;
-        if (c.rank() != 0 || (J.debug_flags & 32)) { c.sync(); return; }                  // replicas hold identical values
+        if (c.rank() != 0 || (dbg_ & 32)) { c.sync(); return; }                  // replicas hold identical values
         for (int i = c.tid(); i < LDS(); i += c.nthreads()) {
             const int s = i / R, r = i % R;
             if (!valid_row(r)) continue;
@@ -1283,7 +1318,7 @@ struct Block {
         const Smem& m = P.sm;
         const int NS = P.NS, nh = P.nh;
 #pragma unroll
-        for (int r = 0; r < R; ++r) imgrow[r] = J.obs + ((size_t)t * P.cfg.B + grow[r] / P.cfg.K) * P.PX;
+        for (int r = 0; r < R; ++r) imgrow[r] = obs_ + ((size_t)t * P.cfg.B + grow[r] / P.cfg.K) * P.PX;
 #ifndef SQAIR_HOST_EMU
         if (m.img_n > 0) {
             // TMA: one bulk copy per sequence of this block's rows, completion on an mbarrier whose phase is the frame
@@ -1294,7 +1329,7 @@ struct Block {
                 const uint32_t bar = smem_u32(SQ_SM + m.ImgBar);
                 mbar_expect_tx(bar, (uint32_t)(nimg * P.PX) * 4u);
                 for (int i = 0; i < nimg; ++i)
-                    bulk_g2s(smem_u32(SQ_SM + m.Img + i * P.PX), J.obs + ((size_t)t * P.cfg.B + b0 + i) * P.PX, (uint32_t)P.PX * 4u, bar);
+                    bulk_g2s(smem_u32(SQ_SM + m.Img + i * P.PX), obs_ + ((size_t)t * P.cfg.B + b0 + i) * P.PX, (uint32_t)P.PX * 4u, bar);
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) imgrow[r] = SQ_SM + m.Img + (grow[r] / P.cfg.K - b0) * P.PX;
@@ -1337,10 +1372,13 @@ struct Block {
     }
 
     SQ_DEV void run() {
-        calls_init(c, J.prm);
+        calls_init(c, prm_);
         init_sequence();
         for (int t = 0; t < P.cfg.T; ++t) frame(t);
     }
 };
+#ifndef SQAIR_HOST_EMU
+#undef P
+#endif
 
 }  // namespace sq

@@ -85,7 +85,7 @@ class ParamStore(object):
 
     def packed(self, cfg=None):
         """Kernel-side copy for a call with configuration `cfg` (the packed layout depends on the launch shape the
-        library picks for the call: cluster size and ring chunking); re-packed only after the parameters changed."""
+        library picks for the call: the cluster size); re-packed only after the parameters changed."""
         cfg = cfg or self.cfg
         s = _capi.query_sizes(cfg)
         key = (s.cluster_size, s.packed_floats, cfg.n)

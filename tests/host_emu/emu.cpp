@@ -26,9 +26,20 @@ static void pack_host(const Plan& plan, const std::vector<ParamEntry>& tab, cons
         for (int k = 0; k < pc.K; ++k)
             for (int n = 0; n < pc.N; ++n) {
                 const int vrow = pc.vrow0 + k, vcol = pc.vcol0 + n, panel = vcol / L.Nc, cc = vcol - panel * L.Nc;
-                packed[(size_t)L.w_off + (size_t)panel * L.panel_floats + frag_off(L.ksteps, cc >> 4, vrow >> 3, cc & 15, vrow & 7)] +=
+                packed[(size_t)L.w1_off + (size_t)panel * (L.panel_floats / 2) + frag_off(L.ksteps, cc >> 4, vrow >> 3, cc & 15, vrow & 7)] +=
                     params[pc.src_off + (int64_t)k * pc.src_ld + n];
             }
+    }
+    for (int id = 0; id < L_COUNT; ++id) {          // same split as split_panels_kernel
+        const Layer& L = plan.L[id];
+        if (L.nhead == 0) continue;
+        for (int i = 0; i < L.npanel * (L.panel_floats / 2); ++i) {
+            float hi, lo;
+            split_weight(packed[(size_t)L.w1_off + i], hi, lo);
+            const size_t d = (size_t)L.w_off + (size_t)(i >> 7) * 256 + (i & 127);
+            packed[d] = hi;
+            packed[d + 128] = lo;
+        }
     }
 }
 
