@@ -593,8 +593,6 @@ struct Block {
     const float* imgrow[R];         // frame of each row for the current t
     const float* img_g;             // frame of the row this lane feeds to the MMA B fragment (row min(lane / 4, R - 1))
     uint32_t frame_parity;          // mbarrier phase of the current frame's TMA copy
-    int grow[R];                    // global row (clamped) of each local row
-    bool valid[R];
 
 #ifdef SQAIR_HOST_EMU
     SQ_DEV Block(Ctx& c_, const Job& J_, int row0_) : c(c_), P(SQ_PLAN_OF(c_)), J(J_), row0(row0_) {
@@ -604,9 +602,6 @@ struct Block {
         prm_ = J_.prm; obs_ = J_.obs; eps_where_ = J_.eps_where; eps_what_ = J_.eps_what; u_pres_ = J_.u_pres; dbg_ = J_.debug_flags;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            int gr = row0 + r;
-            valid[r] = gr < P.rows;
-            grow[r] = valid[r] ? gr : P.rows - 1;
             imgrow[r] = nullptr;
         }
         img_g = nullptr;
@@ -631,7 +626,7 @@ struct Block {
 #endif
     }
     SQ_DEV size_t nidx(int t, int r, int slot2) const {      // noise index of (t, row, slot in [0,2n))
-        return ((size_t)t * P.rows + grow[r]) * (2 * P.NS) + slot2;
+        return ((size_t)t * P.rows + grow_of(r)) * (2 * P.NS) + slot2;
     }
     enum { RA_QPRES = 0, RA_PPRES = 1, RA_NPROP = 2, RA_NDISC = 3, RA_QNUM = 4, RA_PNUM = 5, RA_LL = 6 };
     enum { LP_PQWHAT = 0, LP_PQWHERE = 1, LP_PPWHAT = 2, LP_PPWHERE = 3, LP_PROB = 4,
@@ -1146,18 +1141,10 @@ struct Block {
         }
         c.sync();
     }
-    SQ_DEV bool valid_row(int r) const {
-        bool v = valid[0];
-#pragma unroll
-        for (int q = 1; q < R; ++q) if (r == q) v = valid[q];
-        return v;
-    }
-    SQ_DEV int grow_of(int r) const {
-        int v = grow[0];
-#pragma unroll
-        for (int q = 1; q < R; ++q) if (r == q) v = grow[q];
-        return v;
-    }
+    // local row r of this block: is it a real row, and its global index (clamped: padding rows recompute the last row).
+    // Plain arithmetic on purpose: member arrays indexed with a run-time r would pin the whole object to local memory.
+    SQ_DEV bool valid_row(int r) const { return row0 + r < P.rows; }
+    SQ_DEV int grow_of(int r) const { return row0 + r < P.rows ? row0 + r : P.rows - 1; }
 
     // ------------------------------------------------------------------------------------------
     // decoder + canvas + pixel likelihood (modules.py:435-467; seq.py:271-273)
@@ -1215,7 +1202,7 @@ struct Block {
                 canvas += prm(P.po.mean_img + px) * mask;                           // modules.py:465
                 const float std = mask * sf + (1.f - mask) * sb;                    // modules.py:453
                 ll[r] += normal_lp(imgrow[r][px], canvas, std);
-                if (o.canvas && valid[r]) o.canvas[(trow + grow[r]) * PX + px] = canvas;
+                if (o.canvas && valid_row(r)) o.canvas[(trow + grow_of(r)) * PX + px] = canvas;
             }
         }
         // block reduction of the R partial sums, then the cluster's partial sums meet in every block
@@ -1318,13 +1305,13 @@ struct Block {
         const Smem& m = P.sm;
         const int NS = P.NS, nh = P.nh;
 #pragma unroll
-        for (int r = 0; r < R; ++r) imgrow[r] = obs_ + ((size_t)t * P.cfg.B + grow[r] / P.cfg.K) * P.PX;
+        for (int r = 0; r < R; ++r) imgrow[r] = obs_ + ((size_t)t * P.cfg.B + grow_of(r) / P.cfg.K) * P.PX;
 #ifndef SQAIR_HOST_EMU
         if (m.img_n > 0) {
             // TMA: one bulk copy per sequence of this block's rows, completion on an mbarrier whose phase is the frame
             // index; the first glimpse extraction of the frame waits for it (a few dense layers later).  Every thread is
             // past the barrier that ended the previous frame, so nobody still reads the old frame.
-            const int b0 = grow[0] / P.cfg.K, nimg = grow[R - 1] / P.cfg.K - b0 + 1;
+            const int b0 = grow_of(0) / P.cfg.K, nimg = grow_of(R - 1) / P.cfg.K - b0 + 1;
             if (c.tid() == 0) {
                 const uint32_t bar = smem_u32(SQ_SM + m.ImgBar);
                 mbar_expect_tx(bar, (uint32_t)(nimg * P.PX) * 4u);
@@ -1332,7 +1319,7 @@ struct Block {
                     bulk_g2s(smem_u32(SQ_SM + m.Img + i * P.PX), obs_ + ((size_t)t * P.cfg.B + b0 + i) * P.PX, (uint32_t)P.PX * 4u, bar);
             }
 #pragma unroll
-            for (int r = 0; r < R; ++r) imgrow[r] = SQ_SM + m.Img + (grow[r] / P.cfg.K - b0) * P.PX;
+            for (int r = 0; r < R; ++r) imgrow[r] = SQ_SM + m.Img + (grow_of(r) / P.cfg.K - b0) * P.PX;
             frame_parity = (uint32_t)(t & 1);
         }
 #endif
