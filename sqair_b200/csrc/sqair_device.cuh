@@ -142,9 +142,19 @@ SQ_DEV void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 // plain read-only loads: when streaming they sustain 117 GB/s per SM, L1::no_allocate only 74 (tools/ldg_stream.cu)
+#ifndef SQAIR_LDG_KIND
+#define SQAIR_LDG_KIND 0
+#endif
 SQ_DEV float4 ldg_stream(const float4* p) {
     float4 v;
-    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+#if SQAIR_LDG_KIND == 1
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+#elif SQAIR_LDG_KIND == 2
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+#else
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+#endif
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
 // activations: fp32 -> (hi, lo): hi = x truncated to the tf32 mantissa (so hi + r == x exactly), lo = r rounded to tf32
@@ -354,8 +364,13 @@ SQ_DEV void mma_kstep2(float (&acc)[4], const AFrag& a0, float p0, float p1, con
 // (activations, x[k][row]) come from shared memory -- or from the frame for SEG_IMAGE.  The last k-step of a
 // segment may read up to 7 feature rows past the segment: the matching weight rows are zero and shared memory only
 // ever holds finite values (it is cleared at kernel start), so those products vanish.
+#ifdef SQAIR_UNIT_NOINLINE
+#define SQ_UNIT SQ_DEVNI
+#else
+#define SQ_UNIT SQ_DEV
+#endif
 template <int R, bool IMAGE>
-SQ_DEV void mma_unit(const Layer& L, const float4* SQ_RESTRICT wp, int k0, int k1, int slot, const float* SQ_RESTRICT img_g,
+SQ_UNIT void mma_unit(const Layer& L, const float4* SQ_RESTRICT wp, int k0, int k1, int slot, const float* SQ_RESTRICT img_g,
                      int lane, float (&acc)[4]) {
     const int g = lane >> 2, t = lane & 3, gr = g < R ? g : R - 1;
     AFrag buf[MMA_U];
