@@ -26,3 +26,14 @@ def combine_batch_means(local_means, n_local, group=None):
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     return (buf[:-1] / buf[-1]).to(local_means.dtype).reshape(local_means.shape)
+
+
+def allreduce_flat_gradient(flat_grad, n_local, n_global, group=None):
+    """The one collective of a training step: every rank holds the gradient of ITS shard's batch mean in
+    the flat parameter layout (`sqair_param_layout` order); the global-batch gradient is sum_r grad_r * n_r / n_global.
+    In place, one all-reduce (NCCL over NVLink on the GPU box, gloo in the CPU tests).  The backward kernels that
+    produce `flat_grad` are not built yet; the objective-side inputs are (`ops.objective_grad`)."""
+    flat_grad.mul_(float(n_local) / float(n_global))
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return flat_grad

@@ -31,6 +31,10 @@ def _worker(rank, world, port, q):
     out, obj = TL.run_oracle(cfg, imgs[:, start:start + count], params, noise)
     local = torch.tensor([float(obj['elbo_vae']), float(obj['elbo_iwae'])])
     combined = parallel.combine_batch_means(local, count)
+    # flat-gradient all-reduce: per-rank gradients of shard means -> gradient of the global batch mean
+    g = torch.full((7,), float(rank + 1))
+    parallel.allreduce_flat_gradient(g, count, full.B)
+    assert torch.allclose(g, torch.full((7,), (1. * 3 + 2. * 2) / 5.)), g
     q.put((rank, start, count, out['log_weights_per_timestep'], combined.numpy()))
     dist.barrier()
     dist.destroy_process_group()
