@@ -141,6 +141,13 @@ int sqair_objective(const float* log_w_t, const float* disc_lp_t, int32_t T, int
 int sqair_objective_grad(const float* log_w_t, const float* disc_lp_t, int32_t T, int32_t B, int32_t K,
                          float* d_log_weights, float* d_discrete_log_prob, void* stream);
 
+/* Weight gradient of one dense layer (the GEMM-shaped part of the backward pass): dW [K,N] (+)= X^T dY for
+ * the stashed layer inputs X [M,K] and output gradients dY [M,N], M = rows x frames x slots, all row-major fp32.
+ * fp32-faithful on the tensor cores (tf32 hi/lo split of both operands, four products, per-k-step fp32 accumulation).
+ * accumulate != 0 adds into dW (which must then be initialised), otherwise dW is overwritten. */
+int sqair_wgrad(const float* x, const float* dy, float* dw, int32_t M, int32_t K, int32_t N, int32_t accumulate,
+                void* stream);
+
 /* Per-op entry points (unit parity / roofline of the bandwidth-shaped pieces).
  * sqair_stn_glimpse: SpatialTransformer forward (modules.py:165-172,204-218): img [N,H,W],
  *   where-logits [N,4] -> glimpse [N,G,G].

@@ -568,6 +568,79 @@ __global__ void canvas_ll_kernel(const float* __restrict__ glimpse, const float*
     }
 }
 
+// Weight gradient dW[K,N] (+)= X[M,K]^T dY[M,N].  Block tile 64 (K) x 64 (N), 4 warps of 32 x 32 (2 m16 x 4 n8 MMA tiles),
+// M walked in chunks of 32 rows staged in shared memory (row stride 72 floats: conflict-free fragment reads), grid.z
+// splits M (partial tiles meet by atomicAdd).  Same arithmetic as the forward layers: tf32 (hi, lo) of both operands,
+// four products per 8 reduction steps summed from zero on the tensor core, fp32 round-to-nearest accumulation outside.
+constexpr int WG_T = 64, WG_MC = 32, WG_LD = 72;
+__global__ void __launch_bounds__(128) wgrad_kernel(const float* __restrict__ X, const float* __restrict__ dY, float* __restrict__ dW,
+                                                    int M, int K, int N, int m_per_block, int atomic) {
+    __shared__ float Xs[WG_MC * WG_LD], Ys[WG_MC * WG_LD];
+    const int n0 = blockIdx.x * WG_T, k0 = blockIdx.y * WG_T;
+    const int m_begin = blockIdx.z * m_per_block, m_end = min(M, m_begin + m_per_block);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int wk = (warp >> 1) * 32, wn = (warp & 1) * 32;          // warp tile origin inside the block tile
+    float acc[2][4][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[a][b][q] = 0.f;
+    for (int m0 = m_begin; m0 < m_end; m0 += WG_MC) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < WG_MC * WG_T; i += blockDim.x) {     // zero-filled edges
+            const int mm = i / WG_T, cc = i - mm * WG_T, m = m0 + mm;
+            Xs[mm * WG_LD + cc] = (m < m_end && k0 + cc < K) ? __ldg(X + (size_t)m * K + k0 + cc) : 0.f;
+            Ys[mm * WG_LD + cc] = (m < m_end && n0 + cc < N) ? __ldg(dY + (size_t)m * N + n0 + cc) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ms = 0; ms < WG_MC; ms += 8) {
+            uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {       // A = X^T: element (row k, col m) = Xs[m][k]
+                const float* p = Xs + (ms + t) * WG_LD + wk + a * 16 + g;
+                split_tf32(p[0], ah[a][0], al[a][0]);
+                split_tf32(p[8], ah[a][1], al[a][1]);
+                split_tf32(p[4 * WG_LD], ah[a][2], al[a][2]);
+                split_tf32(p[4 * WG_LD + 8], ah[a][3], al[a][3]);
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {       // B = dY: element (row m, col n)
+                const float* p = Ys + (ms + t) * WG_LD + wn + b * 8 + g;
+                split_tf32(p[0], bh[b][0], bl[b][0]);
+                split_tf32(p[4 * WG_LD], bh[b][1], bl[b][1]);
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    float d[4];
+                    mma_tf32_zero(d, al[a], bl[b][0], bl[b][1]);
+                    mma_tf32(d, al[a], bh[b][0], bh[b][1]);
+                    mma_tf32(d, ah[a], bl[b][0], bl[b][1]);
+                    mma_tf32(d, ah[a], bh[b][0], bh[b][1]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[a][b][q] += d[q];
+                }
+        }
+    }
+    // C fragment: d[0] = (row g, col 2t), d[1] = (g, 2t+1), d[2] = (g+8, 2t), d[3] = (g+8, 2t+1)
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = k0 + wk + a * 16 + g + (q >> 1) * 8, n = n0 + wn + b * 8 + 2 * t + (q & 1);
+                if (k < K && n < N) {
+                    if (atomic) atomicAdd(dW + (size_t)k * N + n, acc[a][b][q]);
+                    else dW[(size_t)k * N + n] = acc[a][b][q];
+                }
+            }
+}
+
 // bilinear sample with zero padding plus its derivatives w.r.t. the sample position; `w4`/`idx4` receive the four texel
 // weights / linear indices (-1 = outside) for the scatter of the data gradient.
 struct Bilin {
@@ -864,6 +937,24 @@ int sqair_stn_glimpse(const float* img, const float* where, float* glimpse, int3
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     stn_glimpse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(img, where, glimpse, N, H, W, G);
+    CUDA_TRY(cudaGetLastError());
+    return SQAIR_OK;
+}
+
+int sqair_wgrad(const float* x, const float* dy, float* dw, int32_t M, int32_t K, int32_t N, int32_t accumulate, void* stream) {
+    if (!x || !dy || !dw || M < 1 || K < 1 || N < 1) return fail(SQAIR_EINVAL, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tiles = ((N + WG_T - 1) / WG_T) * ((K + WG_T - 1) / WG_T);
+    // split M so that the grid covers the 148 SMs a few times over; partial tiles then meet by atomicAdd
+    int msplit = (4 * 148 + tiles - 1) / tiles;
+    const int max_split = (M + 4 * WG_MC - 1) / (4 * WG_MC);
+    if (msplit > max_split) msplit = max_split;
+    if (msplit < 1) msplit = 1;
+    int m_per_block = ((M + msplit - 1) / msplit + WG_MC - 1) / WG_MC * WG_MC;
+    msplit = (M + m_per_block - 1) / m_per_block;
+    const int atomic = (msplit > 1 || accumulate) ? 1 : 0;
+    if (atomic && !accumulate) CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)K * N * sizeof(float), st));
+    wgrad_kernel<<<dim3((N + WG_T - 1) / WG_T, (K + WG_T - 1) / WG_T, msplit), 128, 0, st>>>(x, dy, dw, M, K, N, m_per_block, atomic);
     CUDA_TRY(cudaGetLastError());
     return SQAIR_OK;
 }

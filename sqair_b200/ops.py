@@ -153,3 +153,19 @@ def canvas_ll_grad(glimpse, where, presence, mean_img, img, d_ll, output_std=0.3
                                            _ptr(d_gl), _ptr(d_wh), _ptr(d_mi), N, n, H, W, G, float(output_std),
                                            float(output_std if bg_std is None else bg_std), _stream()))
     return d_gl, d_wh, d_mi
+
+
+def wgrad(x: torch.Tensor, dy: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """Weight gradient of a dense layer: x [M,K], dy [M,N] -> x^T dy [K,N] (added into `out` when given)."""
+    _need_cuda(x, dy)
+    M, K = x.shape
+    N = dy.shape[1]
+    if dy.shape[0] != M:
+        raise ValueError('x and dy must have the same number of rows')
+    acc = out is not None
+    if out is None:
+        out = torch.empty(K, N, dtype=torch.float32, device=x.device)
+    else:
+        _need_cuda(out)
+    check(_capi.lib().sqair_wgrad(_ptr(x), _ptr(dy), _ptr(out), M, K, N, int(acc), _stream()))
+    return out

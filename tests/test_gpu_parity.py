@@ -273,3 +273,19 @@ def test_canvas_ll_grad_op():
     for got, want in ((d_gl, glimpse.grad), (d_wh, where.grad), (d_mi, mean_img.grad)):
         w = want.numpy()
         np.testing.assert_allclose(got.cpu().numpy(), w, rtol=2e-3, atol=2e-3 * np.abs(w).max())
+
+
+@pytest.mark.parametrize('M,K,N', [(6400, 672, 256), (1600, 264, 109), (37, 5, 3), (640, 400, 256)])
+def test_wgrad_op(M, K, N):
+    """Weight-gradient GEMM of the backward pass (x^T dy, 3xTF32-split tensor-core path) against float64."""
+    ops, dev = _gpu()
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    dy = (rng.standard_normal((M, N)) * 0.1).astype(np.float32)
+    want = x.astype(np.float64).T @ dy.astype(np.float64)
+    got = ops.wgrad(torch.from_numpy(x).to(dev), torch.from_numpy(dy).to(dev)).cpu().numpy()
+    scale = np.sqrt(M) * 0.1
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-6 * scale)
+    base = torch.from_numpy(rng.standard_normal((K, N)).astype(np.float32)).to(dev)
+    got2 = ops.wgrad(torch.from_numpy(x).to(dev), torch.from_numpy(dy).to(dev), out=base.clone()).cpu().numpy()
+    np.testing.assert_allclose(got2, want + base.cpu().numpy().astype(np.float64), rtol=1e-5, atol=2e-6 * scale + 1e-6)
