@@ -174,7 +174,6 @@ __device__ long long g_trace[3][L_COUNT];      // per layer id: cycles inside de
 __device__ long long g_trace_last;
 #endif
 
-enum { CTL_CALL = 0, CTL_DESC };
 
 // cluster barrier, split phase: arrive (release) ... wait (acquire)
 SQ_DEV void cluster_arrive(Ctx& c) {
@@ -283,10 +282,6 @@ SQ_DEV void calls_init(Ctx& c, const float* prm) {
 #ifdef SQAIR_HOST_EMU
     c.call_idx = 0;
 #else
-    if (c.tid() == 0) {
-        int* ctl = reinterpret_cast<int*>(SQ_SM + P.sm.Ctl);
-        for (int i = 0; i < 16; ++i) ctl[i] = 0;
-    }
     if (c.tid() < DESC_WORDS) SQ_SM[P.sm.Desc + c.tid()] = SQ_LDG(prm + P.ltab_off + (int)P.seq[0] * DESC_WORDS + c.tid());
     c.sync();
 #endif
@@ -371,13 +366,16 @@ SQ_DEV void mma_kstep2(float (&acc)[4], const AFrag& a0, float p0, float p1, con
 #endif
 template <int R, bool IMAGE>
 SQ_UNIT void mma_unit(const Layer& L, const float4* SQ_RESTRICT wp, int k0, int k1, int slot, const float* SQ_RESTRICT img_g,
-                     int lane, float (&acc)[4]) {
+                     int lane, float (&acc)[4], bool wait_first) {
     const int g = lane >> 2, t = lane & 3, gr = g < R ? g : R - 1;
     AFrag buf[MMA_U];
 #pragma unroll
     for (int j = 0; j < MMA_U; ++j)
         if (k0 + j < k1) buf[j] = ldg_afrag(wp + j * 64);
     wp += MMA_U * 64;
+    // The previous dense call left its cluster barrier open (its outputs are this call's inputs): the weight loads above
+    // do not depend on them, so their L2 latency overlaps the wait.
+    if (wait_first) cluster_wait_();
     int si = 0;                                        // segment that holds k-step k0
     while (si + 1 < L.nseg && L.seg[si + 1].ks0 <= k0) ++si;
     int seg_end = 0, ld4 = 0, step = 0, K = 0, kloc = 0;
@@ -443,9 +441,13 @@ SQ_UNIT void mma_unit(const Layer& L, const float4* SQ_RESTRICT wp, int k0, int 
 // (m-tile of 16 columns) x (k-slice), dealt round-robin to the warps; the slices' partial sums meet in shared
 // memory; all threads then finish one output each (activation) and store it into every block of the cluster.
 // ---------------------------------------------------------------------------------------------
+// flags: bit 0 = the previous dense call deferred its cluster barrier wait (do it here, after the first weight loads are
+// in flight); bit 1 = the caller promises that the next operation is another dense call, so this call may leave its
+// own barrier open.  Returns true when it did.  call_idx / desc_cur: position in Plan::seq and descriptor slot (kept in
+// registers by the caller).
 template <int R>
-SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot,
-                    const float* const* imgrow, const float* SQ_RESTRICT img_g, int dbg) {
+SQ_DEVNI bool dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot,
+                    const float* const* imgrow, const float* SQ_RESTRICT img_g, int dbg, int flags, int call_idx, int desc_cur) {
     const auto& P = SQ_PLAN;
 #ifdef SQAIR_HOST_EMU
     const Layer& L = P.L[layer_id];
@@ -454,14 +456,11 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
         abort();
     }
     if (++c.call_idx >= P.nseq) c.call_idx = 0;
-    (void)img_g;
+    (void)img_g; (void)call_idx; (void)desc_cur;
 #else
-    // block-wide counters (shared memory): call index, descriptor slot
-    int* ctl = reinterpret_cast<int*>(SQ_SM + P.sm.Ctl);
-    int call_idx = ctl[CTL_CALL];
-    const int desc_cur = ctl[CTL_DESC];
     if (++call_idx >= P.nseq) call_idx = 0;
-    // the descriptor of this call was staged in shared memory during the previous call; start fetching the next one
+    // the descriptor of this call was staged in shared memory during the previous call (before that call's block
+    // barrier, so it is visible even if the cluster barrier of that call is still open); start fetching the next one
     const Layer& L = *reinterpret_cast<const Layer*>(SQ_SM + P.sm.Desc + desc_cur * DESC_WORDS);
     float next_desc_word = 0.f;
     if (c.tid() < DESC_WORDS) next_desc_word = SQ_LDG(prm + P.ltab_off + (int)P.seq[call_idx] * DESC_WORDS + c.tid());
@@ -487,12 +486,14 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
 #endif
     float* red = SQ_SM + P.sm.Red;
     int ks = 1;
+    bool waited = !(flags & 1);                  // false: the previous call's cluster barrier is still open
 #ifdef SQAIR_HOST_EMU
     std::vector<float> redv;
 #endif
     if (work) {
         const float* panel = panel_ptr(L, prm, c.rank());
 #ifdef SQAIR_HOST_EMU
+        if (!waited) { cluster_wait(c); waited = true; }
         // one sequential thread: plain fp32 dot products over the same fragment-ordered panel and segment table
         redv.assign((size_t)Nc * R, 0.f);
         for (int col = 0; col < Nc; ++col)
@@ -528,8 +529,9 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
 #endif
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             const float4* wp = reinterpret_cast<const float4*>(panel) + ((size_t)mt * ksteps + k0) * 64 + lane;
-            if (L.seg[0].kind == SEG_IMAGE) mma_unit<R, true>(L, wp, k0, k1, slot, img_g, lane, acc);
-            else mma_unit<R, false>(L, wp, k0, k1, slot, img_g, lane, acc);
+            if (L.seg[0].kind == SEG_IMAGE) mma_unit<R, true>(L, wp, k0, k1, slot, img_g, lane, acc, !waited);
+            else mma_unit<R, false>(L, wp, k0, k1, slot, img_g, lane, acc, !waited);
+            waited = true;
             // C fragment: acc[0] = (col g, row 2t), acc[1] = (g, 2t+1), acc[2] = (g+8, 2t), acc[3] = (g+8, 2t+1)
             float* rp = red + ((size_t)sl * Nc + mt * 16 + g) * R;
             if (2 * t < R) { rp[2 * t] = acc[0]; rp[8 * R + 2 * t] = acc[2]; }
@@ -538,6 +540,10 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
         SQ_TICK(c, 1);
 #endif
     }
+    if (!waited) cluster_wait(c);                // warps without a unit in this layer (and the emulator)
+#ifndef SQAIR_HOST_EMU
+    if (c.tid() < DESC_WORDS) SQ_SM[P.sm.Desc + (desc_cur ^ 1) * DESC_WORDS + c.tid()] = next_desc_word;
+#endif
     c.sync();
     SQ_TICK(c, 2);
 #ifdef SQAIR_SAFE_EXCHANGE
@@ -563,15 +569,17 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
             }
         }
     }
-#ifndef SQAIR_HOST_EMU
-    if (c.tid() < DESC_WORDS) SQ_SM[P.sm.Desc + (desc_cur ^ 1) * DESC_WORDS + c.tid()] = next_desc_word;
-    if (c.tid() == 0) {      // every thread computed the same values; readers are behind the barrier that follows
-        ctl[CTL_CALL] = call_idx; ctl[CTL_DESC] = desc_cur ^ 1;
-    }
-#endif
     SQ_TICK(c, 3);
-    if (exchange) { cluster_arrive(c); cluster_wait(c); }     // phase B: all slices have landed everywhere
-    else c.sync();
+    bool deferred = false;
+    if (exchange) {                              // phase B: all slices have landed everywhere
+        cluster_arrive(c);
+#ifndef SQAIR_SAFE_EXCHANGE
+        deferred = (flags & 2) != 0;
+#endif
+        if (!deferred) cluster_wait(c);
+    } else {
+        c.sync();
+    }
     SQ_TICK(c, 4);
 #if defined(SQAIR_PROFILE) && !defined(SQAIR_HOST_EMU)
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -580,6 +588,7 @@ SQ_DEVNI void dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
         g_trace_last = t_exit;
     }
 #endif
+    return deferred;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -604,6 +613,8 @@ struct Block {
     const float* eps_what_;
     const float* u_pres_;
     int dbg_;
+    mutable int call_idx_, desc_cur_;    // position in Plan::seq / descriptor slot of the next dense call
+    mutable bool pend_;                  // the last dense call left its cluster barrier open
     int row0;                       // first global row of this block
     const float* imgrow[R];         // frame of each row for the current t
     const float* img_g;             // frame of the row this lane feeds to the MMA B fragment (row min(lane / 4, R - 1))
@@ -614,6 +625,7 @@ struct Block {
 #else
     SQ_DEV Block(Ctx& c_, const Job& J_, int row0_) : c(c_), J(J_), row0(row0_) {
 #endif
+        call_idx_ = 0; desc_cur_ = 0; pend_ = false;
         prm_ = J_.prm; obs_ = J_.obs; eps_where_ = J_.eps_where; eps_what_ = J_.eps_what; u_pres_ = J_.u_pres; dbg_ = J_.debug_flags;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -632,13 +644,18 @@ struct Block {
     SQ_DEV float& lp(int k, int s, int r) const { return SQ_SM[P.sm.Lp + k * LDS() + s * R + r]; }
     SQ_DEV float& rowacc(int k, int r) const { return SQ_SM[P.sm.RowAcc + k * R + r]; }
     SQ_DEV float prm(int off) const { return SQ_LDG(prm_ + off); }
-    SQ_DEV void lin(int id, int slot = 0) const {
+    // `next_is_dense`: nothing but another lin() follows (no element-wise stage reads or writes shared memory in
+    // between), so the cluster barrier of this call may be completed inside the next one, behind its first weight loads
+    SQ_DEV void lin(int id, int slot = 0, bool next_is_dense = false) const {
         if (dbg_ & 64) return;
+        const int flags = (pend_ ? 1 : 0) | (next_is_dense ? 2 : 0);
 #ifdef SQAIR_HOST_EMU
-        dense<R>(c, prm_, id, slot, imgrow, img_g, dbg_);
+        pend_ = dense<R>(c, prm_, id, slot, imgrow, img_g, dbg_, flags, call_idx_, desc_cur_);
 #else
-        dense<R>(c, prm_, id, slot, nullptr, img_g, dbg_);      // passing the array would pin imgrow[] to local memory
+        pend_ = dense<R>(c, prm_, id, slot, nullptr, img_g, dbg_, flags, call_idx_, desc_cur_);   // (passing imgrow would pin it to local memory)
 #endif
+        if (++call_idx_ >= P.nseq) call_idx_ = 0;
+        desc_cur_ ^= 1;
     }
     SQ_DEV size_t nidx(int t, int r, int slot2) const {      // noise index of (t, row, slot in [0,2n))
         return ((size_t)t * P.rows + grow_of(r)) * (2 * P.NS) + slot2;
@@ -720,8 +737,8 @@ struct Block {
         SQ_SM[m.Coords + 2 * R + r] = tanhf(w2);
         SQ_SM[m.Coords + 3 * R + r] = tanhf(w3);
     }
-    SQ_DEV void encode_glimpse(int last_layer) const {
-        lin(L_ENC1); lin(L_ENC2); lin(last_layer);
+    SQ_DEV void encode_glimpse(int last_layer, bool next_is_dense = false) const {
+        lin(L_ENC1, 0, true); lin(L_ENC2, 0, true); lin(last_layer, 0, next_is_dense);
     }
     // snt.GRU gate algebra (Appendix B) around the two dense calls: Gr <- r*h, then state update.
     SQ_DEV void gru_mul_r(int state_off, int s) const {
@@ -783,17 +800,17 @@ struct Block {
         const bool masked = P.cfg.masked_glimpse != 0;
         prop_prior(s);
         // where_bias MLP and glimpse mask MLP on the slot's temporal state (core.py:291; modules.py:350-356)
-        lin(L_WBMK1, s);
-        lin(L_WB2);
+        lin(L_WBMK1, s, true);
+        lin(L_WB2, 0, masked);
         if (masked) lin(L_MK2);
         for (int r = c.tid(); r < R; r += c.nthreads())
             set_coords(Z(nw + 0, s, r) + SQ_SM[m.Wb + 0 * R + r], Z(nw + 1, s, r) + SQ_SM[m.Wb + 1 * R + r],
                        Z(nw + 2, s, r) + SQ_SM[m.Wb + 2 * R + r], Z(nw + 3, s, r) + SQ_SM[m.Wb + 3 * R + r], r);
         c.sync();
         extract_glimpse(masked);
-        encode_glimpse(L_ENC3_LOC);                               // -> Loc1 (core.py:292-293)
-        lin(L_PRNN, s);                                           // core.py:295-302 -> Hrnn[1]
-        lin(L_PT1, s); lin(L_PT2); lin(L_PT3);                    // core.py:323-324 -> Tp
+        encode_glimpse(L_ENC3_LOC, true);                         // -> Loc1 (core.py:292-293)
+        lin(L_PRNN, s, true);                                     // core.py:295-302 -> Hrnn[1]
+        lin(L_PT1, s, true); lin(L_PT2, 0, true); lin(L_PT3);     // core.py:323-324 -> Tp
         // where ~ MVN_TriL(where_tm1 + us*loc, L) (core.py:326-330; modules.py:535-545)
         for (int r = c.tid(); r < R; r += c.nthreads()) {
             float loc[4], sc[4], eps[4], L[4][4], wh[4];
@@ -844,7 +861,7 @@ struct Block {
             rec(m.PropOut, e, F.what_scale + j, r) = ws;
         }
         c.sync();
-        lin(L_PST1, s); lin(L_PST2);                              // modules.py:506-513
+        lin(L_PST1, s, true); lin(L_PST2);                        // modules.py:506-513
         for (int r = c.tid(); r < R; r += c.nthreads()) {             // core.py:141-144
             const float ptm1 = Z(nw + 4, s, r);
             float logit = ptm1 * SQ_SM[m.Lg + r] + (ptm1 - 1.f) * 88.f;
@@ -933,8 +950,8 @@ struct Block {
         const Smem& m = P.sm;
         const RecF& F = P.rec;
         const int nh = P.nh, nw = P.nw, e = s + 1, ns2 = P.NS + s;
-        lin(L_DRNN, s);
-        lin(L_DT1); lin(L_DT2); lin(L_DT3);
+        lin(L_DRNN, s, true);
+        lin(L_DT1, 0, true); lin(L_DT2, 0, true); lin(L_DT3);
         for (int r = c.tid(); r < R; r += c.nthreads()) {             // core.py:220-227
             const float so = prm(P.po.d_scale_offset);
             float wh[4];
@@ -963,7 +980,7 @@ struct Block {
             rec(m.DiscOut, e, F.what_scale + j, r) = ws;
         }
         c.sync();
-        lin(L_DST1, s); lin(L_DST2);
+        lin(L_DST1, s, true); lin(L_DST2);
         for (int r = c.tid(); r < R; r += c.nthreads()) {
             const float pkm1 = rec(m.DiscOut, s, F.pres, r);      // entry 0 holds the initial 1 (core.py:153)
             float logit = pkm1 * SQ_SM[m.Lg + r] + (pkm1 - 1.f) * 88.f;
@@ -1014,7 +1031,7 @@ struct Block {
             c.sync();
             lin(L_RN1);
             for (int s = 0; s < NS; ++s) {
-                lin(L_RN2, s); lin(L_RN3);
+                lin(L_RN2, s, true); lin(L_RN3);
                 for (int r = c.tid(); r < R; r += c.nthreads()) {
                     float a = 0.f;
 #pragma unroll
@@ -1036,7 +1053,7 @@ struct Block {
             }
             c.sync();
         }
-        if (P.cfg.disc_prior_type == SQAIR_DISC_PRIOR_CAT) { lin(L_SP1); lin(L_SP2); }
+        if (P.cfg.disc_prior_type == SQAIR_DISC_PRIOR_CAT) { lin(L_SP1, 0, true); lin(L_SP2); }
         for (int r = c.tid(); r < R; r += c.nthreads()) {
             const int num = (int)rowacc(RA_NDISC, r);
             // p(N): Categorical(elu(bias + (t>0) tbias + MLP(E[n_prop]))) (sqair_modules.py:208-221)
@@ -1169,7 +1186,7 @@ struct Block {
         const int NS = P.NS, nw = P.nw, G = P.cfg.G, W = P.cfg.W, H = P.cfg.H, g = P.g, PX = P.PX;
         const sqair_outputs& o = J.out;
         const size_t trow = (size_t)t * P.rows;
-        for (int s = 0; s < NS; ++s) { lin(L_DEC1, s); lin(L_DEC2); lin(L_DEC3, s); }
+        for (int s = 0; s < NS; ++s) { lin(L_DEC1, s, true); lin(L_DEC2, 0, true); lin(L_DEC3, s, s + 1 < NS); }
         if (o.glimpse && c.rank() == 0)
             for (int i = c.tid(); i < R * NS * g; i += c.nthreads()) {
                 const int px = i % g, s = (i / g) % NS, r = i / (g * NS);
@@ -1353,7 +1370,7 @@ struct Block {
         for (int s = 0; s < NS; ++s) prop_slot(t, s);
         // latent summary: sum_s pres_s * MLP([what_s, where_s]) (sqair_modules.py:368-385,501)
         for (int s = 0; s < NS; ++s) {
-            lin(L_LAT1, s); lin(L_LAT2);
+            lin(L_LAT1, s, true); lin(L_LAT2);
             for (int i = c.tid(); i < nh * R; i += c.nthreads())
                 SQ_SM[m.DIn + nh * R + i] += SQ_SM[m.A1 + i] * rec(m.PropOut, s + 1, P.rec.pres, i % R);
             c.sync();
@@ -1363,7 +1380,7 @@ struct Block {
             for (int s = 0; s < NS; ++s) a += (sigmoidf_(pri(0, s, r)) - 0.5f) / (float)NS;
             SQ_SM[m.Exp + r] = a;
         }
-        lin(L_IMG1); lin(L_IMG2);                                    // core.py:165, hoisted out of the slot loop
+        lin(L_IMG1, 0, true); lin(L_IMG2);                           // core.py:165, hoisted out of the slot loop
         for (int i = c.tid(); i < nh * R; i += c.nthreads()) SQ_SM[m.Hrnn + i] = prm(P.po.disc_h0 + i / R);
         c.sync();
         for (int s = 0; s < NS; ++s) disc_slot(t, s);
