@@ -148,6 +148,12 @@ int sqair_objective_grad(const float* log_w_t, const float* disc_lp_t, int32_t T
 int sqair_wgrad(const float* x, const float* dy, float* dw, int32_t M, int32_t K, int32_t N, int32_t accumulate,
                 void* stream);
 
+/* Input gradient of one dense layer, the other GEMM of the backward pass: dX [M,K] = dY [M,N] . W^T for the layer's
+ * weight matrix W [K,N] in the reference's own (canonical, row-major) layout.  Same fp32-faithful tensor-core
+ * arithmetic as sqair_wgrad.  (The fused backward kernel will do this product on transposed fragment panels inside
+ * the cluster; this entry point is its unit-parity reference and the building block of an unfused backward.) */
+int sqair_dgrad(const float* dy, const float* w, float* dx, int32_t M, int32_t K, int32_t N, void* stream);
+
 /* Per-op entry points (unit parity / roofline of the bandwidth-shaped pieces).
  * sqair_stn_glimpse: SpatialTransformer forward (modules.py:165-172,204-218): img [N,H,W],
  *   where-logits [N,4] -> glimpse [N,G,G].

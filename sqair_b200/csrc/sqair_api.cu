@@ -641,6 +641,72 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const float* __restrict__ X,
             }
 }
 
+// Input gradient dX[M,K] = dY[M,N] . W[K,N]^T.  Block tile 64 (M) x 64 (K), 4 warps of 32 x 32, N walked in chunks of 32
+// staged in shared memory (row stride 36 floats: conflict-free fragment reads); arithmetic as in wgrad_kernel.
+constexpr int DG_T = 64, DG_NC = 32, DG_LD = 36;
+__global__ void __launch_bounds__(128) dgrad_kernel(const float* __restrict__ dY, const float* __restrict__ Wm, float* __restrict__ dX,
+                                                    int M, int K, int N) {
+    __shared__ float As[DG_T * DG_LD], Bs[DG_T * DG_LD];
+    const int k0 = blockIdx.x * DG_T, m0 = blockIdx.y * DG_T;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int wm = (warp >> 1) * 32, wk = (warp & 1) * 32;
+    float acc[2][4][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[a][b][q] = 0.f;
+    for (int n0 = 0; n0 < N; n0 += DG_NC) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < DG_T * DG_NC; i += blockDim.x) {     // zero-filled edges
+            const int rr = i / DG_NC, cc = i - rr * DG_NC;
+            As[rr * DG_LD + cc] = (m0 + rr < M && n0 + cc < N) ? __ldg(dY + (size_t)(m0 + rr) * N + n0 + cc) : 0.f;
+            Bs[rr * DG_LD + cc] = (k0 + rr < K && n0 + cc < N) ? __ldg(Wm + (size_t)(k0 + rr) * N + n0 + cc) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ns = 0; ns < DG_NC; ns += 8) {
+            uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {       // A = dY: element (row m, col n)
+                const float* p = As + (wm + a * 16 + g) * DG_LD + ns + t;
+                split_tf32(p[0], ah[a][0], al[a][0]);
+                split_tf32(p[8 * DG_LD], ah[a][1], al[a][1]);
+                split_tf32(p[4], ah[a][2], al[a][2]);
+                split_tf32(p[8 * DG_LD + 4], ah[a][3], al[a][3]);
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {       // B = W^T: element (row n, col k) = Bs[k][n]
+                const float* p = Bs + (wk + b * 8 + g) * DG_LD + ns + t;
+                split_tf32(p[0], bh[b][0], bl[b][0]);
+                split_tf32(p[4], bh[b][1], bl[b][1]);
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    float d[4];
+                    mma_tf32_zero(d, al[a], bl[b][0], bl[b][1]);
+                    mma_tf32(d, al[a], bh[b][0], bh[b][1]);
+                    mma_tf32(d, ah[a], bl[b][0], bl[b][1]);
+                    mma_tf32(d, ah[a], bh[b][0], bh[b][1]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[a][b][q] += d[q];
+                }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int m = m0 + wm + a * 16 + g + (q >> 1) * 8, k = k0 + wk + b * 8 + 2 * t + (q & 1);
+                if (m < M && k < K) dX[(size_t)m * K + k] = acc[a][b][q];
+            }
+}
+
 // bilinear sample with zero padding plus its derivatives w.r.t. the sample position; `w4`/`idx4` receive the four texel
 // weights / linear indices (-1 = outside) for the scatter of the data gradient.
 struct Bilin {
@@ -955,6 +1021,13 @@ int sqair_wgrad(const float* x, const float* dy, float* dw, int32_t M, int32_t K
     const int atomic = (msplit > 1 || accumulate) ? 1 : 0;
     if (atomic && !accumulate) CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)K * N * sizeof(float), st));
     wgrad_kernel<<<dim3((N + WG_T - 1) / WG_T, (K + WG_T - 1) / WG_T, msplit), 128, 0, st>>>(x, dy, dw, M, K, N, m_per_block, atomic);
+    CUDA_TRY(cudaGetLastError());
+    return SQAIR_OK;
+}
+
+int sqair_dgrad(const float* dy, const float* w, float* dx, int32_t M, int32_t K, int32_t N, void* stream) {
+    if (!dy || !w || !dx || M < 1 || K < 1 || N < 1) return fail(SQAIR_EINVAL, "bad argument");
+    dgrad_kernel<<<dim3((K + DG_T - 1) / DG_T, (M + DG_T - 1) / DG_T), 128, 0, (cudaStream_t)stream>>>(dy, w, dx, M, K, N);
     CUDA_TRY(cudaGetLastError());
     return SQAIR_OK;
 }

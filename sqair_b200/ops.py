@@ -169,3 +169,15 @@ def wgrad(x: torch.Tensor, dy: torch.Tensor, out: torch.Tensor = None) -> torch.
         _need_cuda(out)
     check(_capi.lib().sqair_wgrad(_ptr(x), _ptr(dy), _ptr(out), M, K, N, int(acc), _stream()))
     return out
+
+
+def dgrad(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """Input gradient of a dense layer: dy [M,N], w [K,N] (the reference's variable layout) -> dy w^T [M,K]."""
+    _need_cuda(dy, w)
+    M, N = dy.shape
+    K = w.shape[0]
+    if w.shape[1] != N:
+        raise ValueError('dy and w must have the same number of columns')
+    out = torch.empty(M, K, dtype=torch.float32, device=dy.device)
+    check(_capi.lib().sqair_dgrad(_ptr(dy), _ptr(w), _ptr(out), M, K, N, _stream()))
+    return out

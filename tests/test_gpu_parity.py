@@ -289,3 +289,15 @@ def test_wgrad_op(M, K, N):
     base = torch.from_numpy(rng.standard_normal((K, N)).astype(np.float32)).to(dev)
     got2 = ops.wgrad(torch.from_numpy(x).to(dev), torch.from_numpy(dy).to(dev), out=base.clone()).cpu().numpy()
     np.testing.assert_allclose(got2, want + base.cpu().numpy().astype(np.float64), rtol=1e-5, atol=2e-6 * scale + 1e-6)
+
+
+@pytest.mark.parametrize('M,K,N', [(6400, 672, 256), (1600, 264, 109), (37, 5, 3), (640, 400, 256)])
+def test_dgrad_op(M, K, N):
+    """Input-gradient GEMM of the backward pass (dy w^T, same split tensor-core arithmetic) against float64."""
+    ops, dev = _gpu()
+    rng = np.random.default_rng(7)
+    dy = (rng.standard_normal((M, N)) * 0.1).astype(np.float32)
+    w = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    want = dy.astype(np.float64) @ w.astype(np.float64).T
+    got = ops.dgrad(torch.from_numpy(dy).to(dev), torch.from_numpy(w).to(dev)).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-6 * np.sqrt(N) * 0.1 / np.sqrt(K))
