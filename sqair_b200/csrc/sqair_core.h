@@ -129,7 +129,7 @@ struct RecF {
 
 // Shared-memory layout (float offsets from the dynamic shared memory base).  [f][S][R] = feature-major.
 struct Smem {
-    int Ctl;      // [16] ints: call counters shared by the block (device only)
+    int Ctl;      // [16] ints: reserved (the call counters moved to registers)
     int Desc;     // [2][DESC_WORDS] staged descriptors of the current / next dense call
     int Z;        // [nw+6][NS][R]: what, where(4), pres, plogit     (latents of the previous frame)
     int Ids;      // [NS][R]

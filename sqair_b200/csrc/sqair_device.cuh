@@ -54,7 +54,7 @@ struct EmuClusterBarrier {
 #endif
 
 // Per-thread view of the block: indices, shared memory, position in the cluster and the state of
-// the weight ring (identical in all threads of a block; advanced deterministically).
+// the call sequence (identical in all threads of a block; advanced deterministically).
 struct Ctx {
 #ifdef SQAIR_HOST_EMU
     int tid_, nthreads_, lane_, nlanes_, warp_, nwarps_, ncompute_, rank_, ncta_;
@@ -85,9 +85,8 @@ struct Ctx {
     SQ_DEV int rank() const { uint32_t r; asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return (int)r; }
     SQ_DEV int ncta() const { uint32_t r; asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return (int)r; }
 #endif
-    // Call counters.  Host emulation keeps them here; on the device they live in the shared-memory words
-    // Smem::Ctl (CTL_*), read once per dense call and written back by one thread, so that dense() never
-    // touches local memory.
+    // Host emulation only: position in Plan::seq (checked against the layer id of every dense call).  On the device the
+    // position and the descriptor slot live in registers of the per-block program (Block::call_idx_, desc_cur_).
     int call_idx;            // dense calls executed in the current frame
 #if defined(SQAIR_PROFILE)
     long long prof[8];       // cycle counters
