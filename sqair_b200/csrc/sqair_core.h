@@ -424,7 +424,7 @@ struct PlanBuilder {
             }
         }
         int per = (l.Ntot + C - 1) / C;
-        if (C > 1 && per >= 16) {
+        if (C > 1 && per >= 8) {          // at least half an m16 tile of real columns per block
             l.split = 1;
             l.Nc = round_up(per, 16);
             l.npanel = (l.Ntot + l.Nc - 1) / l.Nc;
