@@ -140,7 +140,7 @@ static std::string choose_shape_uncached(const sqair_cfg& c, const std::vector<P
 // environment variables, so the last few results are cached (building ~25 candidate plans costs ~1 ms of host time).
 struct ShapeKey {
     sqair_cfg cfg;
-    int env[3];
+    int env[5];
     bool operator==(const ShapeKey& o) const { return memcmp(this, &o, sizeof(ShapeKey)) == 0; }
 };
 static std::mutex g_shape_mutex;
@@ -151,6 +151,7 @@ static std::string choose_shape(const sqair_cfg& c, const std::vector<ParamEntry
     memset(&key, 0, sizeof(key));
     key.cfg = c;
     key.env[0] = env_int("SQAIR_ROWS_PER_CTA"); key.env[1] = env_int("SQAIR_CLUSTER"); key.env[2] = env_int("SQAIR_NO_FRAME_STAGING");
+    key.env[3] = env_int("SQAIR_UNIT_COST"); key.env[4] = env_int("SQAIR_SLICE_COST");
     std::lock_guard<std::mutex> lock(g_shape_mutex);
     for (auto& kv : g_shape_cache)
         if (kv.first == key) { out = *kv.second; return ""; }
@@ -187,7 +188,10 @@ static std::string choose_shape_uncached(const sqair_cfg& c, const std::vector<P
             Shape s;
             bool ok = false;
             for (int stage = env_int("SQAIR_NO_FRAME_STAGING") ? 0 : 1; stage >= 0 && !ok; --stage) {   // frames in shared memory if they fit
-                std::string e = build_plan(c, R, C, s.plan, tab, s.pieces, &s.packed_total, stage != 0);
+                // SQAIR_UNIT_COST / SQAIR_SLICE_COST (tenths of a k-step): k-slicing cost model overrides for tuning sweeps
+                const double uc = env_int("SQAIR_UNIT_COST") ? env_int("SQAIR_UNIT_COST") * 0.1 : 3.0;
+                const double sc = env_int("SQAIR_SLICE_COST") ? env_int("SQAIR_SLICE_COST") * 0.1 : 0.5;
+                std::string e = build_plan(c, R, C, s.plan, tab, s.pieces, &s.packed_total, stage != 0, uc, sc);
                 if (!e.empty()) { err = e; break; }
                 ok = s.plan.sm.total * (int)sizeof(float) <= kSmemLimit;
             }

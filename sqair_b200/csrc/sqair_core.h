@@ -319,6 +319,7 @@ inline int64_t vars_floats(const std::vector<ParamEntry>& v) {
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct PlanBuilder {
+    double unit_cost = 3.0, slice_cost = 0.5;     // k-slicing cost model (in k-steps): start-up of a work unit, one more partial sum
     Plan& p;
     const std::vector<ParamEntry>& tab;
     std::vector<Piece>& pieces;
@@ -449,7 +450,7 @@ struct PlanBuilder {
             const int kper = (l.ksteps + ks - 1) / ks;
             if (ks > 1 && (kper < 2 || (ks - 1) * kper >= l.ksteps)) continue;
             const int rounds = (l.nmt * ks + NWARP - 1) / NWARP;
-            const double cost = (double)rounds * (kper + 3) + 0.5 * ks;
+            const double cost = (double)rounds * (kper + unit_cost) + slice_cost * ks;
             if (cost < best_cost) { best_cost = cost; best = ks; }
         }
         l.ksplit = best;
@@ -483,7 +484,8 @@ inline std::vector<int> frame_sequence(const sqair_cfg& c) {
 // Builds the plan for R rows per cluster of C blocks.  Returns "" on success, else an error message.
 // `pieces` receives the packing table; *packed_total the floats of the packed parameter buffer.
 inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const std::vector<ParamEntry>& tab,
-                              std::vector<Piece>& pieces, int64_t* packed_total, bool stage_frame = true) {
+                              std::vector<Piece>& pieces, int64_t* packed_total, bool stage_frame = true,
+                              double unit_cost = 3.0, double slice_cost = 0.5) {
     memset((void*)&p, 0, sizeof(p));
     pieces.clear();
     p.cfg = c;
@@ -495,6 +497,7 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
     rf.size = 3 * nw + 15;
 
     PlanBuilder B(p, tab, pieces);
+    B.unit_cost = unit_cost; B.slice_cost = slice_cost;
     Smem& m = p.sm;
     if (R < 1 || R > MAXR) return "rows per block must be in [1, 8]";
     const int LDS = NS * R, LDE = (NS + 1) * R;
