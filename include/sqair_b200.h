@@ -8,7 +8,8 @@
  * reference would add is shown in INTEGRATION.md.
  *
  * Conventions: every pointer is a DEVICE pointer owned by the caller unless the name says `host`;
- * the library never allocates device memory; all work is enqueued on `stream` (a cudaStream_t passed
+ * the library never allocates device memory (except one small per-configuration descriptor table that it caches for the
+ * process lifetime); all work is enqueued on `stream` (a cudaStream_t passed
  * as void*; NULL = legacy default stream) and is asynchronous.  Functions return 0 on success or a
  * negative code; `sqair_last_error()` returns a thread-local message for the last failure.
  * All tensors are fp32, C-contiguous.
@@ -140,6 +141,35 @@ int sqair_objective(const float* log_w_t, const float* disc_lp_t, int32_t T, int
  * Either output may be NULL. */
 int sqair_objective_grad(const float* log_w_t, const float* disc_lp_t, int32_t T, int32_t B, int32_t K,
                          float* d_log_weights, float* d_discrete_log_prob, void* stream);
+
+/* ---- training step: forward with stash, backward, gradient in the reference's variable layout -------------------
+ * Stand-in for `opt.compute_gradients(target)` of Model.make_target (sqair/model.py:150-168): TF differentiates the
+ * whole graph of seq.py:181-276; here the forward kernel additionally writes every activation the adjoint needs into a
+ * caller-owned `stash`, and sqair_backward walks the frames in reverse.  Sizes: */
+typedef struct sqair_train_sizes {
+    int64_t stash_floats;            /* activations written by sqair_forward_train, read by sqair_backward     */
+    int64_t workspace_floats;        /* scratch of sqair_backward (per-layer output gradients, state adjoints)   */
+    int64_t backward_param_floats;   /* parameter copy in the layout of the backward GEMMs (sqair_pack_backward) */
+} sqair_train_sizes;
+int sqair_query_train_sizes(const sqair_cfg* cfg, sqair_train_sizes* out);
+
+/* sqair_forward that also fills `stash` (stash_floats floats).  Same outputs, same arithmetic. */
+int sqair_forward_train(const sqair_cfg* cfg, const float* packed_params, const float* obs,
+                        const float* eps_where, const float* eps_what, const float* u_pres,
+                        const sqair_outputs* out, float* stash, void* stream);
+
+/* canonical flat parameters -> backward parameter buffer (once per parameter update, like sqair_pack_params). */
+int sqair_pack_backward(const sqair_cfg* cfg, const float* params, float* bw_params, void* stream);
+
+/* Gradient of the training target w.r.t. every variable of sqair_param_layout (canonical flat layout, overwritten).
+ * d_log_weights / d_discrete_log_prob: [B*K] from sqair_objective_grad (d_discrete_log_prob may be NULL = zeros: the
+ * `-elbo_iwae` target of model.py:156).  `params` is the canonical flat buffer the packed copies were made from; obs and
+ * the noise tensors are the ones the forward call consumed.  *n_launches (nullable) receives the number of kernels and
+ * memsets enqueued.  Asynchronous on `stream`; capturable in a CUDA graph after one warm-up call. */
+int sqair_backward(const sqair_cfg* cfg, const float* params, const float* bw_params, const float* obs,
+                   const float* eps_where, const float* eps_what, const float* stash,
+                   const float* d_log_weights, const float* d_discrete_log_prob,
+                   float* workspace, float* d_params, int32_t* n_launches, void* stream);
 
 /* Weight gradient of one dense layer (the GEMM-shaped part of the backward pass): dW [K,N] (+)= X^T dY for
  * the stashed layer inputs X [M,K] and output gradients dY [M,N], M = rows x frames x slots, all row-major fp32.

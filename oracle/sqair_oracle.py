@@ -53,6 +53,7 @@ class Cfg:
     step_success_prob: float = 0.75
     prop_prior_step_bias: float = 10.0
     output_std: float = 0.3
+    bg_std: float = None            # modules.py:406-407: None -> output_std
     where_update_scale: float = 1.0
     min_std: float = 1e-2
     where_mean: tuple = (-2., -2., 0., 0.)   # only used when rec_where_prior is False
@@ -268,6 +269,11 @@ def bernoulli_log_prob(x, logits):
 # --------------------------------------------------------------------------------------------
 # spatial transformer (modules.py:150-227) -- snt.AffineGridWarper + tf.contrib.resampler
 # --------------------------------------------------------------------------------------------
+def clip_preserve(x, lo, hi):
+    """ops.py:33-42: clipped value, identity gradient (stop_gradient(clipped - x) + x)."""
+    return x + (x.clamp(lo, hi) - x).detach()
+
+
 def to_coords(logits):
     """modules.py:220-227: (scale, shift) = (sigmoid(l[:2]), tanh(l[2:]))."""
     return torch.cat((torch.sigmoid(logits[..., :2]), torch.tanh(logits[..., 2:])), -1)
@@ -298,7 +304,7 @@ def stn_forward(img, coords, G):
     glimpse [N,G,G].  x_pix = (W-1)/2 (sx u + tx) + (W-1)/2, u in linspace(-1,1,G)."""
     N, H, W = img.shape
     sx, sy, tx, ty = coords.unbind(-1)
-    sx, sy = sx.clamp(min=1e-4), sy.clamp(min=1e-4)           # clip_preserve, ops.py:33-42
+    sx, sy = clip_preserve(sx, 1e-4, None), clip_preserve(sy, 1e-4, None)      # modules.py:206; ops.py:33-42
     lin = torch.linspace(-1., 1., G, dtype=img.dtype)
     xs = (W - 1) / 2. * (sx[:, None] * lin[None] + tx[:, None]) + (W - 1) / 2.       # [N,G]
     ys = (H - 1) / 2. * (sy[:, None] * lin[None] + ty[:, None]) + (H - 1) / 2.
@@ -312,7 +318,7 @@ def stn_inverse(glimpse, coords, H, W):
     x_g = (G-1)/2 ((u - tx)/sx) + (G-1)/2 for u in linspace(-1,1,W)."""
     N, G, _ = glimpse.shape
     sx, sy, tx, ty = coords.unbind(-1)
-    sx, sy = sx.clamp(min=1e-4), sy.clamp(min=1e-4)
+    sx, sy = clip_preserve(sx, 1e-4, None), clip_preserve(sy, 1e-4, None)
     lx = torch.linspace(-1., 1., W, dtype=glimpse.dtype)
     ly = torch.linspace(-1., 1., H, dtype=glimpse.dtype)
     xs = (G - 1) / 2. * ((lx[None] - tx[:, None]) / sx[:, None]) + (G - 1) / 2.       # [N,W]
@@ -395,12 +401,13 @@ def affine_diag_normal_tril(p, scale):
 def mvn_tril_log_prob(x, loc, L):
     """tfd.MultivariateNormalTriL.log_prob, d = 4."""
     d = (x - loc)
-    y = torch.zeros_like(d)
+    ys = []
     for i in range(4):                                 # forward substitution L y = d
         acc = d[..., i]
         for j in range(i):
-            acc = acc - L[..., i, j] * y[..., j]
-        y[..., i] = acc / L[..., i, i]
+            acc = acc - L[..., i, j] * ys[j]
+        ys.append(acc / L[..., i, i])
+    y = torch.stack(ys, -1)
     logdet = torch.log(torch.abs(torch.diagonal(L, dim1=-2, dim2=-1))).sum(-1)
     return -0.5 * (y ** 2).sum(-1) - logdet - 2. * LOG_2PI
 
@@ -443,7 +450,7 @@ def propagation_core_step(p, cfg, img, z_tm1_k, temporal_state, state, eps_where
     # presence (core.py:141-144,311-313)
     logit = steps_predictor(p, _PC, pres_tm1, torch.cat((h, temporal_state, what), -1))
     prob = torch.sigmoid(logit)
-    pres = (u_pres[:, None] < prob).float() * pres_tm1
+    pres = (u_pres[:, None] < prob).to(prob.dtype) * pres_tm1
     out = dict(what=what, what_loc=what_loc, what_scale=what_scale, where=where, where_loc=where_loc,
                where_scale=where_scale, presence_prob=prob, presence=pres, presence_logit=logit,
                temporal_state=new_temporal)
@@ -519,7 +526,7 @@ def discovery_core_step(p, cfg, img, conditioning, state, eps_where, eps_what, u
     what = what_loc + what_scale * eps_what
     logit = steps_predictor(p, _DC, pres_km1, torch.cat((h, what), -1))
     prob = torch.sigmoid(logit)
-    pres = (u_pres[:, None] < prob).float() * pres_km1
+    pres = (u_pres[:, None] < prob).to(prob.dtype) * pres_km1
     out = dict(what=what, what_loc=what_loc, what_scale=what_scale, where=where, where_loc=where_loc,
                where_scale=where_scale, presence_prob=prob, presence=pres, presence_logit=logit)
     return out, (what, where, pres, h)
@@ -532,7 +539,7 @@ def bernoulli_to_modified_geometric(presence_prob):
     prob = torch.cumprod(pp, -1)                                                       # prior.py:34-58
     mod = torch.cat((inv[..., :1], inv[..., 1:] * prob[..., :-1], prob[..., -1:]), -1)
     mod = mod / mod.sum(-1, keepdim=True)
-    return mod.float()
+    return mod.to(presence_prob.dtype)          # float32 in the reference (prior.py:67)
 
 
 def recurrent_normal_log_prob(p, cfg, samples, conditioning):
@@ -571,14 +578,15 @@ def discover(p, cfg, img, conditioning, time_step, prior_conditioning, eps_where
     q_where = normal_log_prob(ho['where'], ho['where_loc'], ho['where_scale']).sum(-1) * pres
     joint = bernoulli_to_modified_geometric(ho['presence_prob'][..., 0])               # [B', n+1]
     idx = num_steps.to(torch.int64)[:, None]
-    q_num = torch.log(joint.gather(1, idx)[:, 0].clamp(1e-16, 1.))                     # prior.py:95-102
+    q_num = torch.log(clip_preserve(joint.gather(1, idx)[:, 0], 1e-16, 1.))            # prior.py:95-102
     # priors (:199-226)
     p_what = normal_log_prob(ho['what'], torch.zeros(()), torch.ones(())).sum(-1) * pres
     if cfg.rec_where_prior:
         where_cond = torch.cat((conditioning, prior_conditioning), -1)                 # :154
         p_where = recurrent_normal_log_prob(p, cfg, ho['where'], where_cond).sum(-1) * pres
     else:
-        p_where = normal_log_prob(ho['where'], torch.tensor(cfg.where_mean), torch.tensor(cfg.where_std)).sum(-1) * pres
+        p_where = normal_log_prob(ho['where'], torch.tensor(cfg.where_mean, dtype=pres.dtype),
+                                  torch.tensor(cfg.where_std, dtype=pres.dtype)).sum(-1) * pres
     if cfg.disc_prior_type == 'cat':
         logits = p['model/sequential_air/while/sqair_timestep/discover/step_prior_bias'] \
             + (0. if time_step == 0 else 1.) * \
@@ -661,7 +669,9 @@ def air_decoder(p, cfg, what, where, presence):
     mask = torch.sigmoid(-10. + nz * 20.)                                              # :462
     canvas = canvas + p['decoder/air_decoder/Variable'][None, :, :, 0] * mask          # :465
     std = float(np.float32(np.sqrt(np.float32(cfg.output_std))) ** 2)                   # :419-422
-    out_std = mask * std + (1. - mask) * std                                            # :453 (bg_std = output_std)
+    bg = cfg.output_std if cfg.bg_std is None else cfg.bg_std                           # :406-407
+    bg = float(np.float32(np.sqrt(np.float32(bg))) ** 2)
+    out_std = mask * std + (1. - mask) * bg                                             # :453
     return canvas, out_std, g.reshape(Bp, n, cfg.G, cfg.G)
 
 
@@ -804,3 +814,19 @@ def model_forward(p, cfg, obs, noise):
     obj['mse'] = iwm(mse)
     obj['raw_mse'] = mse.mean()
     return out, obj
+
+
+# --------------------------------------------------------------------------------------------
+# gradients (model.py:150-168: opt.compute_gradients(target)) -- torch autograd through the restatement
+# --------------------------------------------------------------------------------------------
+def model_gradients(p, cfg, obs, noise, target='auto'):
+    """d target / d every variable, target = VIMCO / T (model.py:152-158; NaN at K = 1, targets.py:55) or the
+    `-elbo_iwae / T` branch (model.py:156).  'auto' = VIMCO when K > 1.  Returns (grads by TF name, objective dict)."""
+    leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in p.items())
+    out, obj = model_forward(leaves, cfg, obs, noise)
+    use_vimco = cfg.K > 1 if target == 'auto' else target == 'vimco'
+    tgt = obj['vimco_target'] if use_vimco else obj['iwae_target']
+    gs = torch.autograd.grad(tgt, list(leaves.values()), allow_unused=True)
+    grads = OrderedDict((k, (torch.zeros_like(v) if g is None else g)) for (k, v), g in zip(leaves.items(), gs))
+    missing = [k for (k, _), g in zip(leaves.items(), gs) if g is None]
+    return grads, {k: v.detach() for k, v in obj.items()}, missing

@@ -42,6 +42,10 @@ class SqairSizes(C.Structure):
                [(k, C.c_int32) for k in 'rows rows_per_cta cluster_size n_ctas smem_bytes n_layers'.split()]
 
 
+class SqairTrainSizes(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in 'stash_floats workspace_floats backward_param_floats'.split()]
+
+
 class SqairParamDesc(C.Structure):
     _fields_ = [('name', C.c_char * 160), ('ndim', C.c_int32), ('shape', C.c_int32 * 3),
                 ('offset', C.c_int64), ('packed_offset', C.c_int64)]
@@ -113,6 +117,10 @@ def bind(lib):
     lib.sqair_pack_params.argtypes = [C.POINTER(SqairCfg), vp, vp, vp]
     lib.sqair_fill_noise.argtypes = [C.POINTER(SqairCfg), C.c_uint64, i32, vp, vp, vp, vp]
     lib.sqair_forward.argtypes = [C.POINTER(SqairCfg), vp, vp, vp, vp, vp, C.POINTER(SqairOutputs), vp]
+    lib.sqair_forward_train.argtypes = [C.POINTER(SqairCfg), vp, vp, vp, vp, vp, C.POINTER(SqairOutputs), vp, vp]
+    lib.sqair_query_train_sizes.argtypes = [C.POINTER(SqairCfg), C.POINTER(SqairTrainSizes)]
+    lib.sqair_pack_backward.argtypes = [C.POINTER(SqairCfg), vp, vp, vp]
+    lib.sqair_backward.argtypes = [C.POINTER(SqairCfg), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i32), vp]
     lib.sqair_objective.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.sqair_objective_grad.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     lib.sqair_stn_glimpse.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
@@ -121,13 +129,15 @@ def bind(lib):
     lib.sqair_stn_glimpse_grad.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.sqair_canvas_ll.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp]
     lib.sqair_canvas_ll_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp]
-    for name in ('sqair_query_sizes sqair_param_layout sqair_pack_params sqair_fill_noise sqair_forward '
+    for name in ('sqair_query_sizes sqair_param_layout sqair_pack_params sqair_fill_noise sqair_forward sqair_forward_train '
+                 'sqair_query_train_sizes sqair_pack_backward sqair_backward '
                  'sqair_objective sqair_objective_grad sqair_wgrad sqair_dgrad sqair_stn_glimpse sqair_stn_glimpse_grad sqair_canvas_ll sqair_canvas_ll_grad').split():
         getattr(lib, name).restype = C.c_int
     return lib
 
 
-EXPORTED = ('sqair_last_error sqair_version sqair_query_sizes sqair_param_layout sqair_pack_params '
+EXPORTED = ('sqair_last_error sqair_version sqair_query_sizes sqair_param_layout sqair_pack_params sqair_forward_train '
+            'sqair_query_train_sizes sqair_pack_backward sqair_backward '
             'sqair_fill_noise sqair_forward sqair_objective sqair_objective_grad sqair_stn_glimpse sqair_stn_glimpse_grad sqair_canvas_ll sqair_canvas_ll_grad sqair_wgrad sqair_dgrad').split()
 
 _lib = None
@@ -163,6 +173,12 @@ def param_layout(cfg: SqairCfg):
     arr = (SqairParamDesc * n.value)()
     check(lib().sqair_param_layout(C.byref(cfg), arr, C.byref(n)))
     return [(d.name.decode(), tuple(d.shape[:d.ndim]), d.offset, d.packed_offset) for d in arr]
+
+
+def query_train_sizes(cfg: SqairCfg) -> SqairTrainSizes:
+    s = SqairTrainSizes()
+    check(lib().sqair_query_train_sizes(C.byref(cfg), C.byref(s)))
+    return s
 
 
 def query_sizes(cfg: SqairCfg) -> SqairSizes:

@@ -15,23 +15,24 @@
 #include <vector>
 
 #include "sqair_device.cuh"
+#include "sqair_internal.h"
 
 using namespace sq;
+using sqi::Shape;
+using sqi::choose_shape;
+using sqi::env_int;
+using sqi::fail;
+using sqi::cuda_fail;
 
 static thread_local std::string g_err;
 
-static int fail(int code, const std::string& msg) {
+int sqi::fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
-static int cuda_fail(cudaError_t e, const char* what) {
-    return fail(SQAIR_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+int sqi::cuda_fail(cudaError_t e, const char* what) {
+    return sqi::fail(SQAIR_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
-#define CUDA_TRY(x)                                  \
-    do {                                             \
-        cudaError_t e_ = (x);                        \
-        if (e_ != cudaSuccess) return cuda_fail(e_, #x); \
-    } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // persistent sequence kernel: one cluster of C blocks per R rows, the whole T-frame recursion
@@ -48,6 +49,11 @@ __global__ void __launch_bounds__(NT_LAUNCH) sqair_sequence_kernel(const __grid_
         g_trace_last = clock64();
     }
 #endif
+    // the packed parameters carry a layout header; a buffer packed for another cluster size / model must not be read
+    {
+        const uint32_t* h = reinterpret_cast<const uint32_t*>(job.prm + plan.phdr_off);
+        if (h[0] != PACK_MAGIC || h[1] != (uint32_t)plan.C || h[2] != (uint32_t)plan.NS || h[3] != (uint32_t)plan.PX) __trap();
+    }
     Block<R> blk(c, job, (int)(blockIdx.x / plan.C) * R);
     blk.run();
     if (plan.C > 1) { cluster_arrive(c); cluster_wait(c); }      // no block exits while peers may still write to it
@@ -73,29 +79,79 @@ static const int kRowChoices[] = {1, 2, 3, 4, 5, 6};
 static const int kClusterChoices[] = {1, 2, 3, 4, 5, 6, 7, 8};
 static const int kSmemLimit = 232448;    // 227 KB opt-in shared memory per block on sm_100
 
-// The plan lives in __constant__ memory (descriptor reads are constant-bank loads).  It is re-uploaded only
-// when it changes; an upload waits for the previous launch, which may still be reading the old plan.
+// The plan header lives in __constant__ memory (descriptor reads are constant-bank loads); every device has its own
+// copy of the symbol, so the "what is uploaded" state is kept per device.  The header is re-uploaded only when it
+// changes, after every launch that may still be reading the old one has finished (one event per stream that launched
+// since the last upload).
+struct DevicePlanState {
+    PlanHdr uploaded;
+    bool valid = false;
+    std::vector<std::pair<cudaStream_t, cudaEvent_t>> inflight;
+};
 static std::mutex g_plan_mutex;
-static PlanHdr g_plan_uploaded;
-static bool g_plan_valid = false;
-static cudaEvent_t g_last_launch = nullptr;
+static DevicePlanState g_plan_state[64];
 
-static int upload_plan(const Plan& plan, cudaStream_t st) {
+static bool stream_is_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+    return cs != cudaStreamCaptureStatusNone;
+}
+
+static int upload_plan(const Plan& plan, cudaStream_t st, DevicePlanState& ds) {
     const PlanHdr& hdr = plan;
-    if (g_plan_valid && memcmp(&g_plan_uploaded, &hdr, sizeof(PlanHdr)) == 0) return SQAIR_OK;
-    if (!g_last_launch) CUDA_TRY(cudaEventCreateWithFlags(&g_last_launch, cudaEventDisableTiming));
-    else CUDA_TRY(cudaEventSynchronize(g_last_launch));
-    CUDA_TRY(cudaMemcpyToSymbolAsync(c_plan, &hdr, sizeof(PlanHdr), 0, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));         // the host copy of `plan` may be a temporary
-    g_plan_uploaded = hdr;
-    g_plan_valid = true;
+    if (ds.valid && memcmp(&ds.uploaded, &hdr, sizeof(PlanHdr)) == 0) return SQAIR_OK;
+    if (stream_is_capturing(st))
+        return fail(SQAIR_EINVAL, "the launch plan of this configuration is not resident: run the call once before capturing it in a CUDA graph");
+    for (auto& se : ds.inflight) CUDA_TRY(cudaEventSynchronize(se.second));
+    ds.valid = false;
+    ds.uploaded = hdr;                          // the copy source must outlive the (possibly staged) transfer
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_plan, &ds.uploaded, sizeof(PlanHdr), 0, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ds.valid = true;
+    return SQAIR_OK;
+}
+
+// Layer table of a launch shape (L_COUNT x DESC_WORDS words, staged into shared memory one call ahead by the kernel).
+// It depends on everything the plan depends on (rows per cluster, frame staging, stash offsets), so it is NOT part of
+// the packed parameters: the library keeps one small device copy per (device, table contents), for the process
+// lifetime -- the only device memory it ever allocates.
+struct DevTable {
+    int device;
+    uint64_t hash;
+    std::vector<int32_t> host;
+    float* dev;
+};
+static std::mutex g_ltab_mutex;
+static std::vector<DevTable*> g_ltabs;
+
+static int get_layer_table(const Plan& plan, int device, cudaStream_t st, const float** out) {
+    std::vector<int32_t> tab((size_t)L_COUNT * DESC_WORDS, 0);
+    for (int i = 0; i < L_COUNT; ++i) memcpy(&tab[(size_t)i * DESC_WORDS], &plan.L[i], sizeof(Layer));
+    uint64_t h = 1469598103934665603ull;
+    for (int32_t w : tab) { h ^= (uint32_t)w; h *= 1099511628211ull; }
+    std::lock_guard<std::mutex> lock(g_ltab_mutex);
+    for (DevTable* t : g_ltabs)
+        if (t->device == device && t->hash == h && t->host == tab) { *out = t->dev; return SQAIR_OK; }
+    if (stream_is_capturing(st))
+        return fail(SQAIR_EINVAL, "the layer table of this configuration is not resident: run the call once before capturing it in a CUDA graph");
+    DevTable* t = new DevTable{device, h, std::move(tab), nullptr};
+    CUDA_TRY(cudaMalloc((void**)&t->dev, t->host.size() * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpyAsync(t->dev, t->host.data(), t->host.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    g_ltabs.push_back(t);
+    *out = t->dev;
     return SQAIR_OK;
 }
 
 template <int R>
-static int launch_sequence(const Plan& plan, const Job& job, cudaStream_t st) {
+static int launch_sequence(const Plan& plan, Job job, cudaStream_t st) {
+    int device = 0;
+    CUDA_TRY(cudaGetDevice(&device));
+    if (device < 0 || device >= 64) return fail(SQAIR_EUNSUPPORTED, "device ordinal out of range");
+    int rc = get_layer_table(plan, device, st, &job.ltab);
+    if (rc != SQAIR_OK) return rc;
     std::lock_guard<std::mutex> lock(g_plan_mutex);
-    int rc = upload_plan(plan, st);
+    DevicePlanState& ds = g_plan_state[device];
+    rc = upload_plan(plan, st, ds);
     if (rc != SQAIR_OK) return rc;
     const int smem_bytes = plan.sm.total * (int)sizeof(float);
     CUDA_TRY(cudaFuncSetAttribute(sqair_sequence_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -114,7 +170,19 @@ static int launch_sequence(const Plan& plan, const Job& job, cudaStream_t st) {
     cfg.attrs = attr;
     cfg.numAttrs = plan.C > 1 ? 1 : 0;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, sqair_sequence_kernel<R>, job));
-    CUDA_TRY(cudaEventRecord(g_last_launch, st));
+    if (!stream_is_capturing(st)) {           // (a captured launch replays with the plan that was resident at capture time)
+        cudaEvent_t ev = nullptr;
+        for (auto& se : ds.inflight) if (se.first == st) ev = se.second;
+        if (!ev) {
+            if (ds.inflight.size() >= 32) {
+                for (auto& se : ds.inflight) { cudaEventSynchronize(se.second); cudaEventDestroy(se.second); }
+                ds.inflight.clear();
+            }
+            CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            ds.inflight.emplace_back(st, ev);
+        }
+        CUDA_TRY(cudaEventRecord(ev, st));
+    }
     return SQAIR_OK;
 }
 
@@ -122,14 +190,7 @@ static int launch_sequence(const Plan& plan, const Job& job, cudaStream_t st) {
 // cluster (more blocks = less weight traffic and math per SM, more exchange).  Default: the (R, C) with
 // the lowest modelled frame time among those that fit shared memory and run as a single wave on 148 SMs;
 // SQAIR_ROWS_PER_CTA / SQAIR_CLUSTER override (tuning sweeps).  Packing depends on C only.
-struct Shape {
-    Plan plan;
-    std::vector<Piece> pieces;
-    int64_t packed_total = 0;
-    int R = 0, C = 0;
-};
-
-static int env_int(const char* name) {
+int sqi::env_int(const char* name) {
     const char* e = getenv(name);
     return e ? atoi(e) : 0;
 }
@@ -146,7 +207,7 @@ struct ShapeKey {
 static std::mutex g_shape_mutex;
 static std::vector<std::pair<ShapeKey, std::shared_ptr<Shape>>> g_shape_cache;
 
-static std::string choose_shape(const sqair_cfg& c, const std::vector<ParamEntry>& tab, Shape& out) {
+std::string sqi::choose_shape(const sqair_cfg& c, const std::vector<ParamEntry>& tab, Shape& out) {
     ShapeKey key;
     memset(&key, 0, sizeof(key));
     key.cfg = c;
@@ -275,6 +336,10 @@ __global__ void split_panels_kernel(const __grid_constant__ SplitTab tab, float*
         buf[d] = hi;
         buf[d + 128] = lo;
     }
+}
+
+__global__ void pack_header_kernel(uint32_t* hdr, uint32_t C, uint32_t n, uint32_t px) {
+    if (threadIdx.x == 0) { hdr[0] = PACK_MAGIC; hdr[1] = C; hdr[2] = n; hdr[3] = px; }
 }
 
 // Philox4x32-10 (Salmon et al. 2011), counter = (row, frame, slot, block), key = seed.
@@ -919,11 +984,10 @@ int sqair_pack_params(const sqair_cfg* cfg, const float* params, float* packed, 
     }
     split_panels_kernel<<<dim3(32, stab.n), 256, 0, st>>>(stab, packed);
     CUDA_TRY(cudaGetLastError());
-    // layer table (staged into shared memory one call ahead by the kernel)
-    std::vector<int32_t> ltab((size_t)L_COUNT * DESC_WORDS, 0);
-    for (int i = 0; i < L_COUNT; ++i) memcpy(&ltab[(size_t)i * DESC_WORDS], &sh.plan.L[i], sizeof(Layer));
-    CUDA_TRY(cudaMemcpyAsync(packed + sh.plan.ltab_off, ltab.data(), ltab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    // layout header: the sequence kernel refuses (traps on) a buffer packed for another cluster size / model
+    pack_header_kernel<<<1, 32, 0, st>>>(reinterpret_cast<uint32_t*>(packed + sh.plan.phdr_off), (uint32_t)sh.C, (uint32_t)cfg->n,
+                                         (uint32_t)(cfg->H * cfg->W));
+    CUDA_TRY(cudaGetLastError());
     {
         std::lock_guard<std::mutex> lock(g_tag_mutex);
         bool found = false;
@@ -948,10 +1012,12 @@ int sqair_fill_noise(const sqair_cfg* cfg, uint64_t seed, int32_t row_offset, fl
     return SQAIR_OK;
 }
 
-int sqair_forward(const sqair_cfg* cfg, const float* packed_params, const float* obs, const float* eps_where,
-                  const float* eps_what, const float* u_pres, const sqair_outputs* out, void* stream) {
+static int forward_impl(const sqair_cfg* cfg, const float* packed_params, const float* obs, const float* eps_where,
+                        const float* eps_what, const float* u_pres, const sqair_outputs* out, float* stash, void* stream) {
     if (!cfg || !packed_params || !obs || !eps_where || !eps_what || !u_pres || !out)
         return fail(SQAIR_EINVAL, "null argument");
+    if ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(packed_params)) & 15)
+        return fail(SQAIR_EINVAL, "obs and packed_params must be 16-byte aligned (bulk frame copies / 128-bit weight loads)");
     std::string e = validate_cfg(*cfg);
     if (!e.empty()) return fail(SQAIR_EINVAL, e);
     auto tab = param_table(*cfg);
@@ -965,7 +1031,7 @@ int sqair_forward(const sqair_cfg* cfg, const float* packed_params, const float*
                 return fail(SQAIR_EINVAL, "packed_params were packed for a different launch shape (cluster size); "
                                           "call sqair_pack_params with the configuration of this call");
     }
-    Job job{packed_params, obs, eps_where, eps_what, u_pres, *out, env_int("SQAIR_DEBUG_FLAGS")};
+    Job job{packed_params, obs, eps_where, eps_what, u_pres, *out, env_int("SQAIR_DEBUG_FLAGS"), nullptr, stash};
     cudaStream_t st = (cudaStream_t)stream;
 #ifdef SQAIR_ONLY_R              // tuning builds: one instantiation compiles in seconds
     if (sh.R == SQAIR_ONLY_R) return launch_sequence<SQAIR_ONLY_R>(sh.plan, job, st);
@@ -980,6 +1046,17 @@ int sqair_forward(const sqair_cfg* cfg, const float* packed_params, const float*
     }
 #endif
     return fail(SQAIR_EUNSUPPORTED, "unsupported rows per block");
+}
+
+int sqair_forward(const sqair_cfg* cfg, const float* packed_params, const float* obs, const float* eps_where,
+                  const float* eps_what, const float* u_pres, const sqair_outputs* out, void* stream) {
+    return forward_impl(cfg, packed_params, obs, eps_where, eps_what, u_pres, out, nullptr, stream);
+}
+
+int sqair_forward_train(const sqair_cfg* cfg, const float* packed_params, const float* obs, const float* eps_where,
+                        const float* eps_what, const float* u_pres, const sqair_outputs* out, float* stash, void* stream) {
+    if (!stash) return fail(SQAIR_EINVAL, "null stash (sqair_query_sizes: stash_floats)");
+    return forward_impl(cfg, packed_params, obs, eps_where, eps_what, u_pres, out, stash, stream);
 }
 
 int sqair_objective(const float* log_w_t, const float* disc_lp_t, int32_t T, int32_t B, int32_t K, float* log_weights,

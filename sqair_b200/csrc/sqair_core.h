@@ -49,7 +49,7 @@ constexpr int MAX_SLOTS = 8;
 constexpr int MAXC = 8;          // max cluster size (portable limit)
 constexpr int MAXSEQ = 400;      // dense calls per frame
 constexpr int MAXR = 8;          // rows per block: the N dimension of one m16n8k8 MMA
-constexpr int DESC_WORDS = 96;   // >= sizeof(Layer) / 4, multiple of 4, <= NT (one word per thread when staging)
+constexpr int DESC_WORDS = 104;  // >= sizeof(Layer) / 4, multiple of 4, <= NT (one word per thread when staging)
 
 enum Act { ACT_NONE = 0, ACT_ELU = 1, ACT_SIGMOID = 2, ACT_TANH = 3, ACT_SOFTPLUS = 4 };
 enum SegKind { SEG_SMEM = 0, SEG_IMAGE = 1 };
@@ -71,6 +71,9 @@ struct Head {
     float scale, add;
     int scale_p_off;
     int out_off, out_sstride, out_ld;
+    // training stash (sqair_forward with a stash buffer): the finished output also goes to global memory at
+    //   stash[st_off + ((t * rows + row) * st_entries + entry) * st_width + j];  st_off < 0: not stashed
+    int st_off, st_entries, st_width;
 };
 
 struct Layer {
@@ -109,6 +112,78 @@ enum LayerId {
     L_LAT1, L_LAT2, L_IMG1, L_IMG2, L_DRNN, L_DT1, L_DT2, L_DT3, L_DST1, L_DST2,
     L_RN1, L_RN2, L_RN3, L_SP1, L_SP2, L_DEC1, L_DEC2, L_DEC3, L_COUNT
 };
+
+// ------------------------------------------------------------------------------------------
+// Training stash: every activation the backward pass needs, written by the forward kernel (row-major per
+// (frame, row, entry): the layout the batched backward GEMMs read).  Signal g lives at
+//   stash[g.off + ((t * rows + row) * g.entries + e) * g.width + f]
+// ------------------------------------------------------------------------------------------
+enum SigId {
+    S_Z,                                        // [T+1] latents entering frame t (t = T: final): what, where(4), pres, plogit
+    S_TST, S_PST,                               // GRU states entering the frame
+    S_PGZ, S_PGR, S_PGRH, S_PGC, S_PSTNEW,      // prior GRU: z, r, r*h, candidate, new state
+    S_PRI,                                      // post-processed prior statistics
+    S_HWBMK,                                    // hidden of the where-bias MLP | hidden of the mask MLP
+    S_WB, S_MASK,
+    S_GLM, S_ENCA, S_ENCB, S_ENC,               // glimpse encoder, entries = 3n (use * n + slot): prop glimpse 1, prop glimpse 2, discovery
+    S_PH,                                       // [n+1] propagation RNN hidden, entry 0 = initial state
+    S_PT1, S_PT2, S_TP,
+    S_PROPREC,                                  // [n+1] slot records (RecF), entry 0 = initial "previous slot"
+    S_TGZ, S_TGR, S_TGRH, S_TGC, S_TSTNEW,      // temporal GRU
+    S_TG, S_GT, S_PHS,
+    S_L1, S_L2,
+    S_IMG1, S_DIN, S_EXP,                       // per row
+    S_DH, S_DT1, S_DT2, S_DTP, S_DISCREC, S_DHS,
+    S_HRN, S_RNPREV, S_RNO, S_RNS, S_HSP, S_SPL, S_PERM,
+    S_D1, S_D2, S_DGL,
+    S_COUNT
+};
+
+struct Sig {
+    int off, entries, width;
+};
+
+struct StashLayout {
+    Sig s[S_COUNT];
+    int frames[S_COUNT];
+    int64_t total;         // floats
+};
+
+inline StashLayout build_stash(const sqair_cfg& c) {
+    StashLayout L;
+    memset(&L, 0, sizeof(L));
+    const int n = c.n, nw = c.n_what, nh = c.n_hidden, g = c.G * c.G, hs = nh / 2, rows = c.B * c.K;
+    const int rec = 3 * nw + 15;
+    int64_t cur = 0;
+    auto add = [&](int id, int entries, int width, int frames) {
+        L.s[id].off = (int)cur; L.s[id].entries = entries; L.s[id].width = width; L.frames[id] = frames;
+        cur += (int64_t)frames * rows * entries * width;
+        cur = (cur + 3) / 4 * 4;
+        if (cur > 0x7fffff00LL) L.total = -1;
+    };
+    const int T = c.T;
+    add(S_Z, n, nw + 6, T + 1);
+    add(S_TST, n, nh, T); add(S_PST, n, nh, T);
+    add(S_PGZ, n, nh, T); add(S_PGR, n, nh, T); add(S_PGRH, n, nh, T); add(S_PGC, n, nh, T); add(S_PSTNEW, n, nh, T);
+    add(S_PRI, n, 2 * (4 + nw) + 1, T);
+    add(S_HWBMK, n, 256, T);
+    add(S_WB, n, 4, T); add(S_MASK, n, g, T);
+    add(S_GLM, 3 * n, g, T); add(S_ENCA, 3 * n, nh, T); add(S_ENCB, 3 * n, nh, T); add(S_ENC, 3 * n, 2 * nw, T);
+    add(S_PH, n + 1, nh, T);
+    add(S_PT1, n, nh, T); add(S_PT2, n, nh, T); add(S_TP, n, 8, T);
+    add(S_PROPREC, n + 1, rec, T);
+    add(S_TGZ, n, nh, T); add(S_TGR, n, nh, T); add(S_TGRH, n, nh, T); add(S_TGC, n, nh, T); add(S_TSTNEW, n, nh, T);
+    add(S_TG, n, 2 * nw, T); add(S_GT, n, 3 * nw, T); add(S_PHS, n, hs, T);
+    add(S_L1, n, nh, T); add(S_L2, n, nh, T);
+    add(S_IMG1, 1, nh, T); add(S_DIN, 1, 2 * nh, T); add(S_EXP, 1, 1, T);
+    add(S_DH, n + 1, nh, T); add(S_DT1, n, nh, T); add(S_DT2, n, nh, T); add(S_DTP, n, 8, T);
+    add(S_DISCREC, n + 1, rec, T); add(S_DHS, n, hs, T);
+    add(S_HRN, 1, 128, T); add(S_RNPREV, n, 4, T); add(S_RNO, n, 4, T); add(S_RNS, n, 8, T);
+    add(S_HSP, 1, 10, T); add(S_SPL, 1, n + 1, T); add(S_PERM, 1, n, T);
+    add(S_D1, n, nh, T); add(S_D2, n, nh, T); add(S_DGL, n, g, T);
+    if (L.total == 0) L.total = cur;
+    return L;
+}
 
 // fp32 -> (hi, lo), both exactly representable in tf32: hi = w truncated to 10 mantissa bits (so w - hi is exact), lo = the
 // remainder rounded to nearest.  hi + lo differs from w by <= 2^-22 |w|.
@@ -188,16 +263,31 @@ struct PlanHdr {
     sqair_cfg cfg;
     int R, C, NS, rows, nw, nh, g, PX, LDS;  // LDS = NS*R; C = cluster size; PX = H*W
     int nseq;                                 // dense calls per frame
-    int ltab_off;                             // packed-parameter offset of the layer table (L_COUNT x DESC_WORDS words)
+    int phdr_off;                             // packed-parameter offset of the 4-word layout header {magic, cluster size, n, H*W}
     RecF rec;
     Smem sm;
     POff po;
+    Sig st[S_COUNT];                          // training stash signals (build_stash)
     unsigned char seq[MAXSEQ];                // layer ids in program order (one frame)
+};
+
+// Host-side view of a layer for the backward pass: the layer's "virtual matrix" without the k-step padding of the
+// forward panels.  Rows = concatenated input segments (+ one bias row), columns = concatenated heads.
+struct LayerB {
+    int u0[MAXSEG];       // first unpadded row of every segment
+    int ucol0[MAXHEAD];   // first unpadded column of every head
+    int KU, NU;           // rows without the bias row / columns
+    int has_bias;
+    int64_t bw_off;       // offset of the [KU + 1][NU] row-major matrix in the backward parameter buffer
 };
 
 struct Plan : PlanHdr {
     Layer L[L_COUNT];
+    LayerB LB[L_COUNT];
+    int64_t bw_total;     // floats of the backward parameter buffer
+    POff poc;             // like PlanHdr::po, but offsets into the CANONICAL flat buffer (backward pass)
 };
+constexpr uint32_t PACK_MAGIC = 0x53514152u;
 
 // ------------------------------------------------------------------------------------------
 // Host-side builders
@@ -214,6 +304,7 @@ struct Piece {
     int layer, vrow0, vcol0, K, N;   // vrow0 in the PADDED row space (k-step * 8 + k)
     int64_t src_off;     // canonical offset of element (row0, col0) of the source matrix
     int src_ld;
+    int urow0, ucol0;    // the same block in the unpadded virtual matrix of the backward pass (LayerB)
 };
 
 inline void add_param(std::vector<ParamEntry>& v, const std::string& name, int d0 = -1, int d1 = -1, int d2 = -1) {
@@ -326,6 +417,7 @@ struct PlanBuilder {
     std::string err;
     int cursor = 0;          // shared-memory cursor (floats)
     int64_t wcursor = 0;     // packed-parameter cursor (floats)
+    int64_t bwcursor = 0;    // backward parameter buffer cursor (floats)
 
     PlanBuilder(Plan& plan, const std::vector<ParamEntry>& t, std::vector<Piece>& pc) : p(plan), tab(t), pieces(pc) {
         wcursor = vars_floats(t);
@@ -356,6 +448,7 @@ struct PlanBuilder {
         Seg& s = l.seg[l.nseg];
         s.x_off = x_off; s.ld = ld; s.K = K; s.kind = kind; s.x_sstride = x_sstride;
         s.ks0 = l.ksteps;
+        p.LB[&l - p.L].u0[l.nseg] = l.Ktot;
         l.Ktot += K;
         l.ksteps += (K + 7) / 8;
         return l.nseg++;
@@ -370,8 +463,18 @@ struct PlanBuilder {
         Head& h = l.head[l.nhead];
         h.col0 = l.Ntot; h.N = N; h.b_off = b_off; h.b2_off = -1; h.act = act; h.scale = 1.f; h.add = 0.f;
         h.scale_p_off = -1; h.out_off = out_off; h.out_ld = out_ld; h.out_sstride = out_sstride;
+        h.st_off = -1; h.st_entries = 1; h.st_width = 0;
+        LayerB& lb = p.LB[&l - p.L];
+        lb.ucol0[l.nhead] = lb.NU;
+        lb.NU += N;
         l.Ntot += round_up(N, 4);
         return l.nhead++;
+    }
+    // the head's finished output is also a training-stash signal (columns [col, col + N) of signal `sig`)
+    void stash(Layer& l, int h, int sig, int col = 0) {
+        l.head[h].st_off = p.st[sig].off + col;
+        l.head[h].st_entries = p.st[sig].entries;
+        l.head[h].st_width = p.st[sig].width;
     }
     // weights of (segment s, head h) come from rows [row0, row0+K_s) x cols [col0, col0+N_h) of variable `name`
     void w(int id, int s, int h, const std::string& name, int row0, int col0 = 0) {
@@ -383,6 +486,7 @@ struct PlanBuilder {
         pc.layer = id; pc.vrow0 = vr; pc.vcol0 = l.head[h].col0; pc.K = l.seg[s].K; pc.N = l.head[h].N;
         pc.src_ld = e->shape[1];
         pc.src_off = e->offset + (int64_t)row0 * pc.src_ld + col0;
+        pc.urow0 = p.LB[id].u0[s]; pc.ucol0 = p.LB[id].ucol0[h];
         if (row0 + pc.K > e->shape[0] || col0 + pc.N > e->shape[1]) err = "piece out of range in " + name;
         pieces.push_back(pc);
     }
@@ -407,6 +511,9 @@ struct PlanBuilder {
         const int C = p.C;
         bool any_bias = false;
         for (int h = 0; h < l.nhead; ++h) any_bias |= (l.head[h].b_off >= 0 || l.head[h].b2_off >= 0);
+        LayerB& lb = p.LB[id];
+        lb.KU = l.Ktot;
+        lb.has_bias = any_bias ? 1 : 0;
         if (any_bias) {
             if (l.nseg >= MAXSEG) { err = "too many segments"; return; }
             const int brow = l.ksteps * 8;
@@ -419,11 +526,15 @@ struct PlanBuilder {
                     pc.layer = id; pc.vrow0 = brow; pc.vcol0 = l.head[h].col0; pc.K = 1; pc.N = l.head[h].N;
                     pc.src_off = packed_to_canonical(offs[q]);
                     pc.src_ld = l.head[h].N;
+                    pc.urow0 = lb.KU; pc.ucol0 = lb.ucol0[h];
                     pieces.push_back(pc);
                 }
                 l.head[h].b_off = l.head[h].b2_off = -1;
             }
         }
+        lb.bw_off = bwcursor;
+        bwcursor += (int64_t)(lb.KU + 1) * lb.NU;
+        bwcursor = (bwcursor + 3) / 4 * 4;
         int per = (l.Ntot + C - 1) / C;
         if (C > 1 && per >= 8) {          // at least half an m16 tile of real columns per block
             l.split = 1;
@@ -496,6 +607,11 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
     rf.where_loc = 3 * nw + 5; rf.where_scale = 3 * nw + 9; rf.prob = 3 * nw + 13; rf.logit = 3 * nw + 14;
     rf.size = 3 * nw + 15;
 
+    {
+        const StashLayout SL = build_stash(c);
+        if (SL.total < 0) return "training stash exceeds 2^31 floats";
+        for (int i = 0; i < S_COUNT; ++i) p.st[i] = SL.s[i];
+    }
     PlanBuilder B(p, tab, pieces);
     B.unit_cost = unit_cost; B.slice_cost = slice_cost;
     Smem& m = p.sm;
@@ -580,6 +696,23 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
     po.step_prior_bias = B.off("model/sequential_air/while/sqair_timestep/discover/step_prior_bias");
     po.step_prior_tbias = B.off("model/sequential_air/while/sqair_timestep/discover/step_prior_timestep_bias");
     po.cholesky = B.off(PC + "affine_diag_normal/cholesky_scale");
+    {
+        POff& q = p.poc;
+        auto CO = [&](const std::string& n) { return (int)B.canon(n); };
+        q.mean_img = CO("decoder/air_decoder/Variable");
+        q.output_scale = CO("decoder/air_decoder/decoder/output_scale");
+        q.disc_h0 = CO("discovery/discover/discovery/vanilla_rnn_initial_state_0/w");
+        q.prop_h0 = CO("propagation/sequential_ssm/propagation/vanilla_rnn_initial_state_0/w");
+        q.temporal_h0 = CO(SQ + "propagation/gru_initial_state_0/w");
+        q.prior_h0 = CO(SQ + "propagation/gru_1_initial_state_0/w");
+        q.rn_init_state = c.rec_where_prior ? CO(RN + "discovery/discover/recurrent_normal_impl/vanilla_rnn_initial_state_0/w") : -1;
+        q.rn_init_sample = c.rec_where_prior ? CO(RN + "init_sample") : -1;
+        q.d_scale_offset = CO(DC + "stochastic_transform_param/scale_offset");
+        q.p_scale_offset = CO(PC + "stochastic_transform_param/scale_offset");
+        q.step_prior_bias = CO("model/sequential_air/while/sqair_timestep/discover/step_prior_bias");
+        q.step_prior_tbias = CO("model/sequential_air/while/sqair_timestep/discover/step_prior_timestep_bias");
+        q.cholesky = CO(PC + "affine_diag_normal/cholesky_scale");
+    }
 
     auto Bi = [&](const std::string& n) { return B.off(n + "/b"); };
     const int zw = m.Z, zwhere = m.Z + nw * LDS;      // Z: what rows 0..nw-1, where nw..nw+3, pres nw+4
@@ -603,6 +736,7 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
         B.head(l, nh, B.off("propagation/gru_1/br"), ACT_SIGMOID, m.Gr, R);
         B.w(L_PGRU_ZR, 0, 0, "propagation/gru_1/wz", 0); B.w(L_PGRU_ZR, 1, 0, "propagation/gru_1/uz", 0);
         B.w(L_PGRU_ZR, 0, 1, "propagation/gru_1/wr", 0); B.w(L_PGRU_ZR, 1, 1, "propagation/gru_1/ur", 0);
+        B.stash(l, 0, S_PGZ); B.stash(l, 1, S_PGR);
         B.finish(L_PGRU_ZR);
     }
     {
@@ -611,6 +745,7 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
         B.seg(l, m.Gr, R, nh);                          // Gr holds r*h
         B.head(l, nh, B.off("propagation/gru_1/bh"), ACT_TANH, m.Gc, R);
         B.w(L_PGRU_C, 0, 0, "propagation/gru_1/wh", 0); B.w(L_PGRU_C, 1, 0, "propagation/gru_1/uh", 0);
+        B.stash(l, 0, S_PGC);
         B.finish(L_PGRU_C);
     }
     simple(L_PLIN, m.Pst, LDS, nh, R, "propagation/propagate_prior/linear", 2 * (4 + nw) + 1, ACT_NONE, m.Pri, LDS, R);
@@ -624,25 +759,32 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
         if (c.masked_glimpse) {
             B.head(l, 128, Bi(DC + "air_encoder/mlp/linear"), ACT_ELU, m.Hmk, R);
             B.w(L_WBMK1, 0, 1, DC + "air_encoder/mlp/linear/w", 0);
+            B.stash(l, 1, S_HWBMK, 128);
         }
+        B.stash(l, 0, S_HWBMK, 0);
         B.finish(L_WBMK1);
     }
     simple(L_WB2, m.Hwb, R, 128, 0, PC + "rnn_inpt/mlp/linear_1", 4, ACT_NONE, m.Wb, R).head[0].scale = 0.1f;
+    B.stash(p.L[L_WB2], 0, S_WB);
     B.finish(L_WB2);
     if (c.masked_glimpse) {
         simple(L_MK2, m.Hmk, R, 128, 0, DC + "air_encoder/mlp/linear_1", g, ACT_SIGMOID, m.Mask, R);
+        B.stash(p.L[L_MK2], 0, S_MASK);
         B.finish(L_MK2);
     }
     // ---- glimpse encoder (modules.py:100-112,358-364), shared by discovery and propagation
     simple(L_ENC1, m.Glm, R, g, 0, DC + "encoder_1/mlp/linear", nh, ACT_ELU, m.A0, R);
+    B.stash(p.L[L_ENC1], 0, S_ENCA);
     B.finish(L_ENC1);
     simple(L_ENC2, m.A0, R, nh, 0, DC + "encoder_1/mlp/linear_1", nh, ACT_ELU, m.A1, R);
+    B.stash(p.L[L_ENC2], 0, S_ENCB);
     B.finish(L_ENC2);
     {   // only .loc is consumed at core.py:293: first nw columns of the [nh, 2nw] head
         Layer& l = B.layer(L_ENC3_LOC);
         B.seg(l, m.A1, R, nh);
         B.head(l, nw, Bi(DC + "air_encoder/gaussian_from_param_vec/linear"), ACT_NONE, m.Loc1, R);
         B.w(L_ENC3_LOC, 0, 0, DC + "air_encoder/gaussian_from_param_vec/linear/w", 0);
+        B.stash(l, 0, S_ENC, 0);
         B.finish(L_ENC3_LOC);
     }
     auto gauss_heads = [&](int id, Layer& l, const std::string& lin, int out_off) {    // (loc | softplus(scale)+min_std)
@@ -657,6 +799,7 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
         Layer& l = B.layer(L_ENC3);
         B.seg(l, m.A1, R, nh);
         gauss_heads(L_ENC3, l, DC + "air_encoder/gaussian_from_param_vec/linear", m.Enc);
+        B.stash(l, 0, S_ENC, 0); B.stash(l, 1, S_ENC, nw);
         B.finish(L_ENC3);
     }
     // ---- propagation RNN (core.py:295-302): [loc1, km1(what,where,pres), tm1(what,where,pres), temporal] + h
@@ -671,6 +814,7 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
         l.head[h].b2_off = Bi("propagation/vanilla_rnn/hidden_to_hidden");
         B.wrows(L_PRNN, 0, "propagation/vanilla_rnn/in_to_hidden/w", 0, 3);
         B.w(L_PRNN, 4, 0, "propagation/vanilla_rnn/hidden_to_hidden/w", 0);
+        B.stash(l, h, S_PH);
         B.finish(L_PRNN);
     }
     // ---- propagation transform estimator (core.py:321-327): [h, where_tm1, temporal]
@@ -681,11 +825,14 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
         B.seg(l, m.Tst, LDS, nh, R);
         B.head(l, nh, Bi(PC + "stochastic_transform_param/mlp/linear"), ACT_ELU, m.A0, R);
         B.wrows(L_PT1, 0, PC + "stochastic_transform_param/mlp/linear/w");
+        B.stash(l, 0, S_PT1);
         B.finish(L_PT1);
     }
     simple(L_PT2, m.A0, R, nh, 0, PC + "stochastic_transform_param/mlp/linear_1", nh, ACT_ELU, m.A1, R);
+    B.stash(p.L[L_PT2], 0, S_PT2);
     B.finish(L_PT2);
     simple(L_PT3, m.A1, R, nh, 0, PC + "stochastic_transform_param/mlp/linear_2", 8, ACT_NONE, m.Tp, R);
+    B.stash(p.L[L_PT3], 0, S_TP);
     B.finish(L_PT3);
     // ---- temporal GRU (core.py:339-340): x = [h, where, loc2, scale2], state = Tst
     const int where_cur = m.PropOut + R + rf.where * LDE;          // this slot's where (entry s+1)
@@ -699,6 +846,7 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
         B.head(l, nh, B.off("propagation/gru/br"), ACT_SIGMOID, m.Gr, R);
         B.wrows(L_TGRU_ZR, 0, "propagation/gru/wz", 0, 2); B.w(L_TGRU_ZR, 3, 0, "propagation/gru/uz", 0);
         B.wrows(L_TGRU_ZR, 1, "propagation/gru/wr", 0, 2); B.w(L_TGRU_ZR, 3, 1, "propagation/gru/ur", 0);
+        B.stash(l, 0, S_TGZ); B.stash(l, 1, S_TGR);
         B.finish(L_TGRU_ZR);
     }
     {
@@ -709,6 +857,7 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
         B.seg(l, m.Gr, R, nh);
         B.head(l, nh, B.off("propagation/gru/bh"), ACT_TANH, m.Gc, R);
         B.wrows(L_TGRU_C, 0, "propagation/gru/wh", 0, 2); B.w(L_TGRU_C, 3, 0, "propagation/gru/uh", 0);
+        B.stash(l, 0, S_TGC);
         B.finish(L_TGRU_C);
     }
     // ---- what heads on the new temporal state (core.py:343-349); Gc holds the new temporal state
@@ -719,6 +868,7 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
         int h = B.head(l, 3 * nw, Bi(PC + "what/linear"), ACT_SIGMOID, m.Gt, R);
         l.head[h].scale = 0.9999f;
         B.w(L_PHEADS, 0, h, PC + "what/linear/w", 0);
+        B.stash(l, 0, S_TG, 0); B.stash(l, 1, S_TG, nw); B.stash(l, h, S_GT);
         B.finish(L_PHEADS);
     }
     // ---- propagation steps predictor (modules.py:506-513): [h, temporal(old), what]
@@ -729,14 +879,17 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
         B.seg(l, m.PropOut + R + rf.what * LDE, LDE, nw, R);
         B.head(l, s, Bi(PC + "steps_predictor/mlp/linear"), ACT_ELU, m.Hs, R);
         B.wrows(L_PST1, 0, PC + "steps_predictor/mlp/linear/w");
+        B.stash(l, 0, S_PHS);
         B.finish(L_PST1);
     }
     simple(L_PST2, m.Hs, R, s, 0, PC + "steps_predictor/mlp/linear_1", 1, ACT_NONE, m.Lg, R);
     B.finish(L_PST2);
     // ---- latent encoder (sqair_modules.py:368-385): [what, where] of a propagated slot
     simple(L_LAT1, m.PropOut + R, LDE, nw + 4, R, SQ + "sqair_timestep/mlp/linear", nh, ACT_ELU, m.A0, R);
+    B.stash(p.L[L_LAT1], 0, S_L1);
     B.finish(L_LAT1);
     simple(L_LAT2, m.A0, R, nh, 0, SQ + "sqair_timestep/mlp/linear_1", nh, ACT_ELU, m.A1, R);
+    B.stash(p.L[L_LAT2], 0, S_L2);
     B.finish(L_LAT2);
     // ---- image encoder (core.py:165), once per frame
     {
@@ -744,9 +897,11 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
         B.seg(l, 0, 0, P, 0, SEG_IMAGE);
         B.head(l, nh, Bi(DC + "encoder/mlp/linear"), ACT_ELU, m.A0, R);
         B.w(L_IMG1, 0, 0, DC + "encoder/mlp/linear/w", 0);
+        B.stash(l, 0, S_IMG1);
         B.finish(L_IMG1);
     }
     simple(L_IMG2, m.A0, R, nh, 0, DC + "encoder/mlp/linear_1", nh, ACT_ELU, m.DIn, R);
+    B.stash(p.L[L_IMG2], 0, S_DIN, 0);
     B.finish(L_IMG2);
     // ---- discovery RNN (core.py:164-176,197-198): [img_enc, conditioning, km1(what,where,pres)] + h
     {
@@ -758,13 +913,17 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
         l.head[h].b2_off = Bi("discovery/vanilla_rnn/hidden_to_hidden");
         B.wrows(L_DRNN, 0, "discovery/vanilla_rnn/in_to_hidden/w", 0, 1);
         B.w(L_DRNN, 2, 0, "discovery/vanilla_rnn/hidden_to_hidden/w", 0);
+        B.stash(l, h, S_DH);
         B.finish(L_DRNN);
     }
     simple(L_DT1, Hnew, R, nh, 0, DC + "stochastic_transform_param/mlp/linear", nh, ACT_ELU, m.A0, R);
+    B.stash(p.L[L_DT1], 0, S_DT1);
     B.finish(L_DT1);
     simple(L_DT2, m.A0, R, nh, 0, DC + "stochastic_transform_param/mlp/linear_1", nh, ACT_ELU, m.A1, R);
+    B.stash(p.L[L_DT2], 0, S_DT2);
     B.finish(L_DT2);
     simple(L_DT3, m.A1, R, nh, 0, DC + "stochastic_transform_param/mlp/linear_2", 8, ACT_NONE, m.Tp, R);
+    B.stash(p.L[L_DT3], 0, S_DTP);
     B.finish(L_DT3);
     {
         Layer& l = B.layer(L_DST1);
@@ -772,6 +931,7 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
         B.seg(l, m.DiscOut + R + rf.what * LDE, LDE, nw, R);
         B.head(l, s, Bi(DC + "steps_predictor/mlp/linear"), ACT_ELU, m.Hs, R);
         B.wrows(L_DST1, 0, DC + "steps_predictor/mlp/linear/w");
+        B.stash(l, 0, S_DHS);
         B.finish(L_DST1);
     }
     simple(L_DST2, m.Hs, R, s, 0, DC + "steps_predictor/mlp/linear_1", 1, ACT_NONE, m.Lg, R);
@@ -785,6 +945,7 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
             B.seg(l, m.Exp, R, 1);
             B.head(l, 128, Bi(RN + "linear_1"), ACT_ELU, m.Hrn, R);
             B.wrows(L_RN1, 0, RN + "linear_1/w");
+            B.stash(l, 0, S_HRN);
             B.finish(L_RN1);
         }
         {
@@ -795,6 +956,7 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
             l.head[h].b2_off = Bi(RN + "vanilla_rnn/hidden_to_hidden");
             B.w(L_RN2, 0, 0, RN + "vanilla_rnn/in_to_hidden/w", 0);
             B.w(L_RN2, 1, 0, RN + "vanilla_rnn/hidden_to_hidden/w", 0);
+            B.stash(l, h, S_RNO);
             B.finish(L_RN2);
         }
         {
@@ -806,21 +968,27 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
             l.head[h1].add = 1e-2f;
             B.w(L_RN3, 0, 0, RN + "linear/w", 0, 0);
             B.w(L_RN3, 0, 1, RN + "linear/w", 0, 4);
+            B.stash(l, 0, S_RNS, 0); B.stash(l, h1, S_RNS, 4);
             B.finish(L_RN3);
         }
     }
     // ---- step-count prior MLP (sqair_modules.py:217-218)
     simple(L_SP1, m.Exp, R, 1, 0, "discovery/discover/mlp/linear", 10, ACT_ELU, m.Hsp, R);
+    B.stash(p.L[L_SP1], 0, S_HSP);
     B.finish(L_SP1);
     simple(L_SP2, m.Hsp, R, 10, 0, "discovery/discover/mlp/linear_1", NS + 1, ACT_NONE, m.Spl, R);
+    B.stash(p.L[L_SP2], 0, S_SPL);
     B.finish(L_SP2);
     // ---- glimpse decoder (modules.py:131-147)
     simple(L_DEC1, zw, LDS, nw, R, "decoder/air_decoder/decoder/mlp/linear", nh, ACT_ELU, m.A0, R);
+    B.stash(p.L[L_DEC1], 0, S_D1);
     B.finish(L_DEC1);
     simple(L_DEC2, m.A0, R, nh, 0, "decoder/air_decoder/decoder/mlp/linear_1", nh, ACT_ELU, m.A1, R);
+    B.stash(p.L[L_DEC2], 0, S_D2);
     B.finish(L_DEC2);
     simple(L_DEC3, m.A1, R, nh, 0, "decoder/air_decoder/decoder/mlp/linear_2", g, ACT_NONE, m.Dgl, LDS, R)
         .head[0].scale_p_off = po.output_scale;
+    B.stash(p.L[L_DEC3], 0, S_DGL);
     B.finish(L_DEC3);
 
     // reduction scratch: every k-slice parks its partial sums, [ksplit][Nc][R]
@@ -842,8 +1010,8 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
     for (size_t i = 0; i < q.size(); ++i) p.seq[i] = (unsigned char)q[i];
     static_assert(sizeof(Layer) <= DESC_WORDS * 4, "DESC_WORDS too small");
     static_assert(DESC_WORDS <= NT, "descriptor staging uses one thread per word");
-    p.ltab_off = (int)((B.wcursor + 31) / 32 * 32);
-    B.wcursor = p.ltab_off + (int64_t)L_COUNT * DESC_WORDS;
+    p.bw_total = B.bwcursor;
+    p.phdr_off = (int)((B.wcursor + 31) / 32 * 32);
     if (packed_total) *packed_total = (B.wcursor + 31) / 32 * 32 + 32;
     return B.err;
 }

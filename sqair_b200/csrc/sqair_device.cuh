@@ -269,6 +269,8 @@ struct Job {
     const float* u_pres;     // [T][rows][2n]
     sqair_outputs out;
     int debug_flags;         // tuning experiments only: 1 = skip the MMA math (garbage results), 4/8/16/32/64 skip other stages
+    const float* ltab;       // layer table of this launch shape: L_COUNT x DESC_WORDS words (library-owned device buffer)
+    float* stash;            // training stash (build_stash layout) or nullptr (inference)
 };
 
 SQ_DEV bool layer_has_work(const Layer& L, int rank) { return !L.split || rank < L.npanel; }
@@ -276,12 +278,13 @@ SQ_DEV const float* panel_ptr(const Layer& L, const float* prm, int rank) {
     return prm + L.w_off + (size_t)(L.split ? rank : 0) * L.panel_floats;
 }
 
-SQ_DEV void calls_init(Ctx& c, const float* prm) {
+SQ_DEV void calls_init(Ctx& c, const float* ltab) {
     const auto& P = SQ_PLAN;
 #ifdef SQAIR_HOST_EMU
     c.call_idx = 0;
+    (void)ltab;
 #else
-    if (c.tid() < DESC_WORDS) SQ_SM[P.sm.Desc + c.tid()] = SQ_LDG(prm + P.ltab_off + (int)P.seq[0] * DESC_WORDS + c.tid());
+    if (c.tid() < DESC_WORDS) SQ_SM[P.sm.Desc + c.tid()] = SQ_LDG(ltab + (int)P.seq[0] * DESC_WORDS + c.tid());
     c.sync();
 #endif
 }
@@ -444,9 +447,12 @@ SQ_UNIT void mma_unit(const Layer& L, const float4* SQ_RESTRICT wp, int k0, int 
 // in flight); bit 1 = the caller promises that the next operation is another dense call, so this call may leave its
 // own barrier open.  Returns true when it did.  call_idx / desc_cur: position in Plan::seq and descriptor slot (kept in
 // registers by the caller).
+// Training stash: `stash` != nullptr makes every finished output also go to global memory (Head::st_off), at frame
+// st_t, rows row0 + r, entry st_entry of the head's signal.
 template <int R>
-SQ_DEVNI bool dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot,
-                    const float* const* imgrow, const float* SQ_RESTRICT img_g, int dbg, int flags, int call_idx, int desc_cur) {
+SQ_DEVNI bool dense(Ctx& c, const float* SQ_RESTRICT prm, const float* SQ_RESTRICT ltab, int layer_id, int slot,
+                    const float* const* imgrow, const float* SQ_RESTRICT img_g, int dbg, int flags, int call_idx, int desc_cur,
+                    float* SQ_RESTRICT stash, int st_t, int st_entry, int row0) {
     const auto& P = SQ_PLAN;
 #ifdef SQAIR_HOST_EMU
     const Layer& L = P.L[layer_id];
@@ -455,14 +461,14 @@ SQ_DEVNI bool dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
         abort();
     }
     if (++c.call_idx >= P.nseq) c.call_idx = 0;
-    (void)img_g; (void)call_idx; (void)desc_cur;
+    (void)img_g; (void)call_idx; (void)desc_cur; (void)ltab;
 #else
     if (++call_idx >= P.nseq) call_idx = 0;
     // the descriptor of this call was staged in shared memory during the previous call (before that call's block
     // barrier, so it is visible even if the cluster barrier of that call is still open); start fetching the next one
     const Layer& L = *reinterpret_cast<const Layer*>(SQ_SM + P.sm.Desc + desc_cur * DESC_WORDS);
     float next_desc_word = 0.f;
-    if (c.tid() < DESC_WORDS) next_desc_word = SQ_LDG(prm + P.ltab_off + (int)P.seq[call_idx] * DESC_WORDS + c.tid());
+    if (c.tid() < DESC_WORDS) next_desc_word = SQ_LDG(ltab + (int)P.seq[call_idx] * DESC_WORDS + c.tid());
     (void)imgrow;
 #endif
     SQ_TICK(c, 5);                               // time since the previous dense call (element-wise stages)
@@ -566,6 +572,8 @@ SQ_DEVNI bool dense(Ctx& c, const float* SQ_RESTRICT prm, int layer_id, int slot
             } else {
                 SQ_SM[off] = v;
             }
+            if (stash != nullptr && H.st_off >= 0 && row0 + r < P.rows && (L.split || c.rank() == 0))
+                stash[(size_t)H.st_off + ((size_t)(st_t * P.rows + row0 + r) * H.st_entries + st_entry) * H.st_width + j] = v;
         }
     }
     SQ_TICK(c, 3);
@@ -612,6 +620,9 @@ struct Block {
     const float* eps_what_;
     const float* u_pres_;
     int dbg_;
+    const float* ltab_;
+    float* stash_;                       // training stash or nullptr
+    int t_;                              // current frame
     mutable int call_idx_, desc_cur_;    // position in Plan::seq / descriptor slot of the next dense call
     mutable bool pend_;                  // the last dense call left its cluster barrier open
     int row0;                       // first global row of this block
@@ -626,6 +637,7 @@ struct Block {
 #endif
         call_idx_ = 0; desc_cur_ = 0; pend_ = false;
         prm_ = J_.prm; obs_ = J_.obs; eps_where_ = J_.eps_where; eps_what_ = J_.eps_what; u_pres_ = J_.u_pres; dbg_ = J_.debug_flags;
+        ltab_ = J_.ltab; stash_ = J_.stash; t_ = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             imgrow[r] = nullptr;
@@ -645,19 +657,36 @@ struct Block {
     SQ_DEV float prm(int off) const { return SQ_LDG(prm_ + off); }
     // `next_is_dense`: nothing but another lin() follows (no element-wise stage reads or writes shared memory in
     // between), so the cluster barrier of this call may be completed inside the next one, behind its first weight loads
-    SQ_DEV void lin(int id, int slot = 0, bool next_is_dense = false) const {
+    // `st_entry`: entry of the training-stash signals this call's outputs belong to (default: the slot)
+    SQ_DEV void lin(int id, int slot = 0, bool next_is_dense = false, int st_entry = -1) const {
         if (dbg_ & 64) return;
         const int flags = (pend_ ? 1 : 0) | (next_is_dense ? 2 : 0);
+        if (st_entry < 0) st_entry = slot;
 #ifdef SQAIR_HOST_EMU
-        pend_ = dense<R>(c, prm_, id, slot, imgrow, img_g, dbg_, flags, call_idx_, desc_cur_);
+        pend_ = dense<R>(c, prm_, ltab_, id, slot, imgrow, img_g, dbg_, flags, call_idx_, desc_cur_, stash_, t_, st_entry, row0);
 #else
-        pend_ = dense<R>(c, prm_, id, slot, nullptr, img_g, dbg_, flags, call_idx_, desc_cur_);   // (passing imgrow would pin it to local memory)
+        pend_ = dense<R>(c, prm_, ltab_, id, slot, nullptr, img_g, dbg_, flags, call_idx_, desc_cur_, stash_, t_, st_entry, row0);   // (passing imgrow would pin it to local memory)
 #endif
         if (++call_idx_ >= P.nseq) call_idx_ = 0;
         desc_cur_ ^= 1;
     }
     SQ_DEV size_t nidx(int t, int r, int slot2) const {      // noise index of (t, row, slot in [0,2n))
         return ((size_t)t * P.rows + grow_of(r)) * (2 * P.NS) + slot2;
+    }
+    // Training stash of a signal that an element-wise stage produced: nfeat features of entry `entry`, read from
+    // shared memory at smem_off + f * fstride + r.  The (replicated) state is split by features across the cluster's
+    // blocks; consecutive threads write consecutive features of one row.
+    SQ_DEV void stash_copy(int sig, int t, int entry, int smem_off, int fstride, int nfeat, int col0 = 0) const {
+        if (stash_ == nullptr) return;
+        const Sig g = P.st[sig];
+        const int per = (nfeat + c.ncta() - 1) / c.ncta(), f0 = c.rank() * per;
+        const int cnt = (f0 + per < nfeat ? f0 + per : nfeat) - f0;
+        for (int i = c.tid(); i < cnt * R; i += c.nthreads()) {
+            const int r = i / cnt, f = f0 + i - r * cnt;
+            if (valid_row(r))
+                stash_[(size_t)g.off + ((size_t)(t * P.rows + row0 + r) * g.entries + entry) * g.width + col0 + f] =
+                    SQ_SM[smem_off + f * fstride + r];
+        }
     }
     enum { RA_QPRES = 0, RA_PPRES = 1, RA_NPROP = 2, RA_NDISC = 3, RA_QNUM = 4, RA_PNUM = 5, RA_LL = 6 };
     enum { LP_PQWHAT = 0, LP_PQWHERE = 1, LP_PPWHAT = 2, LP_PPWHERE = 3, LP_PROB = 4,
@@ -693,8 +722,8 @@ struct Block {
         }
         if (P.cfg.rec_where_prior)
             for (int i = c.tid(); i < 4 * R; i += c.nthreads()) SQ_SM[m.RnInit + i] = prm(P.po.rn_init_state + i / R);
-        (void)NS;
         c.sync();
+        for (int s = 0; s < NS; ++s) stash_copy(S_Z, 0, s, m.Z + s * R, LDS(), nw + 6);
     }
 
     // the frame's bulk copy has landed (returns at once when it already has; no-op when frames are read from global)
@@ -707,7 +736,7 @@ struct Block {
 #endif
     }
     // forward spatial transformer (modules.py:165-172,204-218) at Coords -> Glm (* Mask)
-    SQ_DEV void extract_glimpse(bool use_mask) const {
+    SQ_DEV void extract_glimpse(bool use_mask, int st_entry) const {
         const Smem& m = P.sm;
         const int G = P.cfg.G, W = P.cfg.W, H = P.cfg.H;
         const float hw = 0.5f * (float)(W - 1), hh = 0.5f * (float)(H - 1);
@@ -727,6 +756,7 @@ struct Block {
             SQ_SM[m.Glm + i] = v;
         }
         c.sync();
+        stash_copy(S_GLM, t_, st_entry, m.Glm, R, P.g);
     }
     // to_coords (modules.py:220-227) + clip_preserve(scale, 1e-4) (modules.py:206)
     SQ_DEV void set_coords(float w0, float w1, float w2, float w3, int r) const {
@@ -736,17 +766,18 @@ struct Block {
         SQ_SM[m.Coords + 2 * R + r] = tanhf(w2);
         SQ_SM[m.Coords + 3 * R + r] = tanhf(w3);
     }
-    SQ_DEV void encode_glimpse(int last_layer, bool next_is_dense = false) const {
-        lin(L_ENC1, 0, true); lin(L_ENC2, 0, true); lin(last_layer, 0, next_is_dense);
+    SQ_DEV void encode_glimpse(int last_layer, int st_entry, bool next_is_dense = false) const {
+        lin(L_ENC1, 0, true, st_entry); lin(L_ENC2, 0, true, st_entry); lin(last_layer, 0, next_is_dense, st_entry);
     }
     // snt.GRU gate algebra (Appendix B) around the two dense calls: Gr <- r*h, then state update.
-    SQ_DEV void gru_mul_r(int state_off, int s) const {
+    SQ_DEV void gru_mul_r(int state_off, int s, int sig_rh) const {
         const Smem& m = P.sm;
         for (int i = c.tid(); i < P.nh * R; i += c.nthreads()) {
             int f = i / R, r = i % R;
             SQ_SM[m.Gr + i] *= SQ_SM[state_off + f * LDS() + s * R + r];
         }
         c.sync();
+        stash_copy(sig_rh, t_, s, m.Gr, R, P.nh);
     }
 
     // ------------------------------------------------------------------------------------------
@@ -756,7 +787,7 @@ struct Block {
         const Smem& m = P.sm;
         const int nh = P.nh, nw = P.nw;
         lin(L_PGRU_ZR, s);
-        gru_mul_r(m.Pst, s);
+        gru_mul_r(m.Pst, s, S_PGRH);
         lin(L_PGRU_C, s);
         for (int i = c.tid(); i < nh * R; i += c.nthreads()) {
             int f = i / R, r = i % R;
@@ -765,6 +796,7 @@ struct Block {
             h = (1.f - z) * h + z * SQ_SM[m.Gc + i];
         }
         c.sync();
+        stash_copy(S_PSTNEW, t_, s, m.Pst + s * R, LDS(), nh);
         lin(L_PLIN, s);
         // stats post-processing: rows 0 logit | 1..4 where_loc | 5..4+nw what_loc | where_scale(4) | what_scale(nw)
         const int nstat = 2 * (4 + nw) + 1;
@@ -787,6 +819,7 @@ struct Block {
             pri(f, s, r) = v;
         }
         c.sync();
+        stash_copy(S_PRI, t_, s, m.Pri + s * R, LDS(), nstat);
     }
 
     // ------------------------------------------------------------------------------------------
@@ -800,16 +833,16 @@ struct Block {
         prop_prior(s);
         // where_bias MLP and glimpse mask MLP on the slot's temporal state (core.py:291; modules.py:350-356)
         lin(L_WBMK1, s, true);
-        lin(L_WB2, 0, masked);
-        if (masked) lin(L_MK2);
+        lin(L_WB2, 0, masked, s);
+        if (masked) lin(L_MK2, 0, false, s);
         for (int r = c.tid(); r < R; r += c.nthreads())
             set_coords(Z(nw + 0, s, r) + SQ_SM[m.Wb + 0 * R + r], Z(nw + 1, s, r) + SQ_SM[m.Wb + 1 * R + r],
                        Z(nw + 2, s, r) + SQ_SM[m.Wb + 2 * R + r], Z(nw + 3, s, r) + SQ_SM[m.Wb + 3 * R + r], r);
         c.sync();
-        extract_glimpse(masked);
-        encode_glimpse(L_ENC3_LOC, true);                         // -> Loc1 (core.py:292-293)
-        lin(L_PRNN, s, true);                                     // core.py:295-302 -> Hrnn[1]
-        lin(L_PT1, s, true); lin(L_PT2, 0, true); lin(L_PT3);     // core.py:323-324 -> Tp
+        extract_glimpse(masked, s);
+        encode_glimpse(L_ENC3_LOC, s, true);                      // -> Loc1 (core.py:292-293)
+        lin(L_PRNN, s, true, s + 1);                              // core.py:295-302 -> Hrnn[1]
+        lin(L_PT1, s, true); lin(L_PT2, 0, true, s); lin(L_PT3, 0, false, s);     // core.py:323-324 -> Tp
         // where ~ MVN_TriL(where_tm1 + us*loc, L) (core.py:326-330; modules.py:535-545)
         for (int r = c.tid(); r < R; r += c.nthreads()) {
             float loc[4], sc[4], eps[4], L[4][4], wh[4];
@@ -834,11 +867,11 @@ struct Block {
             set_coords(wh[0], wh[1], wh[2], wh[3], r);
         }
         c.sync();
-        extract_glimpse(masked);
-        encode_glimpse(L_ENC3);                                   // -> Enc = (loc2, scale2) (core.py:336-337)
+        extract_glimpse(masked, P.NS + s);
+        encode_glimpse(L_ENC3, P.NS + s);                         // -> Enc = (loc2, scale2) (core.py:336-337)
         // temporal GRU (core.py:339-340); new state left in Gc, Tst updated at the end of the slot
         lin(L_TGRU_ZR, s);
-        gru_mul_r(m.Tst, s);
+        gru_mul_r(m.Tst, s, S_TGRH);
         lin(L_TGRU_C, s);
         for (int i = c.tid(); i < nh * R; i += c.nthreads()) {
             int f = i / R, r = i % R;
@@ -846,7 +879,8 @@ struct Block {
             SQ_SM[m.Gc + i] = (1.f - z) * h + z * SQ_SM[m.Gc + i];
         }
         c.sync();
-        lin(L_PHEADS);                                            // core.py:343-349 -> Tg, Gt
+        stash_copy(S_TSTNEW, t_, s, m.Gc, R, nh);
+        lin(L_PHEADS, 0, false, s);                               // core.py:343-349 -> Tg, Gt
         for (int i = c.tid(); i < nw * R; i += c.nthreads()) {        // core.py:351-357
             int j = i / R, r = i % R;
             float fg = SQ_SM[m.Gt + i], ig = SQ_SM[m.Gt + nw * R + i], tg = SQ_SM[m.Gt + 2 * nw * R + i];
@@ -924,6 +958,7 @@ struct Block {
             SQ_SM[m.Hrnn + i] = SQ_SM[m.Hrnn + nh * R + i];
         }
         c.sync();
+        stash_copy(S_PROPREC, t_, e, m.PropOut + e * R, LDE(), F.size);
     }
 
     // L = fill_triangular(cholesky_scale) * scale[:, None] + diag(scale) (modules.py:535-545).
@@ -949,8 +984,8 @@ struct Block {
         const Smem& m = P.sm;
         const RecF& F = P.rec;
         const int nh = P.nh, nw = P.nw, e = s + 1, ns2 = P.NS + s;
-        lin(L_DRNN, s, true);
-        lin(L_DT1, 0, true); lin(L_DT2, 0, true); lin(L_DT3);
+        lin(L_DRNN, s, true, s + 1);
+        lin(L_DT1, 0, true, s); lin(L_DT2, 0, true, s); lin(L_DT3, 0, false, s);
         for (int r = c.tid(); r < R; r += c.nthreads()) {             // core.py:220-227
             const float so = prm(P.po.d_scale_offset);
             float wh[4];
@@ -969,8 +1004,8 @@ struct Block {
         // element-wise stage reads Hrnn[1] right before the next L_DRNN writes it from a peer block.
         for (int i = c.tid(); i < nh * R; i += c.nthreads()) SQ_SM[m.Hrnn + i] = SQ_SM[m.Hrnn + nh * R + i];
         c.sync();
-        extract_glimpse(false);                                   // discovery passes no mask (core.py:217)
-        encode_glimpse(L_ENC3);
+        extract_glimpse(false, 2 * P.NS + s);                     // discovery passes no mask (core.py:217)
+        encode_glimpse(L_ENC3, 2 * P.NS + s);
         for (int i = c.tid(); i < nw * R; i += c.nthreads()) {        // core.py:216-218
             int j = i / R, r = i % R;
             float wl = SQ_SM[m.Enc + i], ws = SQ_SM[m.Enc + nw * R + i];
@@ -1013,6 +1048,7 @@ struct Block {
             }
         }
         c.sync();
+        stash_copy(S_DISCREC, t_, e, m.DiscOut + e * R, LDE(), F.size);
     }
 
     // discovery priors and the number-of-steps posterior (sqair_modules.py:149-226; modules.py:548-607;
@@ -1028,9 +1064,10 @@ struct Block {
                 SQ_SM[m.RnPrev0 + i] = (s == 0) ? prm(P.po.rn_init_sample + f) : rec(m.DiscOut, s, F.where + f, r);
             }
             c.sync();
+            for (int s = 0; s < NS; ++s) stash_copy(S_RNPREV, t_, s, m.RnPrev0 + s * R, LDS(), 4);
             lin(L_RN1);
             for (int s = 0; s < NS; ++s) {
-                lin(L_RN2, s, true); lin(L_RN3);
+                lin(L_RN2, s, true); lin(L_RN3, 0, false, s);
                 for (int r = c.tid(); r < R; r += c.nthreads()) {
                     float a = 0.f;
 #pragma unroll
@@ -1136,6 +1173,7 @@ struct Block {
             rowacc(7, r) = nsteps;
         }
         c.sync();
+        stash_copy(S_PERM, t_, 0, m.Perm, R, NS);
         // new z_t and the 9 compacted heads
         const size_t trow = (size_t)t * P.rows;
         for (int i = c.tid(); i < F.size * LDS(); i += c.nthreads()) {
@@ -1171,6 +1209,7 @@ struct Block {
             }
         }
         c.sync();
+        for (int j = 0; j < NS; ++j) stash_copy(S_Z, t + 1, j, m.Z + j * R, LDS(), nw + 6);
     }
     // local row r of this block: is it a real row, and its global index (clamped: padding rows recompute the last row).
     // Plain arithmetic on purpose: member arrays indexed with a run-time r would pin the whole object to local memory.
@@ -1185,7 +1224,7 @@ struct Block {
         const int NS = P.NS, nw = P.nw, G = P.cfg.G, W = P.cfg.W, H = P.cfg.H, g = P.g, PX = P.PX;
         const sqair_outputs& o = J.out;
         const size_t trow = (size_t)t * P.rows;
-        for (int s = 0; s < NS; ++s) { lin(L_DEC1, s, true); lin(L_DEC2, 0, true); lin(L_DEC3, s, s + 1 < NS); }
+        for (int s = 0; s < NS; ++s) { lin(L_DEC1, s, true); lin(L_DEC2, 0, true, s); lin(L_DEC3, s, s + 1 < NS); }
         if (o.glimpse && c.rank() == 0)
             for (int i = c.tid(); i < R * NS * g; i += c.nthreads()) {
                 const int px = i % g, s = (i / g) % NS, r = i / (g * NS);
@@ -1366,10 +1405,20 @@ struct Block {
             SQ_SM[m.DIn + nh * R + i] = 0.f;                         // conditioning accumulator
         }
         c.sync();
+        t_ = t;
+        if (stash_ != nullptr) {                                  // state entering the frame, initial slot records
+            for (int s = 0; s < NS; ++s) {
+                stash_copy(S_TST, t, s, m.Tst + s * R, LDS(), nh);
+                stash_copy(S_PST, t, s, m.Pst + s * R, LDS(), nh);
+            }
+            stash_copy(S_PH, t, 0, m.Hrnn, R, nh);
+            stash_copy(S_PROPREC, t, 0, m.PropOut, LDE(), P.rec.size);
+            stash_copy(S_DISCREC, t, 0, m.DiscOut, LDE(), P.rec.size);
+        }
         for (int s = 0; s < NS; ++s) prop_slot(t, s);
         // latent summary: sum_s pres_s * MLP([what_s, where_s]) (sqair_modules.py:368-385,501)
         for (int s = 0; s < NS; ++s) {
-            lin(L_LAT1, s, true); lin(L_LAT2);
+            lin(L_LAT1, s, true); lin(L_LAT2, 0, false, s);
             for (int i = c.tid(); i < nh * R; i += c.nthreads())
                 SQ_SM[m.DIn + nh * R + i] += SQ_SM[m.A1 + i] * rec(m.PropOut, s + 1, P.rec.pres, i % R);
             c.sync();
@@ -1379,9 +1428,12 @@ struct Block {
             for (int s = 0; s < NS; ++s) a += (sigmoidf_(pri(0, s, r)) - 0.5f) / (float)NS;
             SQ_SM[m.Exp + r] = a;
         }
+        stash_copy(S_DIN, t, 0, m.DIn + nh * R, R, nh, nh);          // conditioning (the image encoding follows below)
         lin(L_IMG1, 0, true); lin(L_IMG2);                           // core.py:165, hoisted out of the slot loop
         for (int i = c.tid(); i < nh * R; i += c.nthreads()) SQ_SM[m.Hrnn + i] = prm(P.po.disc_h0 + i / R);
         c.sync();
+        stash_copy(S_EXP, t, 0, m.Exp, R, 1);
+        stash_copy(S_DH, t, 0, m.Hrnn, R, nh);
         for (int s = 0; s < NS; ++s) disc_slot(t, s);
         disc_priors(t);
         choose_latents(t);
@@ -1390,7 +1442,7 @@ struct Block {
     }
 
     SQ_DEV void run() {
-        calls_init(c, prm_);
+        calls_init(c, ltab_);
         init_sequence();
         for (int t = 0; t < P.cfg.T; ++t) frame(t);
     }

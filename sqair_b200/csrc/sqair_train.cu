@@ -1,0 +1,464 @@
+// sqair_train.cu -- CUDA backend of the backward pass (sqair_backward.h) and its C ABI.
+//
+// Kernels: `bwd_stage_kernel<STAGE>` (one thread block per row: the hand-written adjoints of the element-wise stages),
+// `dgrad_kernel` (dX = dY . W^T for M = rows or rows x slots, fp32 FFMA, activation derivative fused into the operand
+// load, input-segment scatter / accumulate fused into the epilogue), `wgrad_kernel` (dW += X^T . dY over M = T x rows x
+// slots on the tensor cores, fp32-faithful tf32 split), column sums, and the packing / unpacking between the reference's
+// variables and the per-layer virtual matrices.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "sqair_backward.h"
+#include "sqair_internal.h"
+
+using namespace sq;
+using sqi::Shape;
+using sqi::fail;
+
+// ---------------------------------------------------------------------------------------------
+// row stages
+// ---------------------------------------------------------------------------------------------
+struct DevEx {
+    int tid, nt;
+    float* scratch;
+    float* red;          // [4][32]
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void sum4(float (&v)[4]) {
+        const int lane = tid & 31, warp = tid >> 5, nw = (nt + 31) >> 5;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float x = v[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) red[q * 32 + warp] = x;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float x = 0.f;
+            for (int w = 0; w < nw; ++w) x += red[q * 32 + w];
+            v[q] = x;
+        }
+        __syncthreads();
+    }
+};
+
+template <int STAGE>
+__global__ void bwd_stage_kernel(const __grid_constant__ BwdCtx c, int t, int s) {
+    extern __shared__ float bw_smem[];
+    __shared__ float red[4 * 32];
+    DevEx ex;
+    ex.tid = threadIdx.x; ex.nt = blockDim.x; ex.scratch = bw_smem; ex.red = red;
+    bw_stage<STAGE>(c, ex, t, s, (int)blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dgrad: dX_seg[m, k - k0] (=|+=) sum_n A[m, n] W[k, n],  A = a * act'(y)   (fp32 FFMA)
+// Block = DG_BM rows x DG_BK input features; the transposed virtual matrix Wt[n][k] makes both operand tiles
+// coalesced.  N is walked in chunks of DG_NC staged in shared memory with register prefetch of the next chunk.
+// ---------------------------------------------------------------------------------------------
+constexpr int DG_BM = 32, DG_BK = 64, DG_NC = 32, DG_THREADS = 256;
+
+struct DgradDev {
+    DgradArgs a;
+    const float* wt;       // [N][K + 1] transposed virtual matrix
+    int ldt;               // K + 1
+};
+
+__device__ __forceinline__ const float* addr_row(const Addr& a, int m, int ny) {
+    return a.p + (size_t)(m / ny) * a.outer + (size_t)(m % ny) * a.inner;
+}
+
+__global__ void __launch_bounds__(DG_THREADS) dgrad_kernel(const __grid_constant__ DgradDev D) {
+    const DgradArgs& A = D.a;
+    __shared__ __align__(16) float As[DG_NC][DG_BM + 2];
+    __shared__ __align__(16) float Ws[DG_NC][DG_BK + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * DG_BM, kb = blockIdx.x * DG_BK;
+    const int tm = tid >> 4, tk = tid & 15;              // 16 x 16 threads: rows 2 tm.., features 4 tk..
+    // operand-load coordinates
+    const int a_m = tid >> 5, a_n = tid & 31;            // A: 8 rows per pass, 4 passes
+    const int w_n = tid >> 6, w_k = tid & 63;            // W: 4 n per pass, 8 passes
+    const float* arow[4];
+    const float* yrow[4];
+    float* drow[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int m = m0 + a_m + 8 * p;
+        const bool ok = m < A.M;
+        arow[p] = ok ? addr_row(A.a, m, A.ny) : nullptr;
+        yrow[p] = (ok && A.y.p) ? addr_row(A.y, m, A.ny) : nullptr;
+        drow[p] = (ok && A.dy.p && blockIdx.x == 0) ? const_cast<float*>(addr_row(A.dy, m, A.ny)) : nullptr;
+    }
+    float acc[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float ra[4], rw[8];
+    auto fetch = [&](int n0) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int n = n0 + a_n;
+            float v = 0.f;
+            if (arow[p] && n < A.N) {
+                v = arow[p][n];
+                if (yrow[p]) v *= act_deriv(A.act, yrow[p][n], A.act_scale, A.act_add);
+                if (drow[p]) drow[p][n] = v;
+            }
+            ra[p] = v;
+        }
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int n = n0 + w_n + 4 * p, k = kb + w_k;
+            rw[p] = (n < A.N && k < A.K) ? __ldg(D.wt + (size_t)n * D.ldt + k) : 0.f;
+        }
+    };
+    const bool has_k = A.nseg > 0 && kb < A.K;
+    if (!has_k && blockIdx.x != 0) return;
+    fetch(0);
+    for (int n0 = 0; n0 < A.N; n0 += DG_NC) {
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < 4; ++p) As[a_n][a_m + 8 * p] = ra[p];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) Ws[w_n + 4 * p][w_k] = rw[p];
+        __syncthreads();
+        if (n0 + DG_NC < A.N) fetch(n0 + DG_NC);
+        if (has_k) {
+#pragma unroll
+            for (int nn = 0; nn < DG_NC; ++nn) {
+                const float2 av = *reinterpret_cast<const float2*>(&As[nn][2 * tm]);
+                const float4 wv = *reinterpret_cast<const float4*>(&Ws[nn][4 * tk]);
+                acc[0][0] += av.x * wv.x; acc[0][1] += av.x * wv.y; acc[0][2] += av.x * wv.z; acc[0][3] += av.x * wv.w;
+                acc[1][0] += av.y * wv.x; acc[1][1] += av.y * wv.y; acc[1][2] += av.y * wv.z; acc[1][3] += av.y * wv.w;
+            }
+        }
+    }
+    if (!has_k) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int k = kb + 4 * tk + j;
+        if (k >= A.K) continue;
+        int si = -1;
+        for (int q = 0; q < A.nseg; ++q)
+            if (k >= A.seg[q].k0 && k < A.seg[q].k1) si = q;
+        if (si < 0) continue;
+        const DgradArgs::Seg& S = A.seg[si];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int m = m0 + 2 * tm + i;
+            if (m >= A.M) continue;
+            float* d = const_cast<float*>(addr_row(S.d, m, A.ny)) + (k - S.k0);
+            if (S.mode == SEGM_STORE) *d = acc[i][j]; else *d += acc[i][j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: dW[k, n] += sum_m X[m, k] dY[m, n]   (tensor cores, tf32 hi/lo split of both operands, four products,
+// fp32 accumulation outside the tensor core -- same arithmetic as the forward layers)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32_(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
+}
+__device__ __forceinline__ void mma_tf32_zero_(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+__device__ __forceinline__ void mma_tf32_(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int WG_T = 64, WG_MC = 32, WG_LD = 72;
+__global__ void __launch_bounds__(128) wgrad_addr_kernel(const __grid_constant__ WgradArgs A, int m_per_block) {
+    __shared__ float Xs[WG_MC * WG_LD], Ys[WG_MC * WG_LD];
+    const int n0 = blockIdx.x * WG_T, k0 = blockIdx.y * WG_T;
+    const int m_begin = blockIdx.z * m_per_block, m_end = min(A.M, m_begin + m_per_block);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int wk = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int cc = threadIdx.x & 63, mm0 = threadIdx.x >> 6;          // loader: column cc, rows mm0, mm0 + 2, ...
+    float acc[2][4][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[a][b][q] = 0.f;
+    for (int m0 = m_begin; m0 < m_end; m0 += WG_MC) {
+        __syncthreads();
+#pragma unroll 4
+        for (int mm = mm0; mm < WG_MC; mm += 2) {
+            const int m = m0 + mm;
+            float xv = 0.f, yv = 0.f;
+            if (m < m_end) {
+                if (k0 + cc < A.K) xv = __ldg(addr_row(A.x, m, A.ny) + k0 + cc);
+                if (n0 + cc < A.N) yv = __ldg(addr_row(A.dy, m, A.ny) + n0 + cc);
+            }
+            Xs[mm * WG_LD + cc] = xv;
+            Ys[mm * WG_LD + cc] = yv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ms = 0; ms < WG_MC; ms += 8) {
+            uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const float* p = Xs + (ms + t) * WG_LD + wk + a * 16 + g;
+                split_tf32_(p[0], ah[a][0], al[a][0]);
+                split_tf32_(p[8], ah[a][1], al[a][1]);
+                split_tf32_(p[4 * WG_LD], ah[a][2], al[a][2]);
+                split_tf32_(p[4 * WG_LD + 8], ah[a][3], al[a][3]);
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const float* p = Ys + (ms + t) * WG_LD + wn + b * 8 + g;
+                split_tf32_(p[0], bh[b][0], bl[b][0]);
+                split_tf32_(p[4 * WG_LD], bh[b][1], bl[b][1]);
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    float d[4];
+                    mma_tf32_zero_(d, al[a], bl[b][0], bl[b][1]);
+                    mma_tf32_(d, al[a], bh[b][0], bh[b][1]);
+                    mma_tf32_(d, ah[a], bl[b][0], bl[b][1]);
+                    mma_tf32_(d, ah[a], bh[b][0], bh[b][1]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[a][b][q] += d[q];
+                }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = k0 + wk + a * 16 + g + (q >> 1) * 8, n = n0 + wn + b * 8 + 2 * t + (q & 1);
+                if (k < A.K && n < A.N) atomicAdd(A.dw + (size_t)k * A.ldw + n, acc[a][b][q]);
+            }
+}
+
+// out[n] += sum_m dY[m, n]: 32 columns x 8 row lanes per block, grid.y splits M
+__global__ void __launch_bounds__(256) colsum_kernel(const __grid_constant__ ColsumArgs A, int m_per_block) {
+    __shared__ float red[8][33];
+    const int col = threadIdx.x & 31, rl = threadIdx.x >> 5, n = blockIdx.x * 32 + col;
+    const int m_begin = blockIdx.y * m_per_block, m_end = min(A.M, m_begin + m_per_block);
+    float a = 0.f;
+    if (n < A.N)
+        for (int m = m_begin + rl; m < m_end; m += 8) a += __ldg(addr_row(A.dy, m, A.ny) + n);
+    red[rl][col] = a;
+    __syncthreads();
+    if (rl == 0 && n < A.N) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += red[q][col];
+        atomicAdd(A.out + n, s);
+    }
+}
+
+__global__ void img_reduce_kernel(const float* __restrict__ dy, float* __restrict__ out, int TB, int K, int nh) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < TB * nh; i += gridDim.x * blockDim.x) {
+        const int b = i / nh, j = i - b * nh;
+        float a = 0.f;
+        for (int k = 0; k < K; ++k) a += dy[((size_t)b * K + k) * nh + j];
+        out[i] = a;
+    }
+}
+
+// pieces of the reference's variables <-> per-layer virtual matrices ([KU + 1][NU] row-major, and transposed)
+struct BPiece {
+    int K, N, src_off, src_ld, NU, ldt;
+    long long dst, dst_t;       // offsets of element (0, 0) of the piece in the row-major / transposed copy
+};
+struct BPieceTab {
+    int n;
+    BPiece p[160];
+};
+
+__global__ void pack_backward_kernel(const __grid_constant__ BPieceTab tab, const float* __restrict__ src, float* __restrict__ bw) {
+    const BPiece& pc = tab.p[blockIdx.y];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pc.K * pc.N; i += gridDim.x * blockDim.x) {
+        const int k = i / pc.N, n = i - k * pc.N;
+        const float v = src[(size_t)pc.src_off + (size_t)k * pc.src_ld + n];
+        atomicAdd(bw + pc.dst + (long long)k * pc.NU + n, v);            // (a bias row may be the sum of two bias vectors)
+        atomicAdd(bw + pc.dst_t + (long long)n * pc.ldt + k, v);
+    }
+}
+
+__global__ void unpack_backward_kernel(const __grid_constant__ BPieceTab tab, const float* __restrict__ dwv, float* __restrict__ d_params) {
+    const BPiece& pc = tab.p[blockIdx.y];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pc.K * pc.N; i += gridDim.x * blockDim.x) {
+        const int k = i / pc.N, n = i - k * pc.N;
+        atomicAdd(d_params + (size_t)pc.src_off + (size_t)k * pc.src_ld + n, dwv[pc.dst + (long long)k * pc.NU + n]);
+    }
+}
+
+__global__ void small_to_params_kernel(const float* __restrict__ small, float* __restrict__ d_params, POff po) {
+    const int i = threadIdx.x;
+    if (i < 10) d_params[po.cholesky + i] += small[SM_CHOL + i];
+    if (i == 10) d_params[po.d_scale_offset] += small[SM_DSO];
+    if (i == 11) d_params[po.p_scale_offset] += small[SM_PSO];
+    if (i == 12) d_params[po.output_scale] += small[SM_OUTSCALE];
+}
+
+static void fill_piece_tab(const Shape& sh, BPieceTab& bt) {
+    memset(&bt, 0, sizeof(bt));
+    bt.n = (int)sh.pieces.size();
+    for (size_t i = 0; i < sh.pieces.size(); ++i) {
+        const Piece& p = sh.pieces[i];
+        const LayerB& LB = sh.plan.LB[p.layer];
+        BPiece& b = bt.p[i];
+        b.K = p.K; b.N = p.N; b.src_off = (int)p.src_off; b.src_ld = p.src_ld; b.NU = LB.NU; b.ldt = LB.KU + 1;
+        b.dst = LB.bw_off + (long long)p.urow0 * LB.NU + p.ucol0;
+        b.dst_t = sh.plan.bw_total + LB.bw_off + (long long)p.ucol0 * (LB.KU + 1) + p.urow0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backend
+// ---------------------------------------------------------------------------------------------
+struct CudaBackend {
+    cudaStream_t st;
+    const Shape* sh;
+    int rows;
+    int scratch_bytes;
+    cudaError_t err = cudaSuccess;
+    long launches = 0;
+
+    void check() {
+        if (err == cudaSuccess) err = cudaGetLastError();
+        ++launches;
+    }
+    template <int STAGE>
+    void stage(const BwdCtx& c, int t, int s) {
+        const int threads = STAGE == BS_CANVAS ? 256 : 128;
+        bwd_stage_kernel<STAGE><<<rows, threads, scratch_bytes, st>>>(c, t, s);
+        check();
+    }
+    void dgrad(const DgradArgs& A) {
+        DgradDev D;
+        D.a = A;
+        D.wt = A.w + sh->plan.bw_total;          // transposed copy sits bw_total floats behind the row-major one
+        D.ldt = A.K + 1;
+        int gx = A.nseg > 0 ? (A.K + DG_BK - 1) / DG_BK : 1;
+        dgrad_kernel<<<dim3(gx, (A.M + DG_BM - 1) / DG_BM), DG_THREADS, 0, st>>>(D);
+        check();
+    }
+    void wgrad(const WgradArgs& A) {
+        const int tiles = ((A.N + WG_T - 1) / WG_T) * ((A.K + WG_T - 1) / WG_T);
+        int msplit = (4 * 148 + tiles - 1) / tiles;
+        const int max_split = (A.M + 4 * WG_MC - 1) / (4 * WG_MC);
+        if (msplit > max_split) msplit = max_split;
+        if (msplit < 1) msplit = 1;
+        const int m_per_block = ((A.M + msplit - 1) / msplit + WG_MC - 1) / WG_MC * WG_MC;
+        msplit = (A.M + m_per_block - 1) / m_per_block;
+        wgrad_addr_kernel<<<dim3((A.N + WG_T - 1) / WG_T, (A.K + WG_T - 1) / WG_T, msplit), 128, 0, st>>>(A, m_per_block);
+        check();
+    }
+    void colsum(const ColsumArgs& A) {
+        const int gx = (A.N + 31) / 32;
+        int msplit = (2 * 148 + gx - 1) / gx;
+        const int max_split = (A.M + 63) / 64;
+        if (msplit > max_split) msplit = max_split;
+        if (msplit < 1) msplit = 1;
+        const int m_per_block = (A.M + msplit - 1) / msplit;
+        colsum_kernel<<<dim3(gx, (A.M + m_per_block - 1) / m_per_block), 256, 0, st>>>(A, m_per_block);
+        check();
+    }
+    void zero(float* p, int64_t n) {
+        if (n <= 0) return;
+        cudaError_t e = cudaMemsetAsync(p, 0, (size_t)n * sizeof(float), st);
+        if (err == cudaSuccess) err = e;
+        ++launches;
+    }
+    void img_reduce(const float* dy, float* out, int TB, int K, int nh) {
+        img_reduce_kernel<<<(TB * nh + 255) / 256, 256, 0, st>>>(dy, out, TB, K, nh);
+        check();
+    }
+    void unpack(const float* dwv, float* d_params) {
+        BPieceTab bt;
+        fill_piece_tab(*sh, bt);
+        unpack_backward_kernel<<<dim3(32, bt.n), 256, 0, st>>>(bt, dwv, d_params);
+        check();
+    }
+    void small_to_params(const float* small, float* d_params, const POff& po) {
+        small_to_params_kernel<<<1, 32, 0, st>>>(small, d_params, po);
+        check();
+    }
+};
+
+static std::string prepare(const sqair_cfg* cfg, Shape& sh, std::vector<ParamEntry>& tab) {
+    std::string e = validate_cfg(*cfg);
+    if (!e.empty()) return e;
+    tab = param_table(*cfg);
+    return sqi::choose_shape(*cfg, tab, sh);
+}
+
+extern "C" {
+
+int sqair_query_train_sizes(const sqair_cfg* cfg, sqair_train_sizes* out) {
+    if (!cfg || !out) return fail(SQAIR_EINVAL, "null argument");
+    Shape sh;
+    std::vector<ParamEntry> tab;
+    std::string e = prepare(cfg, sh, tab);
+    if (!e.empty()) return fail(SQAIR_EINVAL, e);
+    const StashLayout SL = build_stash(*cfg);
+    if (SL.total < 0) return fail(SQAIR_EUNSUPPORTED, "training stash exceeds 2^31 floats");
+    const BwdLayout BL = build_bwd_layout(*cfg, sh.plan);
+    out->stash_floats = SL.total;
+    out->workspace_floats = BL.total;
+    out->backward_param_floats = 2 * sh.plan.bw_total;
+    return SQAIR_OK;
+}
+
+int sqair_pack_backward(const sqair_cfg* cfg, const float* params, float* bw_params, void* stream) {
+    if (!cfg || !params || !bw_params) return fail(SQAIR_EINVAL, "null argument");
+    Shape sh;
+    std::vector<ParamEntry> tab;
+    std::string e = prepare(cfg, sh, tab);
+    if (!e.empty()) return fail(SQAIR_EINVAL, e);
+    if (sh.pieces.size() > 160) return fail(SQAIR_EUNSUPPORTED, "too many variables");
+    cudaStream_t st = (cudaStream_t)stream;
+    BPieceTab bt;
+    fill_piece_tab(sh, bt);
+    CUDA_TRY(cudaMemsetAsync(bw_params, 0, (size_t)2 * sh.plan.bw_total * sizeof(float), st));
+    pack_backward_kernel<<<dim3(32, bt.n), 256, 0, st>>>(bt, params, bw_params);
+    CUDA_TRY(cudaGetLastError());
+    return SQAIR_OK;
+}
+
+int sqair_backward(const sqair_cfg* cfg, const float* params, const float* bw_params, const float* obs, const float* eps_where,
+                   const float* eps_what, const float* stash, const float* d_log_weights, const float* d_discrete_log_prob,
+                   float* workspace, float* d_params, int32_t* n_launches, void* stream) {
+    if (!cfg || !params || !bw_params || !obs || !eps_where || !eps_what || !stash || !d_log_weights || !workspace || !d_params)
+        return fail(SQAIR_EINVAL, "null argument");
+    Shape sh;
+    std::vector<ParamEntry> tab;
+    std::string e = prepare(cfg, sh, tab);
+    if (!e.empty()) return fail(SQAIR_EINVAL, e);
+    const BwdLayout BL = build_bwd_layout(*cfg, sh.plan);
+    BwdInputs in;
+    in.params = params; in.bw = bw_params; in.obs = obs; in.eps_where = eps_where; in.eps_what = eps_what; in.stash = stash;
+    in.d_log_w = d_log_weights; in.d_disc_lp = d_discrete_log_prob; in.ws = workspace; in.d_params = d_params; in.vimco = 1;
+    CudaBackend be;
+    be.st = (cudaStream_t)stream; be.sh = &sh; be.rows = cfg->B * cfg->K;
+    be.scratch_bytes = bw_stage_scratch_floats(*cfg) * (int)sizeof(float);
+    if (be.scratch_bytes > 48 * 1024) return fail(SQAIR_EUNSUPPORTED, "glimpses do not fit the shared memory of the canvas stage");
+    static_assert(sizeof(BwdCtx) <= 4000, "BwdCtx must fit the kernel parameter space");
+    BwdDriver<CudaBackend> drv(be, *cfg, sh.plan, sh.plan.poc, BL, in);
+    drv.param_count_ = tab.back().offset + tab.back().count;
+    drv.run(d_params);
+    if (be.err != cudaSuccess) return sqi::cuda_fail(be.err, "sqair_backward");
+    if (n_launches) *n_launches = (int32_t)be.launches;
+    return SQAIR_OK;
+}
+
+}  // extern "C"

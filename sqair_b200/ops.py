@@ -62,8 +62,10 @@ def alloc_outputs(cfg: SqairCfg, device, names=None):
     return {k: torch.empty(shapes[k], dtype=torch.float32, device=device) for k in (names or OUTPUT_NAMES)}
 
 
-def forward(cfg: SqairCfg, packed: torch.Tensor, obs: torch.Tensor, noise: dict, outputs: dict = None, names=None):
-    """SequentialAIR over a [T,B,H,W] batch (seq.py:69-84); returns {name: [T, B*K, ...] tensor}."""
+def forward(cfg: SqairCfg, packed: torch.Tensor, obs: torch.Tensor, noise: dict, outputs: dict = None, names=None,
+            stash: torch.Tensor = None):
+    """SequentialAIR over a [T,B,H,W] batch (seq.py:69-84); returns {name: [T, B*K, ...] tensor}.  With `stash` (a
+    float32 buffer of `query_train_sizes(cfg).stash_floats`) the kernel also records what `backward` needs."""
     _need_cuda(packed, obs, noise['eps_where'], noise['eps_what'], noise['u_pres'])
     if tuple(obs.shape) != (cfg.T, cfg.B, cfg.H, cfg.W):
         raise ValueError('obs must be [T,B,H,W] = %s, got %s' % ((cfg.T, cfg.B, cfg.H, cfg.W), tuple(obs.shape)))
@@ -78,9 +80,46 @@ def forward(cfg: SqairCfg, packed: torch.Tensor, obs: torch.Tensor, noise: dict,
     for k, v in outputs.items():
         _need_cuda(v)
         setattr(so, k, v.data_ptr())
-    check(_capi.lib().sqair_forward(C.byref(cfg), _ptr(packed), _ptr(obs), _ptr(noise['eps_where']),
-                                    _ptr(noise['eps_what']), _ptr(noise['u_pres']), C.byref(so), _stream()))
+    if stash is None:
+        check(_capi.lib().sqair_forward(C.byref(cfg), _ptr(packed), _ptr(obs), _ptr(noise['eps_where']),
+                                        _ptr(noise['eps_what']), _ptr(noise['u_pres']), C.byref(so), _stream()))
+    else:
+        _need_cuda(stash)
+        if stash.numel() < _capi.query_train_sizes(cfg).stash_floats:
+            raise ValueError('stash buffer too small for this configuration')
+        check(_capi.lib().sqair_forward_train(C.byref(cfg), _ptr(packed), _ptr(obs), _ptr(noise['eps_where']),
+                                              _ptr(noise['eps_what']), _ptr(noise['u_pres']), C.byref(so), _ptr(stash), _stream()))
     return outputs
+
+
+def pack_backward(cfg: SqairCfg, flat: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """Canonical flat parameters -> the parameter copy the backward GEMMs read (once per parameter update)."""
+    _need_cuda(flat)
+    n = _capi.query_train_sizes(cfg).backward_param_floats
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=flat.device)
+    check(_capi.lib().sqair_pack_backward(C.byref(cfg), _ptr(flat), _ptr(out), _stream()))
+    return out
+
+
+def backward(cfg: SqairCfg, flat: torch.Tensor, bw_params: torch.Tensor, obs: torch.Tensor, noise: dict, stash: torch.Tensor,
+             d_log_w: torch.Tensor, d_disc_lp: torch.Tensor = None, workspace: torch.Tensor = None, d_params: torch.Tensor = None):
+    """`opt.compute_gradients(target)` (model.py:160): gradient of the target w.r.t. every variable, in the canonical
+    flat layout.  d_log_w / d_disc_lp: [B, K] from `objective_grad`.  Returns (d_params, kernels enqueued)."""
+    _need_cuda(flat, bw_params, obs, noise['eps_where'], noise['eps_what'], stash, d_log_w)
+    if workspace is None:
+        workspace = torch.empty(_capi.query_train_sizes(cfg).workspace_floats, dtype=torch.float32, device=flat.device)
+    if d_params is None:
+        d_params = torch.empty_like(flat)
+    _need_cuda(workspace, d_params)
+    if d_disc_lp is not None:
+        _need_cuda(d_disc_lp)
+    n = C.c_int32(0)
+    check(_capi.lib().sqair_backward(C.byref(cfg), _ptr(flat), _ptr(bw_params), _ptr(obs), _ptr(noise['eps_where']),
+                                     _ptr(noise['eps_what']), _ptr(stash), _ptr(d_log_w),
+                                     _ptr(d_disc_lp) if d_disc_lp is not None else None, _ptr(workspace), _ptr(d_params),
+                                     C.byref(n), _stream()))
+    return d_params, n.value
 
 
 def objective(log_w_t: torch.Tensor, disc_lp_t: torch.Tensor, B: int, K: int):

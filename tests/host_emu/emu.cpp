@@ -14,6 +14,7 @@
 #include <vector>
 struct float4 { float x, y, z, w; };
 #include "../../sqair_b200/csrc/sqair_device.cuh"
+#include "../../sqair_b200/csrc/sqair_backward.h"
 
 using namespace sq;
 
@@ -80,9 +81,9 @@ extern "C" int emu_smem_floats(const sqair_cfg* cfg, int R, int C) {
     return plan.sm.total;
 }
 
-extern "C" int emu_forward(const sqair_cfg* cfg, const float* params, const float* obs,
-                           const float* eps_where, const float* eps_what, const float* u_pres,
-                           const sqair_outputs* out, int R, int C) {
+static int emu_forward_impl(const sqair_cfg* cfg, const float* params, const float* obs,
+                            const float* eps_where, const float* eps_what, const float* u_pres,
+                            const sqair_outputs* out, int R, int C, float* stash) {
     std::string e = validate_cfg(*cfg);
     if (!e.empty()) { fprintf(stderr, "emu: %s\n", e.c_str()); return -1; }
     auto tab = param_table(*cfg);
@@ -93,7 +94,7 @@ extern "C" int emu_forward(const sqair_cfg* cfg, const float* params, const floa
     if (!e.empty()) { fprintf(stderr, "emu: %s\n", e.c_str()); return -1; }
     std::vector<float> packed(total, 0.f);
     pack_host(plan, tab, pieces, params, packed);
-    Job job{packed.data(), obs, eps_where, eps_what, u_pres, *out, 0};
+    Job job{packed.data(), obs, eps_where, eps_what, u_pres, *out, 0, nullptr, stash};
     switch (R) {
         case 1: run_clusters<1>(plan, job); break;
         case 2: run_clusters<2>(plan, job); break;
@@ -103,6 +104,162 @@ extern "C" int emu_forward(const sqair_cfg* cfg, const float* params, const floa
         case 6: run_clusters<6>(plan, job); break;
         default: fprintf(stderr, "emu: unsupported R=%d\n", R); return -2;
     }
+    return 0;
+}
+
+extern "C" int emu_forward(const sqair_cfg* cfg, const float* params, const float* obs,
+                           const float* eps_where, const float* eps_what, const float* u_pres,
+                           const sqair_outputs* out, int R, int C) {
+    return emu_forward_impl(cfg, params, obs, eps_where, eps_what, u_pres, out, R, C, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward pass on the host: the same stage functions and driver as the CUDA library (sqair_backward.h) with
+// sequential loops in place of kernels
+// ---------------------------------------------------------------------------------------------
+struct HostEx {
+    int tid = 0, nt = 1;
+    float* scratch;
+    void sync() {}
+    void sum4(float (&)[4]) {}
+};
+
+struct HostBackend {
+    const Plan* plan;
+    const std::vector<Piece>* pieces;
+    int rows;
+    std::vector<float> scratch;
+    long n_dgrad = 0, n_stage = 0, n_wgrad = 0;
+    bool warned = false;
+
+    template <int STAGE>
+    void stage(const BwdCtx& c, int t, int s) {
+        ++n_stage;
+        HostEx ex;
+        ex.scratch = scratch.data();
+        for (int row = 0; row < rows; ++row) bw_stage<STAGE>(c, ex, t, s, row);
+    }
+    static float* at(const Addr& a, int m, int ny) { return a.p + (size_t)(m / ny) * a.outer + (size_t)(m % ny) * a.inner; }
+    void dgrad(const DgradArgs& A) {
+        ++n_dgrad;
+        std::vector<float> av(A.N);
+        for (int m = 0; m < A.M; ++m) {
+            const float* a = at(A.a, m, A.ny);
+            const float* y = A.y.p ? at(A.y, m, A.ny) : nullptr;
+            for (int j = 0; j < A.N; ++j) {
+                av[j] = a[j] * (y ? act_deriv(A.act, y[j], A.act_scale, A.act_add) : 1.f);
+                if (av[j] != av[j] && !warned) {
+                    warned = true;
+                    fprintf(stderr, "emu backward: NaN input of dgrad #%ld (layer %d, row %d, col %d; a %g y %g) after %ld stages\n", n_dgrad,
+                            A.layer, m, j, a[j], y ? y[j] : 0.f, n_stage);
+                }
+            }
+            if (A.dy.p) { float* d = at(A.dy, m, A.ny); for (int j = 0; j < A.N; ++j) d[j] = av[j]; }
+            for (int si = 0; si < A.nseg; ++si) {
+                const DgradArgs::Seg& S = A.seg[si];
+                float* d = at(S.d, m, A.ny);
+                for (int k = S.k0; k < S.k1; ++k) {
+                    const float* w = A.w + (size_t)k * A.N;
+                    double acc = 0.0;
+                    for (int j = 0; j < A.N; ++j) acc += (double)av[j] * w[j];
+                    if (S.mode == SEGM_STORE) d[k - S.k0] = (float)acc; else d[k - S.k0] += (float)acc;
+                }
+            }
+        }
+    }
+    void wgrad(const WgradArgs& A) {
+        ++n_wgrad;
+        std::vector<double> acc((size_t)A.K * A.N, 0.0);
+        for (int m = 0; m < A.M; ++m) {
+            const float* x = at(A.x, m, A.ny);
+            const float* d = at(A.dy, m, A.ny);
+            for (int k = 0; k < A.K; ++k) {
+                const double xv = x[k];
+                if (xv == 0.0) continue;
+                double* a = &acc[(size_t)k * A.N];
+                for (int j = 0; j < A.N; ++j) a[j] += xv * d[j];
+            }
+        }
+        for (int k = 0; k < A.K; ++k)
+            for (int j = 0; j < A.N; ++j) A.dw[(size_t)k * A.ldw + j] += (float)acc[(size_t)k * A.N + j];
+    }
+    void colsum(const ColsumArgs& A) {
+        std::vector<double> acc(A.N, 0.0);
+        for (int m = 0; m < A.M; ++m) {
+            const float* d = at(A.dy, m, A.ny);
+            for (int j = 0; j < A.N; ++j) acc[j] += d[j];
+        }
+        for (int j = 0; j < A.N; ++j) A.out[j] += (float)acc[j];
+    }
+    void zero(float* p, int64_t n) { memset(p, 0, (size_t)n * sizeof(float)); }
+    void img_reduce(const float* dy, float* out, int TB, int K, int nh) {
+        for (int i = 0; i < TB; ++i)
+            for (int j = 0; j < nh; ++j) {
+                float a = 0.f;
+                for (int k = 0; k < K; ++k) a += dy[((size_t)i * K + k) * nh + j];
+                out[(size_t)i * nh + j] = a;
+            }
+    }
+    void unpack(const float* dwv, float* d_params) {
+        for (const auto& pc : *pieces) {
+            const LayerB& LB = plan->LB[pc.layer];
+            for (int k = 0; k < pc.K; ++k)
+                for (int j = 0; j < pc.N; ++j)
+                    d_params[pc.src_off + (int64_t)k * pc.src_ld + j] += dwv[LB.bw_off + (int64_t)(pc.urow0 + k) * LB.NU + pc.ucol0 + j];
+        }
+    }
+    void small_to_params(const float* small, float* d_params, const POff& po) {
+        for (int i = 0; i < 10; ++i) d_params[po.cholesky + i] += small[SM_CHOL + i];
+        d_params[po.d_scale_offset] += small[SM_DSO];
+        d_params[po.p_scale_offset] += small[SM_PSO];
+        d_params[po.output_scale] += small[SM_OUTSCALE];
+    }
+};
+
+// canonical parameters -> backward parameter buffer (virtual matrices); same table as sqair_pack_backward
+static void pack_backward_host(const Plan& plan, const std::vector<Piece>& pieces, const float* params, std::vector<float>& bw) {
+    bw.assign((size_t)plan.bw_total, 0.f);
+    for (const auto& pc : pieces) {
+        const LayerB& LB = plan.LB[pc.layer];
+        for (int k = 0; k < pc.K; ++k)
+            for (int j = 0; j < pc.N; ++j)
+                bw[LB.bw_off + (int64_t)(pc.urow0 + k) * LB.NU + pc.ucol0 + j] += params[pc.src_off + (int64_t)k * pc.src_ld + j];
+    }
+}
+
+extern "C" int64_t emu_stash_floats(const sqair_cfg* cfg) { return build_stash(*cfg).total; }
+
+// forward (with stash) + backward on the host.  d_log_w / d_disc_lp: [rows] upstream gradients of the objective.
+extern "C" int emu_forward_backward(const sqair_cfg* cfg, const float* params, const float* obs, const float* eps_where,
+                                    const float* eps_what, const float* u_pres, const sqair_outputs* out, int R, int C,
+                                    const float* d_log_w, const float* d_disc_lp, float* d_params) {
+    const StashLayout SL = build_stash(*cfg);
+    if (SL.total < 0) return -3;
+    std::vector<float> stash((size_t)SL.total, NAN);
+    int rc = emu_forward_impl(cfg, params, obs, eps_where, eps_what, u_pres, out, R, C, stash.data());
+    if (rc) return rc;
+    auto tab = param_table(*cfg);
+    static Plan plan;
+    std::vector<Piece> pieces;
+    int64_t total = 0;
+    std::string e = build_plan(*cfg, 1, 1, plan, tab, pieces, &total);
+    if (!e.empty()) { fprintf(stderr, "emu: %s\n", e.c_str()); return -1; }
+    std::vector<float> bw;
+    pack_backward_host(plan, pieces, params, bw);
+    const BwdLayout BL = build_bwd_layout(*cfg, plan);
+    std::vector<float> ws((size_t)BL.total, NAN);
+    BwdInputs in;
+    in.params = params; in.bw = bw.data(); in.obs = obs; in.eps_where = eps_where; in.eps_what = eps_what;
+    in.stash = stash.data(); in.d_log_w = d_log_w; in.d_disc_lp = d_disc_lp; in.ws = ws.data(); in.d_params = d_params; in.vimco = 1;
+    HostBackend be;
+    be.plan = &plan; be.pieces = &pieces; be.rows = cfg->B * cfg->K;
+    be.scratch.assign(bw_stage_scratch_floats(*cfg), 0.f);
+    BwdDriver<HostBackend> drv(be, *cfg, plan, plan.poc, BL, in);
+    drv.param_count_ = tab.back().offset + tab.back().count;
+    drv.run(d_params);
+    if (getenv("SQAIR_EMU_VERBOSE"))
+        fprintf(stderr, "emu backward: %ld stages, %ld dgrad, %ld wgrad calls; stash %.1f MB, workspace %.1f MB\n", be.n_stage, be.n_dgrad,
+                be.n_wgrad, SL.total * 4e-6, BL.total * 4e-6);
     return 0;
 }
 

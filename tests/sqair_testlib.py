@@ -97,7 +97,8 @@ def emu_lib():
         d = os.path.join(ROOT, 'tests', 'host_emu')
         so = os.path.join(d, 'libsqair_emu.so')
         srcs = [os.path.join(d, 'emu.cpp'), os.path.join(ROOT, 'sqair_b200', 'csrc', 'sqair_device.cuh'),
-                os.path.join(ROOT, 'sqair_b200', 'csrc', 'sqair_core.h'), os.path.join(ROOT, 'include', 'sqair_b200.h')]
+                os.path.join(ROOT, 'sqair_b200', 'csrc', 'sqair_core.h'), os.path.join(ROOT, 'include', 'sqair_b200.h'),
+                os.path.join(ROOT, 'sqair_b200', 'csrc', 'sqair_backward.h')]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-pthread', '-Wno-unknown-pragmas',
                                    '-o', so, srcs[0]])
@@ -124,3 +125,120 @@ def run_emu(cfg: O.Cfg, imgs, params, noise, R, cluster=1):
                                nz['eps_what'].ctypes.data, nz['u_pres'].ctypes.data, C.byref(so), R, cluster)
     assert rc == 0, rc
     return outs
+
+
+# ---------------------------------------------------------------------------------------------
+# gradients: oracle (torch autograd) and the emulated backward pass
+# ---------------------------------------------------------------------------------------------
+def oracle_gradients(cfg, imgs, params, noise, target='auto', double=False):
+    """d target / d every variable by torch autograd through the oracle -> ({name: array}, objective dict).
+    double=True evaluates the restatement in float64 (the trustworthy value of sums with heavy cancellation).
+    Every variable must receive a gradient (model.py:163-166); with the `geom` count prior the variables of the `cat`
+    prior are not part of the reference graph at all and come back as zeros."""
+    obs, nz = torch.from_numpy(imgs), {k: torch.from_numpy(v) for k, v in noise.items()}
+    if double:
+        old = torch.get_default_dtype()
+        torch.set_default_dtype(torch.float64)
+        try:
+            g, obj, missing = O.model_gradients({k: v.double() for k, v in params.items()}, cfg, obs.double(),
+                                                {k: v.double() for k, v in nz.items()}, target)
+        finally:
+            torch.set_default_dtype(old)
+    else:
+        g, obj, missing = O.model_gradients(params, cfg, obs, nz, target)
+    if cfg.disc_prior_type == 'geom':
+        missing = [k for k in missing if 'discover/mlp/' not in k and 'step_prior' not in k]
+    assert not missing, missing
+    return {k: v.numpy() for k, v in g.items()}, {k: v.numpy() for k, v in obj.items()}
+
+
+def objective_grads(log_w_t, disc_lp_t, B, K, vimco=True):
+    """torch restatement of the first backward stage (targets.py:46-75): gradients of the target w.r.t. the rows' summed
+    log weights / discrete log-probs, each [B*K]."""
+    T = log_w_t.shape[0]
+    a = torch.as_tensor(log_w_t).sum(0).reshape(B, K).clone().requires_grad_(True)
+    b = torch.as_tensor(disc_lp_t).sum(0).reshape(B, K).clone().requires_grad_(True)
+    tgt = (O.vimco(a, b, O.iwae(a)) if vimco else -O.iwae(a).mean()) / T
+    ga, gb = torch.autograd.grad(tgt, [a, b], allow_unused=True)
+    gb = torch.zeros_like(a) if gb is None else gb
+    return ga.reshape(-1).numpy().copy(), gb.reshape(-1).numpy().copy()
+
+
+def run_emu_backward(cfg: O.Cfg, imgs, params, noise, R, cluster=1, vimco=None):
+    """Emulated forward (with stash) + backward -> ({name: gradient}, outputs)."""
+    lib = emu_lib()
+    lib.emu_forward_backward.argtypes = [C.POINTER(_capi.SqairCfg)] + [C.c_void_p] * 5 + \
+        [C.POINTER(_capi.SqairOutputs), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.emu_forward_backward.restype = C.c_int
+    vimco = cfg.K > 1 if vimco is None else vimco
+    # upstream gradients from the oracle's own log weights (they match the kernel's to 1e-4; parity-tested separately)
+    want, _ = run_oracle(cfg, imgs, params, noise)
+    gw, gp = objective_grads(want['log_weights_per_timestep'], want['discrete_log_prob'], cfg.B, cfg.K, vimco)
+    ccfg = capi_cfg(cfg)
+    flat = np.ascontiguousarray(O.flatten_params(params, cfg).numpy())
+    shapes = _capi.output_shapes(ccfg)
+    outs = {k: np.full(s, np.nan, dtype=np.float32) for k, s in shapes.items()}
+    so = _capi.SqairOutputs()
+    for k in _capi.OUTPUT_NAMES:
+        setattr(so, k, outs[k].ctypes.data)
+    imgs = np.ascontiguousarray(imgs, dtype=np.float32)
+    nz = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in noise.items()}
+    gw, gp = np.ascontiguousarray(gw, dtype=np.float32), np.ascontiguousarray(gp, dtype=np.float32)
+    dflat = np.full_like(flat, np.nan)
+    rc = lib.emu_forward_backward(C.byref(ccfg), flat.ctypes.data, imgs.ctypes.data, nz['eps_where'].ctypes.data,
+                                  nz['eps_what'].ctypes.data, nz['u_pres'].ctypes.data, C.byref(so), R, cluster,
+                                  gw.ctypes.data, gp.ctypes.data, dflat.ctypes.data)
+    assert rc == 0, rc
+    grads = {k: v.numpy() for k, v in O.unflatten_params(torch.from_numpy(dflat), cfg).items()}
+    return grads, outs
+
+
+def compare_gradients(got: dict, want: dict, rtol=1e-3, atol_rel=2e-4, floor: dict = None):
+    """Per variable: |got - want| <= rtol * |want| + atol_rel * max|want_variable| (model.py:163-166 demands a gradient
+    for every variable: none may be missing).  `floor` (optional, {name: array}): an fp32 evaluation of the same
+    gradient by the oracle; 3 x its own distance from `want` (float64) is added to the tolerance -- the measured fp32
+    noise floor of sums with heavy cancellation (e.g. the scalar scale offsets).  Returns mismatch descriptions."""
+    bad = []
+    for k, w in want.items():
+        g = got.get(k)
+        if g is None:
+            bad.append('%s: missing' % k)
+            continue
+        g, w = np.asarray(g, dtype=np.float64), np.asarray(w, dtype=np.float64)
+        if g.shape != w.shape:
+            bad.append('%s: shape %s vs %s' % (k, g.shape, w.shape))
+            continue
+        scale = np.abs(w).max()
+        tol = rtol * np.abs(w) + atol_rel * scale + 1e-12
+        if floor is not None:
+            tol = tol + 3.0 * np.abs(np.asarray(floor[k], dtype=np.float64) - w).max()
+        err = np.abs(g - w) - tol
+        if not np.isfinite(g).all() or (err > 0).any():
+            i = np.unravel_index(np.argmax(np.where(np.isfinite(err), err, np.inf)), err.shape) if err.ndim else ()
+            bad.append('%s: %d/%d bad, max|want| %.3e, worst at %s got %.6e want %.6e' %
+                       (k, int((err > 0).sum()) + int((~np.isfinite(g)).sum()), g.size, scale, i, g[i], w[i]))
+    return bad
+
+
+def run_cuda_backward(cfg: O.Cfg, imgs, params, noise, vimco=None, return_outputs=False):
+    """The product path: sqair_forward_train -> sqair_objective_grad -> sqair_backward, through the C ABI."""
+    from sqair_b200 import ops
+    dev = torch.device('cuda:0')
+    ccfg = capi_cfg(cfg)
+    vimco = cfg.K > 1 if vimco is None else vimco
+    flat = O.flatten_params(params, cfg).to(dev)
+    packed = ops.pack_params(ccfg, flat)
+    bw = ops.pack_backward(ccfg, flat)
+    ts = _capi.query_train_sizes(ccfg)
+    stash = torch.full((ts.stash_floats,), float('nan'), dtype=torch.float32, device=dev)      # poison: every read must have been written
+    nz = {k: torch.from_numpy(v).to(dev) for k, v in noise.items()}
+    obs = torch.from_numpy(imgs).to(dev)
+    out = ops.forward(ccfg, packed, obs, nz, stash=stash)
+    d_lw, d_lp = ops.objective_grad(out['log_weights_per_timestep'], out['discrete_log_prob'], cfg.B, cfg.K)
+    ws = torch.full((ts.workspace_floats,), float('nan'), dtype=torch.float32, device=dev)
+    d_params, launches = ops.backward(ccfg, flat, bw, obs, nz, stash, d_lw, d_lp if vimco else None, workspace=ws)
+    torch.cuda.synchronize()
+    grads = {k: v.numpy() for k, v in O.unflatten_params(d_params.cpu(), cfg).items()}
+    if return_outputs:
+        return grads, {k: v.cpu().numpy() for k, v in out.items()}, launches
+    return grads
