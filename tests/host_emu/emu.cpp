@@ -132,9 +132,22 @@ struct HostBackend {
     long n_dgrad = 0, n_stage = 0, n_wgrad = 0;
     bool warned = false;
 
+    const float* frame_gw = nullptr;   // debugging aid: per-frame upstream gradients [T][rows] (SQAIR_EMU_FRAME_GW)
+    const float* frame_gp = nullptr;
     template <int STAGE>
     void stage(const BwdCtx& c, int t, int s) {
         ++n_stage;
+        if (frame_gw) {
+            BwdCtx& cc = const_cast<BwdCtx&>(c);
+            cc.gw = frame_gw + (size_t)t * rows;
+            cc.gp = frame_gp + (size_t)t * rows;
+        }
+        if (STAGE == BS_COMPACT && getenv("SQAIR_EMU_DUMP")) {        // debugging aid: d target / d z_t after the decoder
+            char name[256];
+            snprintf(name, sizeof(name), "%s.gz%d.bin", getenv("SQAIR_EMU_DUMP"), t);
+            FILE* f = fopen(name, "wb");
+            if (f) { fwrite(c.gZc, sizeof(float), (size_t)rows * c.n * c.zw, f); fclose(f); }
+        }
         HostEx ex;
         ex.scratch = scratch.data();
         for (int row = 0; row < rows; ++row) bw_stage<STAGE>(c, ex, t, s, row);
@@ -254,6 +267,7 @@ extern "C" int emu_forward_backward(const sqair_cfg* cfg, const float* params, c
     HostBackend be;
     be.plan = &plan; be.pieces = &pieces; be.rows = cfg->B * cfg->K;
     be.scratch.assign(bw_stage_scratch_floats(*cfg), 0.f);
+    if (getenv("SQAIR_EMU_FRAME_GW")) { be.frame_gw = d_log_w; be.frame_gp = d_disc_lp; }
     BwdDriver<HostBackend> drv(be, *cfg, plan, plan.poc, BL, in);
     drv.param_count_ = tab.back().offset + tab.back().count;
     drv.run(d_params);

@@ -27,10 +27,13 @@ CASES = {
 }
 
 
-def _check(cfg, with_floor=True):
+def _check(cfg, with_floor=True, smooth=True):
     assert torch.cuda.is_available()
-    imgs, params, noise = TL.make_inputs(cfg)
-    want, _ = TL.oracle_gradients(cfg, imgs, params, noise, double=True)
+    if smooth:       # small cases: a noise seed without resampler coordinates on a derivative jump (TL.smooth_inputs)
+        imgs, params, noise, want = TL.smooth_inputs(cfg)
+    else:            # full size: ~50 such samples are unavoidable, each moves 1/50 of one row-frame's likelihood term
+        imgs, params, noise = TL.make_inputs(cfg)
+        want, _ = TL.oracle_gradients(cfg, imgs, params, noise, double=True)
     floor = TL.oracle_gradients(cfg, imgs, params, noise)[0] if with_floor else None
     got, outs, launches = TL.run_cuda_backward(cfg, imgs, params, noise, return_outputs=True)
     fwd, _ = TL.run_oracle(cfg, imgs, params, noise)
@@ -53,7 +56,7 @@ def test_backward_parity(name):
 
 def test_full_size_c2_backward_parity():
     """BASELINE configs[1] / configs[2]: T=10, B=32, K=5, n=4, 50x50, VIMCO target."""
-    _check(O.Cfg(T=10, B=32, K=5, n=4))
+    _check(O.Cfg(T=10, B=32, K=5, n=4), smooth=False)
 
 
 def test_backward_is_reproducible_and_workspace_independent():
