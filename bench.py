@@ -12,6 +12,10 @@ rank owns B=32 of them, no data-path collective.
 `value`  : frames/s with inputs resident in HBM (CUDA events around each step, L2 flushed between).
 `e2e`    : same metric through the public plugin API (`sqair_b200.model.Model`-level call chain) with the
            step's frames coming from pinned HOST memory and the ELBO scalars + log-weights read back.
+`train`  : (nested object) the training step of the reference's loop (scripts/experiment.py:150-155,217-218) on the same
+           workload: noise + forward with stash + VIMCO objective + backward + NCCL all-reduce of the flat gradient
+           (11.8 MB, inside the timed region) + RMSProp update + re-pack; weak scaling (B=32 per GPU).
+`train_strong` : BASELINE configs[2] -- the same step with the GLOBAL batch fixed at 32 (B/N sequences per GPU, VIMCO).
 `--impl reference` : the reference's own CPU path.  TF1/Sonnet cannot be installed here, so this
            arm times the oracle (the torch-CPU restatement of the reference graph, kind "port") on
            all host cores, same config / metric.
@@ -158,13 +162,25 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     value = B * w['T'] / dt
     sample = '%d steps of %d sequences x K=%d x T=%d (torch-CPU fp32 oracle, %d threads)' % (args.steps, B, w['K'], w['T'], cores)
+    # training step of the same port: forward + autograd backward of the VIMCO target (no optimiser), bounded sample
+    tcfg = O.Cfg(T=w['T'], B=min(B, 8), K=w['K'], n=w['n'], H=w['H'], W=w['W'])
+    timgs, tparams, tnoise = TL.make_inputs(tcfg, jitter=0.0)
+    TL.oracle_gradients(tcfg, timgs, tparams, tnoise)
+    t0 = time.perf_counter()
+    tsteps = 2
+    for _ in range(tsteps):
+        TL.oracle_gradients(tcfg, timgs, tparams, tnoise)
+    tdt = (time.perf_counter() - t0) / tsteps
+    train = dict(value=tcfg.B * w['T'] / tdt, unit='frames/s', ms_per_step=tdt * 1e3 * (w['B'] / tcfg.B),
+                 step='forward + backward (torch autograd) of the VIMCO target, no optimiser',
+                 sample='%d steps of %d sequences x K=%d x T=%d' % (tsteps, tcfg.B, w['K'], w['T']))
     line = dict(impl='reference', metric=METRIC, value=value, unit='frames/s', n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=dt * 1e3 * (w['B'] / B), higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='f32', data='synthetic',
                 config=dict(workload=WORKLOAD_NAME, **w),
                 cpu_baseline=dict(value=value, unit='frames/s', cores=cores, kind='port', sample=sample),
                 e2e=dict(value=value, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                gpu_launches=0,
+                gpu_launches=0, train=train, train_strong=train,
                 note='reference TF1/Sonnet cannot run here (Python 2 / TF 1.6); this is its op-for-op torch-CPU restatement')
     print(json.dumps(line), flush=True)
 
@@ -187,6 +203,78 @@ def cpu_baseline_sample():
     dt = (time.perf_counter() - t0) / steps
     return dict(value=cfg.B * cfg.T / dt, unit='frames/s', cores=cores, kind='port',
                 sample='%d steps of 8 sequences x K=5 x T=10 of the same workload, torch-CPU fp32 oracle' % steps)
+
+
+
+def train_section(args, dev, world, rank, B_local, flush, label):
+    """Times the training step at B_local sequences per rank; returns a dict (rank 0) or None."""
+    import torch
+    import torch.distributed as dist
+    from sqair_b200 import _capi, optim, parallel
+    from sqair_b200.model import load_synthetic_model
+    w = dict(WORKLOAD, B=B_local)
+    model = load_synthetic_model(device=dev, rank=rank, row_offset=rank * B_local * w['K'], **w)
+    store = model.sequence.param_store(w['H'], w['W'], dev)
+    parallel.broadcast_parameters(store)
+    opt = optim.make_optimizer('rmsprop', optim.make_schedule(1e-5, '4,6,10', 2000000))     # release_models/mnist_mlp/1/flags.json
+    obs_host = model.synthetic_obs_host()
+    obs_dev = obs_host.to(dev)
+    n_global = B_local * world
+    ar_ev = []
+
+    def step(obs, i, timed_ar=False):
+        gvs = model.compute_gradients(obs, seed=5000 + i)
+        if timed_ar:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        parallel.allreduce_flat_gradient(gvs.flat_grad, B_local, n_global)
+        if timed_ar:
+            b.record(); ar_ev.append((a, b))
+        opt.apply_gradients(gvs)
+        store.packed(model.cfg); store.backward_params(model.cfg)        # re-pack now: it belongs to this step
+        return gvs.objective['scalars']
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(obs_dev, i)
+        step(obs_host.to(dev, non_blocking=True), i).cpu()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        sc = step(obs_dev, 100 + i, timed_ar=True)
+        ev[i][1].record()
+    barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    ar_ms = sum(a.elapsed_time(b) for a, b in ar_ev) / args.steps
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        sc = step(obs_host.to(dev, non_blocking=True), 200 + i).cpu()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    finite = bool(torch.isfinite(sc[:5]).all())
+    times = torch.tensor([total_ms, e2e_ms, ar_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, ar_ms = [float(x) for x in times.cpu()]
+    frames = n_global * w['T'] * args.steps
+    ts = _capi.query_train_sizes(model.cfg)
+    del model
+    if rank != 0:
+        return None
+    return dict(step='noise + forward(stash) + objective + backward + all-reduce(flat gradient, NCCL) + RMSProp + re-pack',
+                value=frames / (total_ms * 1e-3), unit='frames/s', ms_per_step=total_ms / args.steps,
+                scaling=label, sequences_per_gpu=B_local, global_batch=n_global,
+                allreduce_ms=ar_ms, allreduce_bytes=int(store.flat.numel() * 4), collective='NCCL all_reduce(sum) fp32' if world > 1 else 'none (1 rank)',
+                e2e=dict(value=frames / (e2e_ms * 1e-3), unit='frames/s', h2d_bytes_per_step=int(obs_host.numel() * 4),
+                         d2h_bytes_per_step=int(4 * _capi.OBJ_N)),
+                stash_bytes=int(ts.stash_floats * 4), finite=finite, target='VIMCO / T (model.py:150-158)',
+                optimizer='RMSProp(lr 1e-5 piecewise /3, momentum .9)')
 
 
 def run_cuda(args):
@@ -266,6 +354,15 @@ def run_cuda(args):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms, kern_ms = [float(x) for x in times.cpu()]
+    last_scalars = model.last_scalars.cpu()
+    # ---- training step (weak scaling) and BASELINE configs[2] (global batch 32 split over the ranks, VIMCO)
+    train = train_strong = None
+    if not args.no_train:
+        train = train_section(args, dev, world, rank, w['B'], flush, 'weak')
+        if world > 1 and w['B'] % world == 0:
+            train_strong = train_section(args, dev, world, rank, w['B'] // world, flush, 'strong')
+        elif rank == 0:
+            train_strong = dict(train, scaling='strong', note='identical to `train` at one rank')
     frames = w['B'] * w['T'] * world * args.steps
     value = frames / (total_ms * 1e-3)
     if rank == 0:
@@ -292,7 +389,7 @@ def run_cuda(args):
                                   frac=achieved / peaks['hbm_gbs'], traffic=traffic, peak_source=which,
                                   kernel='sqair_sequence_kernel', kernel_ms=kern_ms, algorithmic_bytes=alg,
                                   note='latency-bound dependent chain of small dense layers; see DESIGN.md'),
-                    elbo_iwae=float(model.last_scalars[1]))
+                    elbo_iwae=float(last_scalars[1]), train=train, train_strong=train_strong)
         # tensor-side view of the same launch: algorithmic FLOPs (11.09 M MAC per particle-frame at n=4) over
         # the kernel time, against the measured sustained bf16 peak (the kernel computes 4-product TF32 in fp32)
         flops = 2 * 11092860.0 * w['B'] * w['K'] * w['T']
@@ -316,6 +413,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
+    ap.add_argument('--no-train', action='store_true', help='skip the training-step sections')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU oracle sample (profiling runs)')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -171,6 +171,18 @@ int sqair_backward(const sqair_cfg* cfg, const float* params, const float* bw_pa
                    const float* d_log_weights, const float* d_discrete_log_prob,
                    float* workspace, float* d_params, int32_t* n_launches, void* stream);
 
+/* Optimiser step on the flat canonical buffers: `opt.apply_gradients(gvs)` of the reference's training loop
+ * (scripts/experiment.py:138-146,153-155) with TensorFlow 1.x update rules.  kind = SQAIR_OPT_*:
+ *   RMSPROP  (hyper_a = decay 0.9, hyper_b = momentum 0.9, epsilon 1e-10; slot0 = mean square, initialised to ONE as
+ *            tf.train.RMSPropOptimizer does, slot1 = momentum, zero),
+ *   ADAM     (hyper_a = beta1, hyper_b = beta2, epsilon 1e-8; `lr` must already carry the bias correction
+ *            sqrt(1 - beta2^t) / (1 - beta1^t); slots m, v zero),
+ *   MOMENTUM (hyper_a = momentum; slot0 = accumulator), SGD (no slots).
+ * The gradient used is grad_scale * grad + l2_weight * param (targets.py:31-35 l2_reg).  In place, asynchronous. */
+enum { SQAIR_OPT_RMSPROP = 0, SQAIR_OPT_ADAM = 1, SQAIR_OPT_MOMENTUM = 2, SQAIR_OPT_SGD = 3 };
+int sqair_optimizer_update(int32_t kind, float* params, const float* grad, float* slot0, float* slot1, int64_t n, float lr,
+                           float hyper_a, float hyper_b, float epsilon, float grad_scale, float l2_weight, void* stream);
+
 /* Weight gradient of one dense layer (the GEMM-shaped part of the backward pass): dW [K,N] (+)= X^T dY for
  * the stashed layer inputs X [M,K] and output gradients dY [M,N], M = rows x frames x slots, all row-major fp32.
  * fp32-faithful on the tensor cores (tf32 hi/lo split of both operands, four products, per-k-step fp32 accumulation).

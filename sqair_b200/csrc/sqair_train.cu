@@ -6,6 +6,7 @@
 // slots on the tensor cores, fp32-faithful tf32 split), column sums, and the packing / unpacking between the reference's
 // variables and the per-layer virtual matrices.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <math.h>
 #include <mutex>
 #include <string>
@@ -309,6 +310,43 @@ __global__ void small_to_params_kernel(const float* __restrict__ small, float* _
     if (i == 12) d_params[po.output_scale] += small[SM_OUTSCALE];
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// optimiser step on the flat buffers (scripts/experiment.py:138-146,155: opt.apply_gradients).  TF 1.x update rules:
+//   rmsprop : ms += (1 - decay)(g^2 - ms);  mom = momentum mom + lr g / sqrt(ms + eps);  w -= mom   (slots: ms = 1, mom = 0)
+//   adam    : m += (1 - b1)(g - m);  v += (1 - b2)(g^2 - v);  w -= lr_t m / (sqrt(v) + eps),  lr_t = lr sqrt(1 - b2^t) / (1 - b1^t)
+//   momentum: acc = momentum acc + g;  w -= lr acc          sgd: w -= lr g
+// with g = grad_scale * grad + l2 * w  (targets.l2_reg: weight * sum_v l2_loss(v), gradient weight * v).
+// ---------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) optimizer_kernel(float* __restrict__ w, const float* __restrict__ grad, float* __restrict__ s0,
+                                                        float* __restrict__ s1, int64_t n, float lr, float a, float b, float eps,
+                                                        float grad_scale, float l2) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float wv = w[i];
+        const float g = grad_scale * grad[i] + l2 * wv;
+        if (KIND == SQAIR_OPT_RMSPROP) {
+            float ms = s0[i], mom = s1[i];
+            ms += (g * g - ms) * (1.f - a);
+            mom = mom * b + (g * lr) / sqrtf(ms + eps);
+            s0[i] = ms; s1[i] = mom;
+            w[i] = wv - mom;
+        } else if (KIND == SQAIR_OPT_ADAM) {
+            float m = s0[i], v = s1[i];
+            m += (g - m) * (1.f - a);
+            v += (g * g - v) * (1.f - b);
+            s0[i] = m; s1[i] = v;
+            w[i] = wv - (m * lr) / (sqrtf(v) + eps);
+        } else if (KIND == SQAIR_OPT_MOMENTUM) {
+            const float acc = s0[i] * a + g;
+            s0[i] = acc;
+            w[i] = wv - lr * acc;
+        } else {
+            w[i] = wv - lr * g;
+        }
+    }
+}
+
 static void fill_piece_tab(const Shape& sh, BPieceTab& bt) {
     memset(&bt, 0, sizeof(bt));
     bt.n = (int)sh.pieces.size();
@@ -458,6 +496,25 @@ int sqair_backward(const sqair_cfg* cfg, const float* params, const float* bw_pa
     drv.run(d_params);
     if (be.err != cudaSuccess) return sqi::cuda_fail(be.err, "sqair_backward");
     if (n_launches) *n_launches = (int32_t)be.launches;
+    return SQAIR_OK;
+}
+
+int sqair_optimizer_update(int32_t kind, float* params, const float* grad, float* slot0, float* slot1, int64_t n, float lr,
+                           float hyper_a, float hyper_b, float epsilon, float grad_scale, float l2_weight, void* stream) {
+    if (!params || !grad || n < 0) return fail(SQAIR_EINVAL, "null argument");
+    if ((kind == SQAIR_OPT_RMSPROP || kind == SQAIR_OPT_ADAM) && (!slot0 || !slot1)) return fail(SQAIR_EINVAL, "optimiser slots missing");
+    if (kind == SQAIR_OPT_MOMENTUM && !slot0) return fail(SQAIR_EINVAL, "optimiser slots missing");
+    if (n == 0) return SQAIR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    switch (kind) {
+        case SQAIR_OPT_RMSPROP: optimizer_kernel<SQAIR_OPT_RMSPROP><<<blocks, 256, 0, st>>>(params, grad, slot0, slot1, n, lr, hyper_a, hyper_b, epsilon, grad_scale, l2_weight); break;
+        case SQAIR_OPT_ADAM: optimizer_kernel<SQAIR_OPT_ADAM><<<blocks, 256, 0, st>>>(params, grad, slot0, slot1, n, lr, hyper_a, hyper_b, epsilon, grad_scale, l2_weight); break;
+        case SQAIR_OPT_MOMENTUM: optimizer_kernel<SQAIR_OPT_MOMENTUM><<<blocks, 256, 0, st>>>(params, grad, slot0, slot1, n, lr, hyper_a, hyper_b, epsilon, grad_scale, l2_weight); break;
+        case SQAIR_OPT_SGD: optimizer_kernel<SQAIR_OPT_SGD><<<blocks, 256, 0, st>>>(params, grad, slot0, slot1, n, lr, hyper_a, hyper_b, epsilon, grad_scale, l2_weight); break;
+        default: return fail(SQAIR_EINVAL, "unknown optimiser kind");
+    }
+    CUDA_TRY(cudaGetLastError());
     return SQAIR_OK;
 }
 

@@ -7,6 +7,20 @@ import torch
 from . import _capi, ops
 
 
+class Target(object):
+    """What `Model.make_target` hands to `opt.compute_gradients`: the value of the training target and the backward pass
+    that differentiates it.  float(target) / target.value give the scalar."""
+
+    def __init__(self, model, value, l2_reg):
+        self.model, self.value, self.l2_reg = model, value, l2_reg
+
+    def compute_gradients(self):
+        return self.model.compute_gradients(l2_reg=self.l2_reg)
+
+    def __float__(self):
+        return float(self.value)
+
+
 class Model(object):
     VI_TARGETS = 'iwae reinforce'.split()
     TARGETS = VI_TARGETS
@@ -39,7 +53,7 @@ class Model(object):
             obs = obs[..., 0]
         out = self.sequence(obs, k_particles=self.k_particles, seed=seed, row_offset=self._row_offset, noise=noise,
                             kernel_events=kernel_events)
-        obj = ops.objective(out['log_weights_per_timestep'], out['discrete_log_prob'], self.batch_size, self.k_particles)
+        obj = ops.objective(out['log_weights_per_timestep'], out['discrete_log_prob'], int(obs.shape[1]), self.k_particles)
         return obs, out, obj
 
     def step(self, obs, seed=0, noise=None, kernel_events=None):
@@ -51,6 +65,7 @@ class Model(object):
         return dict(scalars=obj['scalars'], log_weights=obj['log_weights'], outputs=out)
 
     def _build(self, noise=None):
+        self._noise = noise                       # explicit draws (parity tests); None = counter-based from the seed
         obs, out, obj = self._run(self.obs, self._seed, noise)
         self.outputs = out
         self.__dict__.update(out)                                                  # model.py:86
@@ -88,15 +103,64 @@ class Model(object):
 
     # ------------------------------------------------------------------------------------------
     def make_target(self, opt=None, n_train_itr=None, l2_reg=0.):
-        """model.py:150-168: VIMCO target / T (+ L2).  Returns (target, gvs); gradients (`gvs`) need the
-        backward kernels, which this build does not have yet -> None when no optimiser is given."""
-        if opt is not None:
-            raise NotImplementedError('gradient computation (opt.compute_gradients) is not implemented in this build')
-        target = self._vimco_target                       # discrete_log_prob always exists (model.py:152-154)
+        """model.py:150-168: target = VIMCO(log_weights, sum_t discrete_log_prob, elbo_iwae_per_example) / T + L2 and
+        `gvs = opt.compute_gradients(target)` -- one (gradient, variable) pair for EVERY trainable variable (asserted, as
+        model.py:162-166 does).  The gradient comes from the backward pass of the CUDA library on the batch and draws the
+        model was built on.  Without an optimiser only the value is returned (gvs = None)."""
+        store = self.sequence.param_store(self.img_size[0], self.img_size[1], self.device)
+        # discrete_log_prob always exists (model.py:152-154); at K = 1 the VIMCO baseline divides by K - 1 = 0
+        # (targets.py:55) and the usable target is the -elbo_iwae branch (model.py:156)
+        value = self._vimco_target if self.k_particles > 1 else self._iwae_target
         if l2_reg != 0.:
-            store = self.sequence.param_store(self.img_size[0], self.img_size[1], self.device)
-            target = target + l2_reg * 0.5 * (store.flat ** 2).sum()
-        return target, None
+            value = value + l2_reg * 0.5 * (store.flat ** 2).sum()                  # targets.py:31-35
+        if opt is None:
+            return value, None
+        target = Target(self, value, l2_reg)
+        gvs = opt.compute_gradients(target)
+        assert len(gvs) == len(store.table)
+        for g, (name, v) in zip(gvs, gvs.names):
+            assert g[0] is not None, 'Gradient for variable {} is None'.format(name)
+        return target, gvs
+
+    def compute_gradients(self, obs=None, seed=None, noise=None, l2_reg=0.):
+        """Forward (with stash) + objective + backward on `obs` (default: the batch the model was built on).
+        Returns GradsAndVars; `.flat_grad` is the flat gradient of THIS process's batch-mean target."""
+        from .optim import GradsAndVars
+        if obs is None:                           # the batch (and draws) the model was built on
+            obs, noise = self.obs, (self._noise if noise is None else noise)
+        obs = obs.to(self.device, non_blocking=True)
+        seed = self._seed if seed is None else seed
+        if int(obs.shape[1]) != self.batch_size or int(obs.shape[0]) != self.n_timesteps:
+            raise ValueError('batch of shape %s does not match the model (T=%d, B=%d)' %
+                             (tuple(obs.shape), self.n_timesteps, self.batch_size))
+        out, obj, flat_grad = self.sequence.forward_backward(obs, k_particles=self.k_particles, noise=noise, seed=seed,
+                                                             row_offset=self._row_offset)
+        store = self.sequence.param_store(self.img_size[0], self.img_size[1], self.device)
+        if l2_reg != 0.:
+            flat_grad.add_(store.flat, alpha=float(l2_reg))
+        self.outputs, self.last_scalars = out, obj['scalars']
+        variables = store.variables()
+        gvs = GradsAndVars()
+        for name, (shape, off) in store.table.items():
+            n = 1
+            for d in shape:
+                n *= d
+            gvs.append((flat_grad[off:off + n].reshape(shape), variables[name]))
+        gvs.flat_grad, gvs.store, gvs.names = flat_grad, store, list(variables.items())
+        gvs.objective = obj
+        return gvs
+
+    def train_step(self, obs, opt, seed=0, global_step=None, l2_reg=0., group=None, n_global=None):
+        """One iteration of the reference's training loop (scripts/experiment.py:150-155,217-218): gradients of the
+        target on `obs`, data-parallel mean over the ranks of `group` (ONE all-reduce of the flat gradient, NCCL), the
+        optimiser update and the re-pack of the kernel-side parameter copies.  Returns the objective scalars
+        (device tensor: elbo_vae, elbo_iwae, ess, vimco_target, iwae_target)."""
+        from . import parallel
+        gvs = self.compute_gradients(obs, seed, l2_reg=l2_reg)
+        n_global = self.batch_size * parallel.world_size(group) if n_global is None else n_global
+        parallel.allreduce_flat_gradient(gvs.flat_grad, self.batch_size, n_global, group)
+        opt.apply_gradients(gvs, global_step)
+        return gvs.objective['scalars']
 
     def resample(self, *args, **kwargs):
         axis = kwargs.pop('axis', -1)
@@ -127,7 +191,7 @@ class Model(object):
         return self._host_obs
 
 
-def load_synthetic_model(device, rank=0, T=10, B=32, K=5, n=4, H=50, W=50, seed=1234):
+def load_synthetic_model(device, rank=0, T=10, B=32, K=5, n=4, H=50, W=50, seed=1234, row_offset=0):
     """Builds the reference's MNIST model (configs/mlp_mnist_model.py wiring, default flags) on synthetic
     moving-sprite frames of the requested shape; used by bench.py and examples."""
     import numpy as np
@@ -140,5 +204,6 @@ def load_synthetic_model(device, rank=0, T=10, B=32, K=5, n=4, H=50, W=50, seed=
     host = torch.from_numpy(imgs).pin_memory()
     mean_img = imgs.mean((0, 1))
     model = config.load(host.to(device), None, None, mean_img=mean_img)
+    model._row_offset = row_offset              # global index of this shard's first row: keys the counter-based draws
     model._host_obs = host
     return model

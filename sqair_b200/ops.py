@@ -28,13 +28,15 @@ def _need_cuda(*tensors):
             raise ValueError('sqair_b200 expects contiguous float32 CUDA tensors (no CPU fallback exists)')
 
 
-def pack_params(cfg: SqairCfg, flat: torch.Tensor) -> torch.Tensor:
+def pack_params(cfg: SqairCfg, flat: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
     """Canonical flat parameter vector (TF variable order) -> kernel-side buffer."""
     _need_cuda(flat)
     sizes = query_sizes(cfg)
     if flat.numel() != sizes.param_count:
         raise ValueError('expected %d parameters, got %d' % (sizes.param_count, flat.numel()))
-    packed = torch.empty(sizes.packed_floats, dtype=torch.float32, device=flat.device)
+    packed = out if out is not None else torch.empty(sizes.packed_floats, dtype=torch.float32, device=flat.device)
+    if packed.numel() != sizes.packed_floats:
+        raise ValueError('packed buffer has the wrong size')
     check(_capi.lib().sqair_pack_params(C.byref(cfg), _ptr(flat), _ptr(packed), _stream()))
     return packed
 
@@ -120,6 +122,21 @@ def backward(cfg: SqairCfg, flat: torch.Tensor, bw_params: torch.Tensor, obs: to
                                      _ptr(d_disc_lp) if d_disc_lp is not None else None, _ptr(workspace), _ptr(d_params),
                                      C.byref(n), _stream()))
     return d_params, n.value
+
+
+def optimizer_update(kind, params, grad, slot0, slot1, lr, hyper_a, hyper_b, epsilon, grad_scale=1., l2_weight=0.):
+    """One optimiser step on the flat canonical buffers, in place (scripts/experiment.py:138-155; TF 1.x update rules)."""
+    _need_cuda(params, grad)
+    if grad.numel() != params.numel():
+        raise ValueError('gradient and parameter buffers differ in size')
+    for s in (slot0, slot1):
+        if s is not None:
+            _need_cuda(s)
+    check(_capi.lib().sqair_optimizer_update(int(kind), _ptr(params), _ptr(grad), _ptr(slot0) if slot0 is not None else None,
+                                             _ptr(slot1) if slot1 is not None else None, params.numel(), float(lr),
+                                             float(hyper_a), float(hyper_b), float(epsilon), float(grad_scale),
+                                             float(l2_weight), _stream()))
+    return params
 
 
 def objective(log_w_t: torch.Tensor, disc_lp_t: torch.Tensor, B: int, K: int):

@@ -28,12 +28,27 @@ def combine_batch_means(local_means, n_local, group=None):
     return (buf[:-1] / buf[-1]).to(local_means.dtype).reshape(local_means.shape)
 
 
+def world_size(group=None):
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
 def allreduce_flat_gradient(flat_grad, n_local, n_global, group=None):
     """The one collective of a training step: every rank holds the gradient of ITS shard's batch mean in
-    the flat parameter layout (`sqair_param_layout` order); the global-batch gradient is sum_r grad_r * n_r / n_global.
-    In place, one all-reduce (NCCL over NVLink on the GPU box, gloo in the CPU tests).  The backward kernels that
-    produce `flat_grad` are not built yet; the objective-side inputs are (`ops.objective_grad`)."""
-    flat_grad.mul_(float(n_local) / float(n_global))
-    if dist.is_available() and dist.is_initialized():
+    the flat parameter layout (`sqair_param_layout` order, from `sqair_backward`); the global-batch gradient is
+    sum_r grad_r * n_r / n_global.  In place, one all-reduce (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        if n_local != n_global:
+            flat_grad.mul_(float(n_local) / float(n_global))
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    elif n_local != n_global:
+        flat_grad.mul_(float(n_local) / float(n_global))
     return flat_grad
+
+
+def broadcast_parameters(store, src=0, group=None):
+    """Replicas start from rank `src`'s variables (data-parallel training keeps them identical afterwards because every
+    rank applies the same all-reduced gradient)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(store.flat, src=src, group=group)
+        store.mark_dirty()
+    return store

@@ -68,20 +68,32 @@ class ParamStore(object):
     def __init__(self, cfg, device, seed=42, spec=None):
         self.cfg, self.device = cfg, device
         self.table = table(cfg)
+        spec = dict(spec or {})
+        spec.setdefault('where_mean', tuple(cfg.where_mean))
+        spec.setdefault('where_std', tuple(cfg.where_std))
         self.flat = torch.from_numpy(initial_values(cfg, seed, spec)).to(device)
-        self._version, self._packed = 0, {}
+        self._version, self._packed, self._bw = 0, {}, {}
+
+    def variables(self):
+        """name -> VIEW into the flat buffer (in-place writes must be followed by `mark_dirty()`)."""
+        return OrderedDict((n, self.flat[o:o + int(np.prod(s))].reshape(s)) for n, (s, o) in self.table.items())
 
     def state_dict(self):
-        return OrderedDict((n, self.flat[o:o + int(np.prod(s))].reshape(s)) for n, (s, o) in self.table.items())
+        """name -> copy of the variable (checkpoint semantics: later updates do not alias into the returned tensors)."""
+        return OrderedDict((n, v.clone()) for n, v in self.variables().items())
+
+    def mark_dirty(self):
+        """The flat buffer was modified in place (optimiser step, checkpoint load): kernel-side copies are stale."""
+        self._version += 1
 
     def load_state_dict(self, sd):
         for n, (s, o) in self.table.items():
             self.flat[o:o + int(np.prod(s))].copy_(torch.as_tensor(sd[n], dtype=torch.float32).reshape(-1))
-        self._version += 1
+        self.mark_dirty()
 
     def load_flat(self, flat):
         self.flat.copy_(torch.as_tensor(flat, dtype=torch.float32).reshape(-1))
-        self._version += 1
+        self.mark_dirty()
 
     def packed(self, cfg=None):
         """Kernel-side copy for a call with configuration `cfg` (the packed layout depends on the launch shape the
@@ -91,6 +103,17 @@ class ParamStore(object):
         key = (s.cluster_size, s.packed_floats, cfg.n)
         hit = self._packed.get(key)
         if hit is None or hit[0] != self._version:
-            hit = (self._version, ops.pack_params(cfg, self.flat))
+            buf = hit[1] if hit is not None else None          # re-pack into the same buffer (training: every step)
+            hit = (self._version, ops.pack_params(cfg, self.flat, out=buf))
             self._packed[key] = hit
+        return hit[1]
+
+    def backward_params(self, cfg=None):
+        """Parameter copy read by the backward GEMMs (`sqair_pack_backward`), cached like `packed`."""
+        cfg = cfg or self.cfg
+        key = (_capi.query_train_sizes(cfg).backward_param_floats, cfg.n)
+        hit = self._bw.get(key)
+        if hit is None or hit[0] != self._version:
+            hit = (self._version, ops.pack_backward(cfg, self.flat, out=hit[1] if hit is not None else None))
+            self._bw[key] = hit
         return hit[1]

@@ -27,6 +27,7 @@ class SequentialAIR(object):
         self._discover, self._propagate = discover, propagate
         self._spec = self._read_architecture()
         self._stores = {}
+        self._train_bufs = {}
 
     # ---- architecture -> kernel configuration ----------------------------------------------------
     def _read_architecture(self):
@@ -102,3 +103,42 @@ class SequentialAIR(object):
         if kernel_events is not None:
             kernel_events[1].record()
         return AttrDict(out)
+
+    # ---- the operator with its gradient (training) -------------------------------------------------
+    def _train_buffers(self, cfg, device):
+        """Stash / workspace / gradient / noise / output buffers of one call shape, allocated once."""
+        key = (cfg.T, cfg.B, cfg.K, cfg.H, cfg.W, str(device))
+        if key not in self._train_bufs:
+            ts = _capi.query_train_sizes(cfg)
+            store = self.param_store(cfg.H, cfg.W, device)
+            self._train_bufs[key] = AttrDict(
+                stash=torch.empty(ts.stash_floats, dtype=torch.float32, device=device),
+                workspace=torch.empty(ts.workspace_floats, dtype=torch.float32, device=device),
+                d_params=torch.empty_like(store.flat), noise=ops.alloc_noise(cfg, device),
+                outputs=ops.alloc_outputs(cfg, device))
+        return self._train_bufs[key]
+
+    def forward_backward(self, obs, k_particles=1, noise=None, seed=0, row_offset=0, vimco=None):
+        """Forward pass that keeps what the adjoint needs, particle objective, and the gradient of the training target
+        (VIMCO / T when K > 1, else -elbo_iwae / T: model.py:150-158) w.r.t. every variable -- the work of
+        `opt.compute_gradients(target)` (model.py:160).  Returns (outputs, objective dict, flat gradient in
+        `sqair_param_layout` order).  The returned tensors live in per-shape buffers that the next call overwrites."""
+        if obs.dim() == 5:
+            if obs.shape[-1] != 1:
+                raise NotImplementedError('multi-channel frames')
+            obs = obs[..., 0]
+        obs = obs.contiguous()
+        T, B, H, W = obs.shape
+        cfg = self.make_cfg(T, B, k_particles, H, W)
+        store = self.param_store(H, W, obs.device)
+        buf = self._train_buffers(cfg, obs.device)
+        if noise is None:
+            noise = ops.fill_noise(cfg, seed, row_offset, noise=buf.noise)
+        vimco = k_particles > 1 if vimco is None else vimco
+        out = ops.forward(cfg, store.packed(cfg), obs, noise, buf.outputs, stash=buf.stash)
+        lw, lp = out['log_weights_per_timestep'], out['discrete_log_prob']
+        obj = ops.objective(lw, lp, B, k_particles)
+        d_lw, d_lp = ops.objective_grad(lw, lp, B, k_particles)
+        d_params, _ = ops.backward(cfg, store.flat, store.backward_params(cfg), obs, noise, buf.stash, d_lw,
+                                   d_lp if vimco else None, workspace=buf.workspace, d_params=buf.d_params)
+        return AttrDict(out), obj, d_params

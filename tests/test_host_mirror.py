@@ -97,3 +97,19 @@ def test_shard_ranges_cover_batch():
         assert sum(c for _, c in got) == n
         assert all(got[i][0] + got[i][1] == got[i + 1][0] for i in range(w - 1))
     assert parallel.row_offset(32, 8, 3, 5) == 60
+
+
+def test_learning_rate_schedule_matches_the_training_script():
+    """scripts/experiment.py:128-136: stages '4,6,10' of train_itr, the rate divided by 3 at each boundary
+    (tf.train.piecewise_constant: the old value holds AT the boundary step)."""
+    from sqair_b200 import optim
+    lr = optim.make_schedule(1e-5, '4,6,10', 2000000)          # release_models/mnist_mlp/1/flags.json
+    assert lr(0) == pytest.approx(1e-5) and lr(400000) == pytest.approx(1e-5)
+    assert lr(400001) == pytest.approx(1e-5 / 3) and lr(1000000) == pytest.approx(1e-5 / 3)
+    assert lr(1000001) == pytest.approx(1e-5 / 9) and lr(5000000) == pytest.approx(1e-5 / 9)
+    assert optim.make_schedule(3e-4, '', 10)(7) == pytest.approx(3e-4)
+    with pytest.raises(ValueError):
+        optim.piecewise_constant(0, [1, 2], [1.0])
+    with pytest.raises(ValueError):
+        optim.make_optimizer('lbfgs', 1e-3)
+    assert optim.make_optimizer('rmsprop', 1e-5).momentum == 0.9   # experiment.py:140
