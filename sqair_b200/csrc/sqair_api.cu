@@ -37,7 +37,7 @@ int sqi::cuda_fail(cudaError_t e, const char* what) {
 // ---------------------------------------------------------------------------------------------
 // persistent sequence kernel: one cluster of C blocks per R rows, the whole T-frame recursion
 // ---------------------------------------------------------------------------------------------
-template <int R>
+template <int R, bool TR>
 __global__ void __launch_bounds__(NT_LAUNCH) sqair_sequence_kernel(const __grid_constant__ Job job) {
     const PlanHdr& plan = c_plan;
     Ctx c;
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(NT_LAUNCH) sqair_sequence_kernel(const __grid_
         const uint32_t* h = reinterpret_cast<const uint32_t*>(job.prm + plan.phdr_off);
         if (h[0] != PACK_MAGIC || h[1] != (uint32_t)plan.C || h[2] != (uint32_t)plan.NS || h[3] != (uint32_t)plan.PX) __trap();
     }
-    Block<R> blk(c, job, (int)(blockIdx.x / plan.C) * R);
+    Block<R, TR> blk(c, job, (int)(blockIdx.x / plan.C) * R);
     blk.run();
     if (plan.C > 1) { cluster_arrive(c); cluster_wait(c); }      // no block exits while peers may still write to it
 #ifdef SQAIR_PROFILE
@@ -142,8 +142,8 @@ static int get_layer_table(const Plan& plan, int device, cudaStream_t st, const 
     return SQAIR_OK;
 }
 
-template <int R>
-static int launch_sequence(const Plan& plan, Job job, cudaStream_t st) {
+template <int R, bool TR>
+static int launch_sequence_impl(const Plan& plan, Job job, cudaStream_t st) {
     int device = 0;
     CUDA_TRY(cudaGetDevice(&device));
     if (device < 0 || device >= 64) return fail(SQAIR_EUNSUPPORTED, "device ordinal out of range");
@@ -154,7 +154,7 @@ static int launch_sequence(const Plan& plan, Job job, cudaStream_t st) {
     rc = upload_plan(plan, st, ds);
     if (rc != SQAIR_OK) return rc;
     const int smem_bytes = plan.sm.total * (int)sizeof(float);
-    CUDA_TRY(cudaFuncSetAttribute(sqair_sequence_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(sqair_sequence_kernel<R, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const int ncl = (plan.rows + R - 1) / R;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -169,7 +169,7 @@ static int launch_sequence(const Plan& plan, Job job, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = plan.C > 1 ? 1 : 0;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, sqair_sequence_kernel<R>, job));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, sqair_sequence_kernel<R, TR>, job));
     if (!stream_is_capturing(st)) {           // (a captured launch replays with the plan that was resident at capture time)
         cudaEvent_t ev = nullptr;
         for (auto& se : ds.inflight) if (se.first == st) ev = se.second;
@@ -184,6 +184,12 @@ static int launch_sequence(const Plan& plan, Job job, cudaStream_t st) {
         CUDA_TRY(cudaEventRecord(ev, st));
     }
     return SQAIR_OK;
+}
+
+// inference (no stash: the stash code is compiled out) or training instantiation
+template <int R>
+static int launch_sequence(const Plan& plan, const Job& job, cudaStream_t st) {
+    return job.stash ? launch_sequence_impl<R, true>(plan, job, st) : launch_sequence_impl<R, false>(plan, job, st);
 }
 
 // Launch shape.  R rows per cluster (more rows = fewer re-reads of the weights from L2), C blocks per

@@ -449,7 +449,7 @@ SQ_UNIT void mma_unit(const Layer& L, const float4* SQ_RESTRICT wp, int k0, int 
 // registers by the caller).
 // Training stash: `stash` != nullptr makes every finished output also go to global memory (Head::st_off), at frame
 // st_t, rows row0 + r, entry st_entry of the head's signal.
-template <int R>
+template <int R, bool TR>
 SQ_DEVNI bool dense(Ctx& c, const float* SQ_RESTRICT prm, const float* SQ_RESTRICT ltab, int layer_id, int slot,
                     const float* const* imgrow, const float* SQ_RESTRICT img_g, int dbg, int flags, int call_idx, int desc_cur,
                     float* SQ_RESTRICT stash, int st_t, int st_entry, int row0) {
@@ -572,7 +572,7 @@ SQ_DEVNI bool dense(Ctx& c, const float* SQ_RESTRICT prm, const float* SQ_RESTRI
             } else {
                 SQ_SM[off] = v;
             }
-            if (stash != nullptr && H.st_off >= 0 && row0 + r < P.rows && (L.split || c.rank() == 0))
+            if (TR && stash != nullptr && H.st_off >= 0 && row0 + r < P.rows && (L.split || c.rank() == 0))
                 stash[(size_t)H.st_off + ((size_t)(st_t * P.rows + row0 + r) * H.st_entries + st_entry) * H.st_width + j] = v;
         }
     }
@@ -604,7 +604,8 @@ SQ_DEVNI bool dense(Ctx& c, const float* SQ_RESTRICT prm, const float* SQ_RESTRI
 #ifndef SQAIR_HOST_EMU
 #define P c_plan
 #endif
-template <int R>
+// TR = false compiles the training stash out (the inference kernel)
+template <int R, bool TR = true>
 struct Block {
     Ctx& c;
 #ifdef SQAIR_HOST_EMU
@@ -663,9 +664,9 @@ struct Block {
         const int flags = (pend_ ? 1 : 0) | (next_is_dense ? 2 : 0);
         if (st_entry < 0) st_entry = slot;
 #ifdef SQAIR_HOST_EMU
-        pend_ = dense<R>(c, prm_, ltab_, id, slot, imgrow, img_g, dbg_, flags, call_idx_, desc_cur_, stash_, t_, st_entry, row0);
+        pend_ = dense<R, TR>(c, prm_, ltab_, id, slot, imgrow, img_g, dbg_, flags, call_idx_, desc_cur_, stash_, t_, st_entry, row0);
 #else
-        pend_ = dense<R>(c, prm_, ltab_, id, slot, nullptr, img_g, dbg_, flags, call_idx_, desc_cur_, stash_, t_, st_entry, row0);   // (passing imgrow would pin it to local memory)
+        pend_ = dense<R, TR>(c, prm_, ltab_, id, slot, nullptr, img_g, dbg_, flags, call_idx_, desc_cur_, stash_, t_, st_entry, row0);   // (passing imgrow would pin it to local memory)
 #endif
         if (++call_idx_ >= P.nseq) call_idx_ = 0;
         desc_cur_ ^= 1;
@@ -677,7 +678,7 @@ struct Block {
     // shared memory at smem_off + f * fstride + r.  The (replicated) state is split by features across the cluster's
     // blocks; consecutive threads write consecutive features of one row.
     SQ_DEV void stash_copy(int sig, int t, int entry, int smem_off, int fstride, int nfeat, int col0 = 0) const {
-        if (stash_ == nullptr) return;
+        if (!TR || stash_ == nullptr) return;
         const Sig g = P.st[sig];
         const int per = (nfeat + c.ncta() - 1) / c.ncta(), f0 = c.rank() * per;
         const int cnt = (f0 + per < nfeat ? f0 + per : nfeat) - f0;
@@ -1406,7 +1407,7 @@ struct Block {
         }
         c.sync();
         t_ = t;
-        if (stash_ != nullptr) {                                  // state entering the frame, initial slot records
+        if (TR && stash_ != nullptr) {                            // state entering the frame, initial slot records
             for (int s = 0; s < NS; ++s) {
                 stash_copy(S_TST, t, s, m.Tst + s * R, LDS(), nh);
                 stash_copy(S_PST, t, s, m.Pst + s * R, LDS(), nh);
