@@ -261,43 +261,53 @@ SQB_HD void bw_canvas(const BwdCtx& c, EX& ex, int t, int row) {
     const float* mean_img = c.prm + c.po.mean_img;
     const float* img = c.obs + ((size_t)t * c.cfg.B + row / c.cfg.K) * c.PX;
     float* dmean = c.xt[X_MEAN] + (size_t)(t * c.rows + row) * c.PX;
-    for (int px = ex.tid; px < c.PX; px += ex.nt) {
-        const int iy = px / W, ix = px % W;
+    for (int px0 = 0; px0 < c.PX; px0 += ex.nt) {            // uniform trip count: the where sums are reduced per warp
+        const int px = px0 + ex.tid;
+        const bool act = px < c.PX;
+        const int iy = act ? px / W : 0, ix = act ? px % W : 0;
         const float u = blin11(ix, W), v = blin11(iy, H);
-        float cv = 0.f, nz = 0.f;
-        for (int s = 0; s < n; ++s) {
-            const float pres = cc[s * 7 + 4];
-            if (pres == 0.f) continue;
-            const float xg = hg * ((u - cc[s * 7 + 2]) / cc[s * 7 + 0]) + hg;
-            const float yg = hg * ((v - cc[s * 7 + 3]) / cc[s * 7 + 1]) + hg;
-            const float* gs = sg + s * g;
-            cv += pres * bilin_grad(xg, yg, G, G, [&](int gx, int gy) { return gs[gy * G + gx]; }).val;
-            nz += pres * bilin_grad(xg, yg, G, G, [&](int, int) { return 1.f; }).val;
+        float d_cv = 0.f, d_nz = 0.f;
+        if (act) {
+            float cv = 0.f, nz = 0.f;
+            for (int s = 0; s < n; ++s) {
+                const float pres = cc[s * 7 + 4];
+                if (pres == 0.f) continue;
+                const float xg = hg * ((u - cc[s * 7 + 2]) / cc[s * 7 + 0]) + hg;
+                const float yg = hg * ((v - cc[s * 7 + 3]) / cc[s * 7 + 1]) + hg;
+                const float* gs = sg + s * g;
+                cv += pres * bilin_grad(xg, yg, G, G, [&](int gx, int gy) { return gs[gy * G + gx]; }).val;
+                nz += pres * bilin_grad(xg, yg, G, G, [&](int, int) { return 1.f; }).val;
+            }
+            const float mask = bsigmoid(-10.f + nz * 20.f);
+            const float mi = mean_img[px];
+            cv += mi * mask;
+            const float sd = mask * sf + (1.f - mask) * sb;
+            const float z = (img[px] - cv) / sd;
+            d_cv = up * z / sd;
+            const float d_sd = up * (z * z - 1.f) / sd;
+            const float d_mask = d_cv * mi + d_sd * (sf - sb);
+            d_nz = d_mask * 20.f * mask * (1.f - mask);
+            dmean[px] = d_cv * mask;
         }
-        const float mask = bsigmoid(-10.f + nz * 20.f);
-        const float mi = mean_img[px];
-        cv += mi * mask;
-        const float sd = mask * sf + (1.f - mask) * sb;
-        const float z = (img[px] - cv) / sd;
-        const float d_cv = up * z / sd, d_sd = up * (z * z - 1.f) / sd;
-        const float d_mask = d_cv * mi + d_sd * (sf - sb);
-        const float d_nz = d_mask * 20.f * mask * (1.f - mask);
-        dmean[px] = d_cv * mask;
         for (int s = 0; s < n; ++s) {
             const float pres = cc[s * 7 + 4];
-            if (pres == 0.f) continue;
-            const float sx = cc[s * 7 + 0], sy = cc[s * 7 + 1], tx = cc[s * 7 + 2], ty = cc[s * 7 + 3];
-            const float xg = hg * ((u - tx) / sx) + hg, yg = hg * ((v - ty) / sy) + hg;
-            const float* gs = sg + s * g;
-            const BilinG bg = bilin_grad(xg, yg, G, G, [&](int gx, int gy) { return gs[gy * G + gx]; });
-            const BilinG bo = bilin_grad(xg, yg, G, G, [&](int, int) { return 1.f; });
-            for (int q = 0; q < 4; ++q)
-                if (bg.idx4[q] >= 0) SQB_AADD(dgl + s * g + bg.idx4[q], d_cv * pres * bg.w4[q]);
-            const float d_xg = pres * (d_cv * bg.ddx + d_nz * bo.ddx), d_yg = pres * (d_cv * bg.ddy + d_nz * bo.ddy);
-            SQB_AADD(wsum + s * 4 + 0, d_xg * (-hg * (u - tx) / (sx * sx)));
-            SQB_AADD(wsum + s * 4 + 1, d_yg * (-hg * (v - ty) / (sy * sy)));
-            SQB_AADD(wsum + s * 4 + 2, d_xg * (-hg / sx));
-            SQB_AADD(wsum + s * 4 + 3, d_yg * (-hg / sy));
+            if (pres == 0.f) continue;                        // (uniform over the row's threads)
+            float w4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (act) {
+                const float sx = cc[s * 7 + 0], sy = cc[s * 7 + 1], tx = cc[s * 7 + 2], ty = cc[s * 7 + 3];
+                const float xg = hg * ((u - tx) / sx) + hg, yg = hg * ((v - ty) / sy) + hg;
+                const float* gs = sg + s * g;
+                const BilinG bg = bilin_grad(xg, yg, G, G, [&](int gx, int gy) { return gs[gy * G + gx]; });
+                const BilinG bo = bilin_grad(xg, yg, G, G, [&](int, int) { return 1.f; });
+                for (int q = 0; q < 4; ++q)
+                    if (bg.idx4[q] >= 0) SQB_AADD(dgl + s * g + bg.idx4[q], d_cv * pres * bg.w4[q]);
+                const float d_xg = pres * (d_cv * bg.ddx + d_nz * bo.ddx), d_yg = pres * (d_cv * bg.ddy + d_nz * bo.ddy);
+                w4[0] = d_xg * (-hg * (u - tx) / (sx * sx));
+                w4[1] = d_yg * (-hg * (v - ty) / (sy * sy));
+                w4[2] = d_xg * (-hg / sx);
+                w4[3] = d_yg * (-hg / sy);
+            }
+            ex.warp_add4(wsum + s * 4, w4);
         }
     }
     ex.sync();

@@ -279,12 +279,15 @@ struct LayerB {
     int KU, NU;           // rows without the bias row / columns
     int has_bias;
     int64_t bw_off;       // offset of the [KU + 1][NU] row-major matrix in the backward parameter buffer
+    int64_t bwt_off;      // offset of its transpose [NU][ldt] (after all row-major matrices); rows padded to 16 bytes
+    int ldt;              // round_up(KU + 1, 4)
 };
 
 struct Plan : PlanHdr {
     Layer L[L_COUNT];
     LayerB LB[L_COUNT];
-    int64_t bw_total;     // floats of the backward parameter buffer
+    int64_t bw_total;     // floats of the row-major matrices of the backward parameter buffer
+    int64_t bwt_total;    // floats of the transposed copies that follow them
     POff poc;             // like PlanHdr::po, but offsets into the CANONICAL flat buffer (backward pass)
 };
 constexpr uint32_t PACK_MAGIC = 0x53514152u;
@@ -418,6 +421,7 @@ struct PlanBuilder {
     int cursor = 0;          // shared-memory cursor (floats)
     int64_t wcursor = 0;     // packed-parameter cursor (floats)
     int64_t bwcursor = 0;    // backward parameter buffer cursor (floats)
+    int64_t bwtcursor = 0;   // cursor of the transposed copies
 
     PlanBuilder(Plan& plan, const std::vector<ParamEntry>& t, std::vector<Piece>& pc) : p(plan), tab(t), pieces(pc) {
         wcursor = vars_floats(t);
@@ -535,6 +539,9 @@ struct PlanBuilder {
         lb.bw_off = bwcursor;
         bwcursor += (int64_t)(lb.KU + 1) * lb.NU;
         bwcursor = (bwcursor + 3) / 4 * 4;
+        lb.ldt = round_up(lb.KU + 1, 4);
+        lb.bwt_off = bwtcursor;
+        bwtcursor += (int64_t)lb.NU * lb.ldt;
         int per = (l.Ntot + C - 1) / C;
         if (C > 1 && per >= 8) {          // at least half an m16 tile of real columns per block
             l.split = 1;
@@ -1011,6 +1018,7 @@ inline std::string build_plan(const sqair_cfg& c, int R, int C, Plan& p, const s
     static_assert(sizeof(Layer) <= DESC_WORDS * 4, "DESC_WORDS too small");
     static_assert(DESC_WORDS <= NT, "descriptor staging uses one thread per word");
     p.bw_total = B.bwcursor;
+    p.bwt_total = B.bwtcursor;
     p.phdr_off = (int)((B.wcursor + 31) / 32 * 32);
     if (packed_total) *packed_total = (B.wcursor + 31) / 32 * 32 + 32;
     return B.err;

@@ -27,6 +27,16 @@ struct DevEx {
     float* scratch;
     float* red;          // [4][32]
     __device__ __forceinline__ void sync() { __syncthreads(); }
+    // dst[0..3] += the warp's sums of v[0..3] (all 32 lanes must call; one shared-memory atomic per warp and value)
+    __device__ __forceinline__ void warp_add4(float* dst, const float (&v)[4]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float x = v[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if ((tid & 31) == 0) atomicAdd(dst + q, x);
+        }
+    }
     __device__ __forceinline__ void sum4(float (&v)[4]) {
         const int lane = tid & 31, warp = tid >> 5, nw = (nt + 31) >> 5;
 #pragma unroll
@@ -58,15 +68,17 @@ __global__ void bwd_stage_kernel(const __grid_constant__ BwdCtx c, int t, int s)
 
 // ---------------------------------------------------------------------------------------------
 // dgrad: dX_seg[m, k - k0] (=|+=) sum_n A[m, n] W[k, n],  A = a * act'(y)   (fp32 FFMA)
-// Block = DG_BM rows x DG_BK input features; the transposed virtual matrix Wt[n][k] makes both operand tiles
-// coalesced.  N is walked in chunks of DG_NC staged in shared memory with register prefetch of the next chunk.
+// M is 160 .. 640 rows and the call sits on the dependent chain of the reverse program, so the kernel is built for
+// latency, not throughput: a block owns 32 rows x 32 input features, a lane one row and all 32 features, and the eight
+// warps split the reduction over N (each streams its slice of the transposed matrix Wt[n][k] with warp-uniform
+// 16-byte loads: every weight is read once per block); partial sums meet in shared memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int DG_BM = 32, DG_BK = 64, DG_NC = 32, DG_THREADS = 256;
+constexpr int DG_BM = 32, DG_BK = 32, DG_WARPS = 8, DG_THREADS = 32 * DG_WARPS;
 
 struct DgradDev {
     DgradArgs a;
-    const float* wt;       // [N][K + 1] transposed virtual matrix
-    int ldt;               // K + 1
+    const float* wt;       // [N][ldt] transposed virtual matrix, rows padded to 16 bytes
+    int ldt;
 };
 
 __device__ __forceinline__ const float* addr_row(const Addr& a, int m, int ny) {
@@ -75,87 +87,59 @@ __device__ __forceinline__ const float* addr_row(const Addr& a, int m, int ny) {
 
 __global__ void __launch_bounds__(DG_THREADS) dgrad_kernel(const __grid_constant__ DgradDev D) {
     const DgradArgs& A = D.a;
-    __shared__ __align__(16) float As[DG_NC][DG_BM + 2];
-    __shared__ __align__(16) float Ws[DG_NC][DG_BK + 4];
-    const int tid = threadIdx.x;
-    const int m0 = blockIdx.y * DG_BM, kb = blockIdx.x * DG_BK;
-    const int tm = tid >> 4, tk = tid & 15;              // 16 x 16 threads: rows 2 tm.., features 4 tk..
-    // operand-load coordinates
-    const int a_m = tid >> 5, a_n = tid & 31;            // A: 8 rows per pass, 4 passes
-    const int w_n = tid >> 6, w_k = tid & 63;            // W: 4 n per pass, 8 passes
-    const float* arow[4];
-    const float* yrow[4];
-    float* drow[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const int m = m0 + a_m + 8 * p;
-        const bool ok = m < A.M;
-        arow[p] = ok ? addr_row(A.a, m, A.ny) : nullptr;
-        yrow[p] = (ok && A.y.p) ? addr_row(A.y, m, A.ny) : nullptr;
-        drow[p] = (ok && A.dy.p && blockIdx.x == 0) ? const_cast<float*>(addr_row(A.dy, m, A.ny)) : nullptr;
-    }
-    float acc[2][4];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    float ra[4], rw[8];
-    auto fetch = [&](int n0) {
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const int n = n0 + a_n;
-            float v = 0.f;
-            if (arow[p] && n < A.N) {
-                v = arow[p][n];
-                if (yrow[p]) v *= act_deriv(A.act, yrow[p][n], A.act_scale, A.act_add);
-                if (drow[p]) drow[p][n] = v;
-            }
-            ra[p] = v;
-        }
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            const int n = n0 + w_n + 4 * p, k = kb + w_k;
-            rw[p] = (n < A.N && k < A.K) ? __ldg(D.wt + (size_t)n * D.ldt + k) : 0.f;
-        }
-    };
+    __shared__ float part[DG_WARPS][DG_BM][DG_BK + 1];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m = blockIdx.y * DG_BM + lane, kb = blockIdx.x * DG_BK;
     const bool has_k = A.nseg > 0 && kb < A.K;
     if (!has_k && blockIdx.x != 0) return;
-    fetch(0);
-    for (int n0 = 0; n0 < A.N; n0 += DG_NC) {
-        __syncthreads();
+    const bool valid = m < A.M;
+    const float* arow = valid ? addr_row(A.a, m, A.ny) : nullptr;
+    const float* yrow = (valid && A.y.p) ? addr_row(A.y, m, A.ny) : nullptr;
+    float* drow = (valid && A.dy.p && blockIdx.x == 0) ? const_cast<float*>(addr_row(A.dy, m, A.ny)) : nullptr;
+    const int per = ((A.N + DG_WARPS - 1) / DG_WARPS + 3) & ~3;
+    const int n0 = warp * per, n1 = min(A.N, n0 + per);
+    float acc[DG_BK];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) As[a_n][a_m + 8 * p] = ra[p];
+    for (int j = 0; j < DG_BK; ++j) acc[j] = 0.f;
+    const int nq = has_k ? min(DG_BK / 4, (D.ldt - kb) / 4) : 0;          // 16-byte groups of this tile inside the padded row
+#pragma unroll 2
+    for (int n = n0; n < n1; ++n) {
+        float v = 0.f;
+        if (valid) {
+            v = arow[n];
+            if (yrow) v *= act_deriv(A.act, yrow[n], A.act_scale, A.act_add);
+            if (drow) drow[n] = v;
+        }
+        const float4* wp = reinterpret_cast<const float4*>(D.wt + (size_t)n * D.ldt + kb);
 #pragma unroll
-        for (int p = 0; p < 8; ++p) Ws[w_n + 4 * p][w_k] = rw[p];
-        __syncthreads();
-        if (n0 + DG_NC < A.N) fetch(n0 + DG_NC);
-        if (has_k) {
-#pragma unroll
-            for (int nn = 0; nn < DG_NC; ++nn) {
-                const float2 av = *reinterpret_cast<const float2*>(&As[nn][2 * tm]);
-                const float4 wv = *reinterpret_cast<const float4*>(&Ws[nn][4 * tk]);
-                acc[0][0] += av.x * wv.x; acc[0][1] += av.x * wv.y; acc[0][2] += av.x * wv.z; acc[0][3] += av.x * wv.w;
-                acc[1][0] += av.y * wv.x; acc[1][1] += av.y * wv.y; acc[1][2] += av.y * wv.z; acc[1][3] += av.y * wv.w;
+        for (int q = 0; q < DG_BK / 4; ++q) {
+            if (q < nq) {
+                const float4 w = __ldg(wp + q);
+                acc[4 * q + 0] += v * w.x; acc[4 * q + 1] += v * w.y; acc[4 * q + 2] += v * w.z; acc[4 * q + 3] += v * w.w;
             }
         }
     }
     if (!has_k) return;
 #pragma unroll
+    for (int j = 0; j < DG_BK; ++j) part[warp][lane][j] = acc[j];
+    __syncthreads();
+    const int mi = tid >> 3, kq = (tid & 7) * 4;
+    const int mo = blockIdx.y * DG_BM + mi;
+    if (mo >= A.M) return;
+#pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int k = kb + 4 * tk + j;
+        const int k = kb + kq + j;
         if (k >= A.K) continue;
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < DG_WARPS; ++w) sum += part[w][mi][kq + j];
         int si = -1;
         for (int q = 0; q < A.nseg; ++q)
             if (k >= A.seg[q].k0 && k < A.seg[q].k1) si = q;
         if (si < 0) continue;
         const DgradArgs::Seg& S = A.seg[si];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int m = m0 + 2 * tm + i;
-            if (m >= A.M) continue;
-            float* d = const_cast<float*>(addr_row(S.d, m, A.ny)) + (k - S.k0);
-            if (S.mode == SEGM_STORE) *d = acc[i][j]; else *d += acc[i][j];
-        }
+        float* d = const_cast<float*>(addr_row(S.d, mo, A.ny)) + (k - S.k0);
+        if (S.mode == SEGM_STORE) *d = sum; else *d += sum;
     }
 }
 
@@ -354,9 +338,9 @@ static void fill_piece_tab(const Shape& sh, BPieceTab& bt) {
         const Piece& p = sh.pieces[i];
         const LayerB& LB = sh.plan.LB[p.layer];
         BPiece& b = bt.p[i];
-        b.K = p.K; b.N = p.N; b.src_off = (int)p.src_off; b.src_ld = p.src_ld; b.NU = LB.NU; b.ldt = LB.KU + 1;
+        b.K = p.K; b.N = p.N; b.src_off = (int)p.src_off; b.src_ld = p.src_ld; b.NU = LB.NU; b.ldt = LB.ldt;
         b.dst = LB.bw_off + (long long)p.urow0 * LB.NU + p.ucol0;
-        b.dst_t = sh.plan.bw_total + LB.bw_off + (long long)p.ucol0 * (LB.KU + 1) + p.urow0;
+        b.dst_t = sh.plan.bw_total + LB.bwt_off + (long long)p.ucol0 * LB.ldt + p.urow0;
     }
 }
 
@@ -384,8 +368,9 @@ struct CudaBackend {
     void dgrad(const DgradArgs& A) {
         DgradDev D;
         D.a = A;
-        D.wt = A.w + sh->plan.bw_total;          // transposed copy sits bw_total floats behind the row-major one
-        D.ldt = A.K + 1;
+        const LayerB& LB = sh->plan.LB[A.layer];
+        D.wt = A.w - LB.bw_off + sh->plan.bw_total + LB.bwt_off;      // transposed copies follow the row-major matrices
+        D.ldt = LB.ldt;
         int gx = A.nseg > 0 ? (A.K + DG_BK - 1) / DG_BK : 1;
         dgrad_kernel<<<dim3(gx, (A.M + DG_BM - 1) / DG_BM), DG_THREADS, 0, st>>>(D);
         check();
@@ -453,7 +438,7 @@ int sqair_query_train_sizes(const sqair_cfg* cfg, sqair_train_sizes* out) {
     const BwdLayout BL = build_bwd_layout(*cfg, sh.plan);
     out->stash_floats = SL.total;
     out->workspace_floats = BL.total;
-    out->backward_param_floats = 2 * sh.plan.bw_total;
+    out->backward_param_floats = sh.plan.bw_total + sh.plan.bwt_total;
     return SQAIR_OK;
 }
 
@@ -467,7 +452,7 @@ int sqair_pack_backward(const sqair_cfg* cfg, const float* params, float* bw_par
     cudaStream_t st = (cudaStream_t)stream;
     BPieceTab bt;
     fill_piece_tab(sh, bt);
-    CUDA_TRY(cudaMemsetAsync(bw_params, 0, (size_t)2 * sh.plan.bw_total * sizeof(float), st));
+    CUDA_TRY(cudaMemsetAsync(bw_params, 0, (size_t)(sh.plan.bw_total + sh.plan.bwt_total) * sizeof(float), st));
     pack_backward_kernel<<<dim3(32, bt.n), 256, 0, st>>>(bt, params, bw_params);
     CUDA_TRY(cudaGetLastError());
     return SQAIR_OK;

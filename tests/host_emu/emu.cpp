@@ -122,6 +122,7 @@ struct HostEx {
     float* scratch;
     void sync() {}
     void sum4(float (&)[4]) {}
+    void warp_add4(float* dst, const float (&v)[4]) { for (int q = 0; q < 4; ++q) dst[q] += v[q]; }
 };
 
 struct HostBackend {
