@@ -69,11 +69,15 @@ __global__ void bwd_stage_kernel(const __grid_constant__ BwdCtx c, int t, int s)
 // ---------------------------------------------------------------------------------------------
 // dgrad: dX_seg[m, k - k0] (=|+=) sum_n A[m, n] W[k, n],  A = a * act'(y)   (fp32 FFMA)
 // M is 160 .. 640 rows and the call sits on the dependent chain of the reverse program, so the kernel is built for
-// latency, not throughput: a block owns 32 rows x 32 input features, a lane one row and all 32 features, and the eight
-// warps split the reduction over N (each streams its slice of the transposed matrix Wt[n][k] with warp-uniform
-// 16-byte loads: every weight is read once per block); partial sums meet in shared memory.
+// latency, not throughput.  A block owns 32 rows x 32 input features.  N is walked in phases of 256: all threads first
+// fetch the phase's operand tiles with independent loads (A[32][256] with the activation derivative applied, and the
+// slice Wt[256][32] of the transposed matrix, 16-byte loads) into shared memory -- one memory round trip --, then the
+// eight warps split the 256 n (a lane owns one row and 32 accumulators; weights are shared-memory broadcasts).
+// Partial sums of the warps meet in shared memory (aliasing the tiles).
 // ---------------------------------------------------------------------------------------------
-constexpr int DG_BM = 32, DG_BK = 32, DG_WARPS = 8, DG_THREADS = 32 * DG_WARPS;
+constexpr int DG_BM = 32, DG_BK = 32, DG_WARPS = 8, DG_THREADS = 32 * DG_WARPS, DG_NP = 256;
+constexpr int DG_SMEM_FLOATS = DG_NP * (DG_BM + 1) + DG_NP * DG_BK;        // As[n][33] + Ws[n][32]  (66.8 KB)
+static_assert(DG_WARPS * DG_BM * (DG_BK + 1) <= DG_SMEM_FLOATS, "partial sums alias the operand tiles");
 
 struct DgradDev {
     DgradArgs a;
@@ -87,44 +91,62 @@ __device__ __forceinline__ const float* addr_row(const Addr& a, int m, int ny) {
 
 __global__ void __launch_bounds__(DG_THREADS) dgrad_kernel(const __grid_constant__ DgradDev D) {
     const DgradArgs& A = D.a;
-    __shared__ float part[DG_WARPS][DG_BM][DG_BK + 1];
+    extern __shared__ __align__(16) float dg_smem[];
+    float* As = dg_smem;                                  // [DG_NP][DG_BM + 1]
+    float* Ws = dg_smem + DG_NP * (DG_BM + 1);            // [DG_NP][DG_BK]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m = blockIdx.y * DG_BM + lane, kb = blockIdx.x * DG_BK;
+    const int m0 = blockIdx.y * DG_BM, kb = blockIdx.x * DG_BK;
     const bool has_k = A.nseg > 0 && kb < A.K;
     if (!has_k && blockIdx.x != 0) return;
-    const bool valid = m < A.M;
-    const float* arow = valid ? addr_row(A.a, m, A.ny) : nullptr;
-    const float* yrow = (valid && A.y.p) ? addr_row(A.y, m, A.ny) : nullptr;
-    float* drow = (valid && A.dy.p && blockIdx.x == 0) ? const_cast<float*>(addr_row(A.dy, m, A.ny)) : nullptr;
-    const int per = ((A.N + DG_WARPS - 1) / DG_WARPS + 3) & ~3;
-    const int n0 = warp * per, n1 = min(A.N, n0 + per);
+    const bool store_dy = A.dy.p != nullptr && blockIdx.x == 0;
+    const int nq = has_k ? min(DG_BK / 4, (D.ldt - kb) / 4) : 0;          // 16-byte groups of this tile inside the padded row
     float acc[DG_BK];
 #pragma unroll
     for (int j = 0; j < DG_BK; ++j) acc[j] = 0.f;
-    const int nq = has_k ? min(DG_BK / 4, (D.ldt - kb) / 4) : 0;          // 16-byte groups of this tile inside the padded row
-#pragma unroll 2
-    for (int n = n0; n < n1; ++n) {
-        float v = 0.f;
-        if (valid) {
-            v = arow[n];
-            if (yrow) v *= act_deriv(A.act, yrow[n], A.act_scale, A.act_add);
-            if (drow) drow[n] = v;
+    for (int nb = 0; nb < A.N; nb += DG_NP) {
+        const int np = min(DG_NP, A.N - nb);
+        if (nb) __syncthreads();
+        // A tile: consecutive threads take consecutive n of one row (coalesced); stored transposed
+        for (int i = tid; i < DG_BM * np; i += DG_THREADS) {
+            const int r = i / np, n = i - r * np, m = m0 + r;
+            float v = 0.f;
+            if (m < A.M) {
+                v = addr_row(A.a, m, A.ny)[nb + n];
+                if (A.y.p) v *= act_deriv(A.act, addr_row(A.y, m, A.ny)[nb + n], A.act_scale, A.act_add);
+                if (store_dy) const_cast<float*>(addr_row(A.dy, m, A.ny))[nb + n] = v;
+            }
+            As[n * (DG_BM + 1) + r] = v;
         }
-        const float4* wp = reinterpret_cast<const float4*>(D.wt + (size_t)n * D.ldt + kb);
+        if (has_k) {
+            for (int i = tid; i < np * (DG_BK / 4); i += DG_THREADS) {
+                const int n = i >> 3, q = i & 7;
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q < nq) w = __ldg(reinterpret_cast<const float4*>(D.wt + (size_t)(nb + n) * D.ldt + kb) + q);
+                *reinterpret_cast<float4*>(Ws + n * DG_BK + 4 * q) = w;
+            }
+        }
+        __syncthreads();
+        if (has_k) {
+#pragma unroll 4
+            for (int n = warp; n < np; n += DG_WARPS) {
+                const float v = As[n * (DG_BM + 1) + lane];
+                const float4* wp = reinterpret_cast<const float4*>(Ws + n * DG_BK);
 #pragma unroll
-        for (int q = 0; q < DG_BK / 4; ++q) {
-            if (q < nq) {
-                const float4 w = __ldg(wp + q);
-                acc[4 * q + 0] += v * w.x; acc[4 * q + 1] += v * w.y; acc[4 * q + 2] += v * w.z; acc[4 * q + 3] += v * w.w;
+                for (int q = 0; q < DG_BK / 4; ++q) {
+                    const float4 w = wp[q];
+                    acc[4 * q + 0] += v * w.x; acc[4 * q + 1] += v * w.y; acc[4 * q + 2] += v * w.z; acc[4 * q + 3] += v * w.w;
+                }
             }
         }
     }
     if (!has_k) return;
+    __syncthreads();
+    float* part = dg_smem;                                // [DG_WARPS][DG_BM][DG_BK + 1]
 #pragma unroll
-    for (int j = 0; j < DG_BK; ++j) part[warp][lane][j] = acc[j];
+    for (int j = 0; j < DG_BK; ++j) part[(warp * DG_BM + lane) * (DG_BK + 1) + j] = acc[j];
     __syncthreads();
     const int mi = tid >> 3, kq = (tid & 7) * 4;
-    const int mo = blockIdx.y * DG_BM + mi;
+    const int mo = m0 + mi;
     if (mo >= A.M) return;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -132,7 +154,7 @@ __global__ void __launch_bounds__(DG_THREADS) dgrad_kernel(const __grid_constant
         if (k >= A.K) continue;
         float sum = 0.f;
 #pragma unroll
-        for (int w = 0; w < DG_WARPS; ++w) sum += part[w][mi][kq + j];
+        for (int w = 0; w < DG_WARPS; ++w) sum += part[(w * DG_BM + mi) * (DG_BK + 1) + kq + j];
         int si = -1;
         for (int q = 0; q < A.nseg; ++q)
             if (k >= A.seg[q].k0 && k < A.seg[q].k1) si = q;
@@ -372,7 +394,7 @@ struct CudaBackend {
         D.wt = A.w - LB.bw_off + sh->plan.bw_total + LB.bwt_off;      // transposed copies follow the row-major matrices
         D.ldt = LB.ldt;
         int gx = A.nseg > 0 ? (A.K + DG_BK - 1) / DG_BK : 1;
-        dgrad_kernel<<<dim3(gx, (A.M + DG_BM - 1) / DG_BM), DG_THREADS, 0, st>>>(D);
+        dgrad_kernel<<<dim3(gx, (A.M + DG_BM - 1) / DG_BM), DG_THREADS, DG_SMEM_FLOATS * sizeof(float), st>>>(D);
         check();
     }
     void wgrad(const WgradArgs& A) {
@@ -471,6 +493,7 @@ int sqair_backward(const sqair_cfg* cfg, const float* params, const float* bw_pa
     BwdInputs in;
     in.params = params; in.bw = bw_params; in.obs = obs; in.eps_where = eps_where; in.eps_what = eps_what; in.stash = stash;
     in.d_log_w = d_log_weights; in.d_disc_lp = d_discrete_log_prob; in.ws = workspace; in.d_params = d_params; in.vimco = 1;
+    CUDA_TRY(cudaFuncSetAttribute(dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM_FLOATS * (int)sizeof(float)));
     CudaBackend be;
     be.st = (cudaStream_t)stream; be.sh = &sh; be.rows = cfg->B * cfg->K;
     be.scratch_bytes = bw_stage_scratch_floats(*cfg) * (int)sizeof(float);
