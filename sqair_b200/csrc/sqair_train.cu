@@ -75,8 +75,8 @@ __global__ void bwd_stage_kernel(const __grid_constant__ BwdCtx c, int t, int s)
 // eight warps split the 256 n (a lane owns one row and 32 accumulators; weights are shared-memory broadcasts).
 // Partial sums of the warps meet in shared memory (aliasing the tiles).
 // ---------------------------------------------------------------------------------------------
-constexpr int DG_BM = 32, DG_BK = 32, DG_WARPS = 8, DG_THREADS = 32 * DG_WARPS, DG_NP = 256;
-constexpr int DG_SMEM_FLOATS = DG_NP * (DG_BM + 1) + DG_NP * DG_BK;        // As[n][33] + Ws[n][32]  (66.8 KB)
+constexpr int DG_BM = 32, DG_BK = 32, DG_WARPS = 16, DG_THREADS = 32 * DG_WARPS, DG_NP = 256, DG_LDA = DG_BM + 4;
+constexpr int DG_SMEM_FLOATS = DG_NP * DG_LDA + DG_NP * DG_BK;             // As[n][36] + Ws[n][32]  (69.6 KB)
 static_assert(DG_WARPS * DG_BM * (DG_BK + 1) <= DG_SMEM_FLOATS, "partial sums alias the operand tiles");
 
 struct DgradDev {
@@ -89,53 +89,94 @@ __device__ __forceinline__ const float* addr_row(const Addr& a, int m, int ny) {
     return a.p + (size_t)(m / ny) * a.outer + (size_t)(m % ny) * a.inner;
 }
 
-__global__ void __launch_bounds__(DG_THREADS) dgrad_kernel(const __grid_constant__ DgradDev D) {
+// The kernel runs once per call on a cold instruction cache, so it is written for a SMALL code footprint (the first,
+// fully unrolled version spent 5 of 7 issue-stall cycles on instruction fetch, ncu `stalled_no_instruction`): rolled
+// loops around short unrolled bodies, the activation derivative resolved at compile time.
+template <int ACT>
+__device__ __forceinline__ float act_deriv_t(float y, float scale, float add) {
+    if (ACT == ACT_ELU) return y > 0.f ? 1.f : y + 1.f;
+    if (ACT == ACT_TANH) return 1.f - y * y;
+    if (ACT == ACT_SIGMOID) { const float s_ = y / scale; return scale * s_ * (1.f - s_); }
+    if (ACT == ACT_SOFTPLUS) return -expm1f(-(y - add));
+    return 1.f;
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(DG_THREADS, 1) dgrad_kernel(const __grid_constant__ DgradDev D) {
     const DgradArgs& A = D.a;
     extern __shared__ __align__(16) float dg_smem[];
-    float* As = dg_smem;                                  // [DG_NP][DG_BM + 1]
-    float* Ws = dg_smem + DG_NP * (DG_BM + 1);            // [DG_NP][DG_BK]
+    float* As = dg_smem;                                  // [DG_NP][DG_LDA]  (rows of the tile contiguous: 16-byte loads of 4 rows)
+    float* Ws = dg_smem + DG_NP * DG_LDA;                 // [DG_NP][DG_BK]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * DG_BM, kb = blockIdx.x * DG_BK;
     const bool has_k = A.nseg > 0 && kb < A.K;
     if (!has_k && blockIdx.x != 0) return;
     const bool store_dy = A.dy.p != nullptr && blockIdx.x == 0;
     const int nq = has_k ? min(DG_BK / 4, (D.ldt - kb) / 4) : 0;          // 16-byte groups of this tile inside the padded row
-    float acc[DG_BK];
+    const int rg = lane >> 2, fq = lane & 3;                 // compute: rows 4 rg .. 4 rg + 3, features 8 fq .. 8 fq + 7
+    float acc[4][8];
 #pragma unroll
-    for (int j = 0; j < DG_BK; ++j) acc[j] = 0.f;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     for (int nb = 0; nb < A.N; nb += DG_NP) {
         const int np = min(DG_NP, A.N - nb);
         if (nb) __syncthreads();
-        // A tile: consecutive threads take consecutive n of one row (coalesced); stored transposed
-        for (int i = tid; i < DG_BM * np; i += DG_THREADS) {
-            const int r = i / np, n = i - r * np, m = m0 + r;
-            float v = 0.f;
-            if (m < A.M) {
-                v = addr_row(A.a, m, A.ny)[nb + n];
-                if (A.y.p) v *= act_deriv(A.act, addr_row(A.y, m, A.ny)[nb + n], A.act_scale, A.act_add);
-                if (store_dy) const_cast<float*>(addr_row(A.dy, m, A.ny))[nb + n] = v;
+        // operand fetch: every thread issues a batch of independent loads before it touches the first result
+        if (has_k) {                                             // weight slice Wt[nb .. nb+np)[kb .. kb+32): 4 x 16 bytes per thread
+            constexpr int NW = DG_NP * (DG_BK / 4) / DG_THREADS;
+            float4 wv[NW];
+#pragma unroll
+            for (int j = 0; j < NW; ++j) {
+                const int i = tid + j * DG_THREADS, n = i >> 3, q = i & 7;
+                wv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n < np && q < nq) wv[j] = __ldg(reinterpret_cast<const float4*>(D.wt + (size_t)(nb + n) * D.ldt + kb) + q);
             }
-            As[n * (DG_BM + 1) + r] = v;
+#pragma unroll
+            for (int j = 0; j < NW; ++j) {
+                const int i = tid + j * DG_THREADS, n = i >> 3, q = i & 7;
+                if (n < np) *reinterpret_cast<float4*>(Ws + n * DG_BK + 4 * q) = wv[j];
+            }
         }
-        if (has_k) {
-            for (int i = tid; i < np * (DG_BK / 4); i += DG_THREADS) {
-                const int n = i >> 3, q = i & 7;
-                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (q < nq) w = __ldg(reinterpret_cast<const float4*>(D.wt + (size_t)(nb + n) * D.ldt + kb) + q);
-                *reinterpret_cast<float4*>(Ws + n * DG_BK + 4 * q) = w;
+        // A tile: warp w owns rows 2w, 2w + 1, lane l the columns l, l + 32, ... (coalesced); one row per iteration
+#pragma unroll 1
+        for (int i = 0; i < DG_BM / DG_WARPS; ++i) {
+            const int r = (DG_BM / DG_WARPS) * warp + i, m = m0 + r;
+            const bool okm = m < A.M;
+            const float* arow = okm ? addr_row(A.a, m, A.ny) + nb : nullptr;
+            const float* yrow = (okm && ACT != ACT_NONE) ? addr_row(A.y, m, A.ny) + nb : nullptr;
+            float* drow = (okm && store_dy) ? const_cast<float*>(addr_row(A.dy, m, A.ny)) + nb : nullptr;
+            float av[DG_NP / 32], yv[DG_NP / 32];
+#pragma unroll
+            for (int j = 0; j < DG_NP / 32; ++j) {
+                const int n = lane + 32 * j;
+                const bool ok = okm && n < np;
+                av[j] = ok ? arow[n] : 0.f;
+                yv[j] = (ok && ACT != ACT_NONE) ? yrow[n] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < DG_NP / 32; ++j) {
+                const int n = lane + 32 * j;
+                if (n < np) {
+                    const float v = av[j] * act_deriv_t<ACT>(yv[j], A.act_scale, A.act_add);
+                    if (drow) drow[n] = v;
+                    As[n * DG_LDA + r] = v;
+                }
             }
         }
         __syncthreads();
         if (has_k) {
-#pragma unroll 4
+#pragma unroll 2
             for (int n = warp; n < np; n += DG_WARPS) {
-                const float v = As[n * (DG_BM + 1) + lane];
-                const float4* wp = reinterpret_cast<const float4*>(Ws + n * DG_BK);
+                const float4 a4 = *reinterpret_cast<const float4*>(As + n * DG_LDA + 4 * rg);
+                const float4 w0 = *reinterpret_cast<const float4*>(Ws + n * DG_BK + 8 * fq);
+                const float4 w1 = *reinterpret_cast<const float4*>(Ws + n * DG_BK + 8 * fq + 4);
+                const float av4[4] = {a4.x, a4.y, a4.z, a4.w};
+                const float wv8[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                for (int q = 0; q < DG_BK / 4; ++q) {
-                    const float4 w = wp[q];
-                    acc[4 * q + 0] += v * w.x; acc[4 * q + 1] += v * w.y; acc[4 * q + 2] += v * w.z; acc[4 * q + 3] += v * w.w;
-                }
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] += av4[i] * wv8[j];
             }
         }
     }
@@ -143,15 +184,17 @@ __global__ void __launch_bounds__(DG_THREADS) dgrad_kernel(const __grid_constant
     __syncthreads();
     float* part = dg_smem;                                // [DG_WARPS][DG_BM][DG_BK + 1]
 #pragma unroll
-    for (int j = 0; j < DG_BK; ++j) part[(warp * DG_BM + lane) * (DG_BK + 1) + j] = acc[j];
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) part[(warp * DG_BM + 4 * rg + i) * (DG_BK + 1) + 8 * fq + j] = acc[i][j];
     __syncthreads();
-    const int mi = tid >> 3, kq = (tid & 7) * 4;
+    const int mi = tid >> 4, kq = (tid & 15) * 2;
     const int mo = m0 + mi;
     if (mo >= A.M) return;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
         const int k = kb + kq + j;
-        if (k >= A.K) continue;
+        if (k >= A.K) break;
         float sum = 0.f;
 #pragma unroll
         for (int w = 0; w < DG_WARPS; ++w) sum += part[(w * DG_BM + mi) * (DG_BK + 1) + kq + j];
@@ -394,7 +437,15 @@ struct CudaBackend {
         D.wt = A.w - LB.bw_off + sh->plan.bw_total + LB.bwt_off;      // transposed copies follow the row-major matrices
         D.ldt = LB.ldt;
         int gx = A.nseg > 0 ? (A.K + DG_BK - 1) / DG_BK : 1;
-        dgrad_kernel<<<dim3(gx, (A.M + DG_BM - 1) / DG_BM), DG_THREADS, DG_SMEM_FLOATS * sizeof(float), st>>>(D);
+        const dim3 grid(gx, (A.M + DG_BM - 1) / DG_BM);
+        const size_t smem = DG_SMEM_FLOATS * sizeof(float);
+        switch (A.y.p ? A.act : ACT_NONE) {
+            case ACT_ELU: dgrad_kernel<ACT_ELU><<<grid, DG_THREADS, smem, st>>>(D); break;
+            case ACT_TANH: dgrad_kernel<ACT_TANH><<<grid, DG_THREADS, smem, st>>>(D); break;
+            case ACT_SIGMOID: dgrad_kernel<ACT_SIGMOID><<<grid, DG_THREADS, smem, st>>>(D); break;
+            case ACT_SOFTPLUS: dgrad_kernel<ACT_SOFTPLUS><<<grid, DG_THREADS, smem, st>>>(D); break;
+            default: dgrad_kernel<ACT_NONE><<<grid, DG_THREADS, smem, st>>>(D); break;
+        }
         check();
     }
     void wgrad(const WgradArgs& A) {
@@ -493,7 +544,12 @@ int sqair_backward(const sqair_cfg* cfg, const float* params, const float* bw_pa
     BwdInputs in;
     in.params = params; in.bw = bw_params; in.obs = obs; in.eps_where = eps_where; in.eps_what = eps_what; in.stash = stash;
     in.d_log_w = d_log_weights; in.d_disc_lp = d_discrete_log_prob; in.ws = workspace; in.d_params = d_params; in.vimco = 1;
-    CUDA_TRY(cudaFuncSetAttribute(dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM_FLOATS * (int)sizeof(float)));
+    const int dg_smem_bytes = DG_SMEM_FLOATS * (int)sizeof(float);
+    CUDA_TRY(cudaFuncSetAttribute(dgrad_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(dgrad_kernel<ACT_ELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(dgrad_kernel<ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(dgrad_kernel<ACT_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(dgrad_kernel<ACT_SOFTPLUS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_smem_bytes));
     CudaBackend be;
     be.st = (cudaStream_t)stream; be.sh = &sh; be.rows = cfg->B * cfg->K;
     be.scratch_bytes = bw_stage_scratch_floats(*cfg) * (int)sizeof(float);
