@@ -309,6 +309,20 @@ def run_cuda(args):
         res = model.step(obs_host.to(dev, non_blocking=True), seed=1000 + i)
         return res['scalars'].cpu(), res['log_weights'].cpu()
 
+    # the north star's outputs (ELBO, reconstructions, z_where / z_what / z_pres) read back every step as well
+    out_names = ('canvas', 'what', 'where', 'presence')
+    host_out = {}
+
+    def step_e2e_outputs(i):
+        res = model.step(obs_host.to(dev, non_blocking=True), seed=1000 + i)
+        for k in out_names:
+            t = res['outputs'][k]
+            if k not in host_out:
+                host_out[k] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            host_out[k].copy_(t, non_blocking=True)
+        sc = res['scalars'].cpu()                                   # (synchronises: the copies above are done)
+        return sc, res['log_weights'].cpu()
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -317,6 +331,7 @@ def run_cuda(args):
     for i in range(args.warmup):
         step_device(i)
         step_e2e(i)
+        step_e2e_outputs(i)
     barrier()
 
     # ---- device-resident timing: CUDA events around every step, L2 flushed between steps
@@ -349,11 +364,18 @@ def run_cuda(args):
         step_e2e(i)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e_outputs(i)
+    torch.cuda.synchronize()
+    e2e_out_ms = (time.perf_counter() - t0) * 1e3
+    out_bytes = sum(int(v.numel() * 4) for v in host_out.values())
 
-    times = torch.tensor([total_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([total_ms, e2e_ms, kern_ms, e2e_out_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, kern_ms = [float(x) for x in times.cpu()]
+    total_ms, e2e_ms, kern_ms, e2e_out_ms = [float(x) for x in times.cpu()]
     last_scalars = model.last_scalars.cpu()
     # ---- training step (weak scaling) and BASELINE configs[2] (global batch 32 split over the ranks, VIMCO)
     train = train_strong = None
@@ -383,10 +405,17 @@ def run_cuda(args):
                     clocks=clocks,
                     e2e=dict(value=frames / (e2e_ms * 1e-3), unit='frames/s',
                              h2d_bytes_per_step=int(obs_host.numel() * 4),
-                             d2h_bytes_per_step=int(4 * (_capi.OBJ_N + w['B'] * w['K']))),
+                             d2h_bytes_per_step=int(4 * (_capi.OBJ_N + w['B'] * w['K'])),
+                             reads_back='objective scalars + log_weights [B,K]; the 38 per-frame outputs stay on the device'),
+                    e2e_with_outputs=dict(value=frames / (e2e_out_ms * 1e-3), unit='frames/s',
+                                          h2d_bytes_per_step=int(obs_host.numel() * 4),
+                                          d2h_bytes_per_step=int(4 * (_capi.OBJ_N + w['B'] * w['K'])) + out_bytes,
+                                          reads_back='scalars + log_weights + canvas, what, where, presence [T, B*K, ...] into pinned host memory'),
                     gpu_launches=3 * args.steps,
                     roofline=dict(bound='hbm', achieved=achieved, peak=peaks['hbm_gbs'], unit='GB/s',
-                                  frac=achieved / peaks['hbm_gbs'], traffic=traffic, peak_source=which,
+                                  frac=achieved / peaks['hbm_gbs'], traffic=traffic,
+                                  traffic_source='profiles/latest_traffic.json (ncu --set full capture of this kernel and workload; not re-measured in this run)',
+                                  peak_source=which,
                                   kernel='sqair_sequence_kernel', kernel_ms=kern_ms, algorithmic_bytes=alg,
                                   note='latency-bound dependent chain of small dense layers; see DESIGN.md'),
                     elbo_iwae=float(last_scalars[1]), train=train, train_strong=train_strong)
@@ -395,7 +424,7 @@ def run_cuda(args):
         flops = 2 * 11092860.0 * w['B'] * w['K'] * w['T']
         line['roofline_tensor'] = dict(bound='tensor', achieved=flops / (kern_ms * 1e-3) / 1e12, peak=peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']),
                                        unit='TFLOP/s', frac=flops / (kern_ms * 1e-3) / 1e12 / peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']),
-                                       note='tensor pipe active 12.8% (ncu, profiles/); 4 TF32 products per fp32 MAC, 5 of 8 MMA columns used')
+                                       note='tensor pipe active 15.7% (ncu, profiles/r01f_ncu_full_sequence_kernel.txt); 4 TF32 products per fp32 MAC, 5 of 8 MMA columns used')
         if world == 1:
             try:
                 line['roofline_ops'] = op_rooflines(dev, peaks)

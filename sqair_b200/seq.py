@@ -28,6 +28,7 @@ class SequentialAIR(object):
         self._spec = self._read_architecture()
         self._stores = {}
         self._train_bufs = {}
+        self._infer_bufs = {}
 
     # ---- architecture -> kernel configuration ----------------------------------------------------
     def _read_architecture(self):
@@ -95,8 +96,16 @@ class SequentialAIR(object):
         T, B, H, W = obs.shape
         cfg = self.make_cfg(T, B, k_particles, H, W)
         store = self.param_store(H, W, obs.device)
+        # the 38 output tensors and the noise tensors of a call shape are allocated once and REUSED: what a call returns
+        # is overwritten by the next call with the same shape (pass `outputs=` to keep results)
+        key = (T, B, k_particles, H, W, str(obs.device))
+        buf = self._infer_bufs.get(key)
+        if buf is None:
+            buf = self._infer_bufs[key] = dict(noise=ops.alloc_noise(cfg, obs.device), outputs=ops.alloc_outputs(cfg, obs.device))
         if noise is None:
-            noise = ops.fill_noise(cfg, seed, row_offset, device=obs.device)
+            noise = ops.fill_noise(cfg, seed, row_offset, noise=buf['noise'])
+        if outputs is None:
+            outputs = buf['outputs']
         if kernel_events is not None:
             kernel_events[0].record()
         out = ops.forward(cfg, store.packed(cfg), obs, noise, outputs)

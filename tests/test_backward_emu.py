@@ -12,7 +12,9 @@ CASES = [      # (config, rows per cluster, blocks per cluster) of the emulated 
     (dict(T=3, B=2, K=3, n=3), 3, 2),                                   # VIMCO
     (dict(T=2, B=2, K=2, n=2, prior_type='guided', disc_prior_type='geom'), 1, 4),
     (dict(T=2, B=2, K=2, n=2, prior_type='rw', rec_where_prior=False, masked_glimpse=False), 2, 2),
-    (dict(T=3, B=2, K=2, n=2, rec_where_prior=False, masked_glimpse=False), 2, 1),      # seed 7 puts a canvas row on a bilinear kink
+    (dict(T=3, B=2, K=2, n=2, rec_where_prior=False, masked_glimpse=False), 2, 1),
+    (dict(T=2, B=2, K=2, n=2, bg_std=0.5), 2, 2),                      # background std differs from the object std
+         # seed 7 puts a canvas row on a bilinear kink
 ]
 
 

@@ -20,6 +20,7 @@ CASES = {
     'rw_prior': dict(T=3, B=2, K=2, n=2, prior_type='rw'),
     'guided_geom': dict(T=3, B=2, K=2, n=2, prior_type='guided', disc_prior_type='geom'),
     'no_rec_no_mask': dict(T=3, B=2, K=2, n=2, rec_where_prior=False, masked_glimpse=False),
+    'bg_std_differs': dict(T=3, B=2, K=2, n=2, bg_std=0.5),              # d std / d mask term of the likelihood (modules.py:453)
     'c4_like_64px_n6': dict(T=2, B=2, K=2, n=6, H=64, W=64),
     'one_slot': dict(T=3, B=3, K=2, n=1),
     'max_slots_n8': dict(T=2, B=2, K=2, n=8),

@@ -37,6 +37,7 @@ def run_cuda(cfg, imgs, params, noise, rows_per_cta=None, cluster=None):
         packed = ops.pack_params(ccfg, flat)
         nz = {k: torch.from_numpy(v).to(dev) for k, v in noise.items()}
         out = ops.forward(ccfg, packed, torch.from_numpy(imgs).to(dev), nz)
+        obj = ops.objective(out['log_weights_per_timestep'], out['discrete_log_prob'], cfg.B, cfg.K)
         torch.cuda.synchronize()
     finally:
         os.environ.pop('SQAIR_ROWS_PER_CTA', None)
@@ -45,7 +46,9 @@ def run_cuda(cfg, imgs, params, noise, rows_per_cta=None, cluster=None):
             os.environ['SQAIR_ROWS_PER_CTA'] = old
         if oldc is not None:
             os.environ['SQAIR_CLUSTER'] = oldc
-    return {k: v.cpu().numpy() for k, v in out.items()}
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    res['_objective'] = obj['scalars'].cpu().numpy()
+    return res
 
 
 CASES = {
@@ -55,6 +58,7 @@ CASES = {
     'rw_prior': dict(T=3, B=2, K=2, n=2, prior_type='rw'),
     'guided_geom': dict(T=3, B=2, K=2, n=2, prior_type='guided', disc_prior_type='geom'),
     'no_rec_no_mask': dict(T=3, B=2, K=1, n=2, rec_where_prior=False, masked_glimpse=False),
+    'bg_std_differs': dict(T=3, B=2, K=2, n=2, bg_std=0.5),             # modules.py:406-426,453: std = mask fg + (1 - mask) bg
     'c4_like_64px_n6': dict(T=2, B=2, K=2, n=6, H=64, W=64),
     # edges: a single slot, the maximum slot count, one frame, one row, non-square canvases (one of them with
     # H*W not a multiple of 4: frames are then read from global memory instead of the TMA-staged copy)
@@ -71,9 +75,9 @@ CASES = {
 def test_forward_parity(name):
     cfg = O.Cfg(**CASES[name])
     imgs, params, noise = TL.make_inputs(cfg)
-    want, _ = TL.run_oracle(cfg, imgs, params, noise)
+    want, obj = TL.run_oracle(cfg, imgs, params, noise)
     got = run_cuda(cfg, imgs, params, noise)
-    bad = TL.compare_outputs(got, want)
+    bad = TL.compare_outputs(got, want) + TL.compare_objective(got['_objective'], obj, cfg)
     assert not bad, '\n'.join(bad)
 
 
@@ -95,7 +99,7 @@ def test_full_size_c2_parity():
     imgs, params, noise = TL.make_inputs(cfg)
     want, obj = TL.run_oracle(cfg, imgs, params, noise)
     got = run_cuda(cfg, imgs, params, noise)
-    bad = TL.compare_outputs(got, want)
+    bad = TL.compare_outputs(got, want) + TL.compare_objective(got['_objective'], obj, cfg)   # ELBO-VAE / IWAE, ESS, targets
     assert not bad, '\n'.join(bad)
     assert 0.05 < want['presence'].mean() < 0.95     # both branches exercised
 
@@ -106,7 +110,7 @@ def test_full_size_c4_parity():
     imgs, params, noise = TL.make_inputs(cfg)
     want, obj = TL.run_oracle(cfg, imgs, params, noise)
     got = run_cuda(cfg, imgs, params, noise)
-    bad = TL.compare_outputs(got, want)
+    bad = TL.compare_outputs(got, want) + TL.compare_objective(got['_objective'], obj, cfg)   # ELBO-VAE / IWAE, ESS, targets
     assert not bad, '\n'.join(bad)
 
 
@@ -117,8 +121,35 @@ def test_c5_long_rollout_parity():
     imgs, params, noise = TL.make_inputs(cfg)
     want, obj = TL.run_oracle(cfg, imgs, params, noise)
     got = run_cuda(cfg, imgs, params, noise)
-    bad = TL.compare_outputs(got, want)
+    bad = TL.compare_outputs(got, want) + TL.compare_objective(got['_objective'], obj, cfg)   # ELBO-VAE / IWAE, ESS, targets
     assert not bad, '\n'.join(bad)
+
+
+def test_one_packed_buffer_serves_calls_with_different_rows_per_cluster():
+    """The packed parameters depend on the cluster size only; the per-call layer table (shared-memory offsets, strides,
+    frame staging) is NOT part of them.  One buffer, two batch sizes that the library runs with different rows per
+    cluster: both must match the oracle."""
+    ops, dev = _gpu()
+    from sqair_b200 import _capi
+    seen = {}
+    for B in (1, 2, 3, 4, 6):
+        s = _capi.query_sizes(TL.capi_cfg(O.Cfg(T=2, B=B, K=5, n=2)))
+        seen.setdefault(s.cluster_size, {}).setdefault(s.rows_per_cta, B)
+    pair = next(((c, list(r.values())) for c, r in seen.items() if len(r) >= 2), None)
+    assert pair is not None, 'no two batch sizes share a cluster size with different rows per cluster: %r' % seen
+    (Ba, Bb) = pair[1][:2]
+    cfg_a, cfg_b = O.Cfg(T=2, B=Ba, K=5, n=2), O.Cfg(T=2, B=Bb, K=5, n=2)
+    imgs, params, noise = TL.make_inputs(cfg_a if Ba > Bb else cfg_b)
+    flat = O.flatten_params(params, cfg_a).to(dev)
+    packed = ops.pack_params(TL.capi_cfg(cfg_a), flat)                  # packed ONCE
+    for cfg in (cfg_a, cfg_b, cfg_a):
+        im = np.ascontiguousarray(imgs[:, :cfg.B])
+        nz = {k: np.ascontiguousarray(v[:, :cfg.B * cfg.K]) for k, v in noise.items()}
+        want, _ = TL.run_oracle(cfg, im, params, nz)
+        out = ops.forward(TL.capi_cfg(cfg), packed, torch.from_numpy(im).to(dev), {k: torch.from_numpy(v).to(dev) for k, v in nz.items()})
+        torch.cuda.synchronize()
+        bad = TL.compare_outputs({k: v.cpu().numpy() for k, v in out.items()}, want)
+        assert not bad, 'B=%d: %s' % (cfg.B, '\n'.join(bad))
 
 
 def test_device_noise_matches_numpy_philox():

@@ -160,3 +160,35 @@ def test_synthetic_sequences_shape_and_range():
     empty = [b for b in range(6) if nums[b] == 0]
     for b in empty:
         assert imgs[:, b].max() == 0.
+
+
+def test_oracle_gru_against_torch_grucell():
+    """Independent form of the Sonnet GRU: h' = (1 - z) h + z c with z = sigmoid(x Wz + h Uz + bz),
+    r = sigmoid(x Wr + h Ur + br), c = tanh(x Wh + (r h) Uh + bh).  torch.nn.GRUCell computes
+    h' = (1 - z') n + z' h with n = tanh(W_in x + b_in + r (W_hn h + b_hn)): the two agree when z' = 1 - z -- i.e. with the
+    update-gate weights negated -- provided the candidate uses (r * h) Uh, which GRUCell does NOT (it applies r after the
+    matrix product).  So the check runs GRUCell's gates and rebuilds the candidate the Sonnet way from its own r."""
+    torch.manual_seed(0)
+    nin, nh, B = 7, 5, 4
+    scope = 'g'
+    p = {scope + '/' + k: torch.randn((nin if k[0] == 'w' else nh), nh) * 0.5 for k in ('wz', 'wr', 'wh', 'uz', 'ur', 'uh')}
+    p.update({scope + '/' + k: torch.randn(nh) * 0.5 for k in ('bz', 'br', 'bh')})
+    x, h = torch.randn(B, nin), torch.randn(B, nh)
+    got = O.gru(p, scope, x, h)
+    got = got[0] if isinstance(got, tuple) else got
+    cell = torch.nn.GRUCell(nin, nh)
+    with torch.no_grad():     # GRUCell rows: [r | z | n]; z' = 1 - z  <=>  negate the z weights
+        cell.weight_ih.copy_(torch.cat((p['g/wr'].T, -p['g/wz'].T, p['g/wh'].T)))
+        cell.weight_hh.copy_(torch.cat((p['g/ur'].T, -p['g/uz'].T, p['g/uh'].T)))
+        cell.bias_ih.copy_(torch.cat((p['g/br'], -p['g/bz'], p['g/bh'])))
+        cell.bias_hh.zero_()
+        gi, gh = x @ cell.weight_ih.T + cell.bias_ih, h @ cell.weight_hh.T
+        r = torch.sigmoid(gi[:, :nh] + gh[:, :nh])
+        zc = torch.sigmoid(gi[:, nh:2 * nh] + gh[:, nh:2 * nh])                  # = 1 - z
+        cand = torch.tanh(gi[:, 2 * nh:] + (r * h) @ p['g/uh'])                   # Sonnet: reset applied BEFORE the product
+        want = (1 - zc) * cand + zc * h
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
+    # and the gates themselves are GRUCell's (same r, z' = 1 - z): with Uh = identity-free check of the torch form
+    lin_cell = cell(x, h)
+    n_torch = torch.tanh(gi[:, 2 * nh:] + r * gh[:, 2 * nh:])
+    torch.testing.assert_close(lin_cell, (1 - zc) * n_torch + zc * h, rtol=1e-5, atol=1e-6)
