@@ -1097,6 +1097,13 @@ int sqair_stn_glimpse(const float* img, const float* where, float* glimpse, int3
 int sqair_wgrad(const float* x, const float* dy, float* dw, int32_t M, int32_t K, int32_t N, int32_t accumulate, void* stream) {
     if (!x || !dy || !dw || M < 1 || K < 1 || N < 1) return fail(SQAIR_EINVAL, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
+    {   // Blackwell path: TMA-fed tcgen05.mma (3xTF32) with the accumulator in TMEM, when TMA can describe the operands
+        const sqi::TcOperand ox{x, (int64_t)K, 0, 1}, oy{dy, (int64_t)N, 0, 1};
+        if (sqi::wgrad_tc_supported(ox, oy, M, K, N)) {
+            if (!accumulate) CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)K * N * sizeof(float), st));
+            return sqi::wgrad_tc(ox, oy, dw, N, M, K, N, st);
+        }
+    }
     const int tiles = ((N + WG_T - 1) / WG_T) * ((K + WG_T - 1) / WG_T);
     // split M so that the grid covers the 148 SMs a few times over; partial tiles then meet by atomicAdd
     int msplit = (4 * 148 + tiles - 1) / tiles;

@@ -882,7 +882,8 @@ inline BwdLayout build_bwd_layout(const sqair_cfg& c, const Plan& plan) {
         int e = n;
         if (l == L_ENC1 || l == L_ENC2 || l == L_ENC3) e = 3 * n;
         if (l == L_IMG1 || l == L_IMG2 || l == L_RN1 || l == L_SP1 || l == L_SP2) e = 1;
-        L.dy_e[l] = e; L.dy_w[l] = plan.LB[l].NU;
+        L.dy_e[l] = e;
+        L.dy_w[l] = plan.LB[l].NU >= 32 ? (plan.LB[l].NU + 3) / 4 * 4 : plan.LB[l].NU;      // 16-byte row stride: TMA-addressable
         L.dy_off[l] = take((int64_t)T * rows * e * L.dy_w[l]);
     }
     L.dyz_begin = cur;

@@ -30,4 +30,16 @@ struct Shape {
 std::string choose_shape(const sqair_cfg& c, const std::vector<sq::ParamEntry>& tab, Shape& out);
 int env_int(const char* name);
 
+// Weight-gradient GEMM on the tcgen05 tensor cores (sqair_wgrad_tc.cu): dW[k, n] += sum_m X[m, k] dY[m, n].
+// Row m = z * ny + y of an operand starts at p + z * outer + y * inner (floats); ny <= 1: p + m * outer.
+struct TcOperand {
+    const float* p;
+    int64_t outer, inner;
+    int ny;
+};
+// operands TMA can describe (16-byte aligned base and strides), a reduction block that fits the pipeline, a tile worth it
+bool wgrad_tc_supported(const TcOperand& x, const TcOperand& dy, int M, int K, int N);
+// adds into dw (row stride ldw): zero or initialise it first
+int wgrad_tc(const TcOperand& x, const TcOperand& dy, float* dw, int ldw, int M, int K, int N, cudaStream_t st);
+
 }  // namespace sqi

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <math.h>
+#include <stdio.h>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -418,7 +419,7 @@ struct CudaBackend {
     int rows;
     int scratch_bytes;
     cudaError_t err = cudaSuccess;
-    long launches = 0;
+    long launches = 0, tc_launches = 0;
 
     void check() {
         if (err == cudaSuccess) err = cudaGetLastError();
@@ -449,6 +450,14 @@ struct CudaBackend {
         check();
     }
     void wgrad(const WgradArgs& A) {
+        {   // Blackwell path (sqair_wgrad_tc.cu): TMA + tcgen05.mma + TMEM, whenever TMA can describe both operands
+            const sqi::TcOperand ox{A.x.p, A.x.outer, A.x.inner, A.ny}, oy{A.dy.p, A.dy.outer, A.dy.inner, A.ny};
+            if (sqi::wgrad_tc_supported(ox, oy, A.M, A.K, A.N)) {
+                if (sqi::wgrad_tc(ox, oy, A.dw, A.ldw, A.M, A.K, A.N, st) != SQAIR_OK && err == cudaSuccess) err = cudaErrorInvalidValue;
+                ++launches; ++tc_launches;
+                return;
+            }
+        }
         const int tiles = ((A.N + WG_T - 1) / WG_T) * ((A.K + WG_T - 1) / WG_T);
         int msplit = (4 * 148 + tiles - 1) / tiles;
         const int max_split = (A.M + 4 * WG_MC - 1) / (4 * WG_MC);
@@ -560,6 +569,7 @@ int sqair_backward(const sqair_cfg* cfg, const float* params, const float* bw_pa
     drv.run(d_params);
     if (be.err != cudaSuccess) return sqi::cuda_fail(be.err, "sqair_backward");
     if (n_launches) *n_launches = (int32_t)be.launches;
+    if (sqi::env_int("SQAIR_VERBOSE")) fprintf(stderr, "sqair_backward: %ld launches, %ld of them tcgen05 weight-gradient GEMMs\n", be.launches, be.tc_launches);
     return SQAIR_OK;
 }
 

@@ -308,7 +308,9 @@ def test_canvas_ll_grad_op():
 
 @pytest.mark.parametrize('M,K,N', [(6400, 672, 256), (1600, 264, 109), (37, 5, 3), (640, 400, 256)])
 def test_wgrad_op(M, K, N):
-    """Weight-gradient GEMM of the backward pass (x^T dy, 3xTF32-split tensor-core path) against float64."""
+    """Weight-gradient GEMM of the backward pass (x^T dy; tcgen05 3xTF32 path for TMA-addressable shapes, else the mma.sync
+    split kernel) against float64.  Tolerance: 1e-5 relative + 8e-6 of the typical magnitude sqrt(M) * 0.1 -- the TMEM
+    accumulator rounds toward zero on each of the ~100 chained MMAs of a CTA (measured worst case 5e-6 of that scale)."""
     ops, dev = _gpu()
     rng = np.random.default_rng(6)
     x = rng.standard_normal((M, K)).astype(np.float32)
@@ -316,10 +318,10 @@ def test_wgrad_op(M, K, N):
     want = x.astype(np.float64).T @ dy.astype(np.float64)
     got = ops.wgrad(torch.from_numpy(x).to(dev), torch.from_numpy(dy).to(dev)).cpu().numpy()
     scale = np.sqrt(M) * 0.1
-    np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-6 * scale)
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=8e-6 * scale)
     base = torch.from_numpy(rng.standard_normal((K, N)).astype(np.float32)).to(dev)
     got2 = ops.wgrad(torch.from_numpy(x).to(dev), torch.from_numpy(dy).to(dev), out=base.clone()).cpu().numpy()
-    np.testing.assert_allclose(got2, want + base.cpu().numpy().astype(np.float64), rtol=1e-5, atol=2e-6 * scale + 1e-6)
+    np.testing.assert_allclose(got2, want + base.cpu().numpy().astype(np.float64), rtol=1e-5, atol=8e-6 * scale + 1e-6)
 
 
 @pytest.mark.parametrize('M,K,N', [(6400, 672, 256), (1600, 264, 109), (37, 5, 3), (640, 400, 256)])

@@ -41,7 +41,7 @@ for k in w32:
     b = w64[k].reshape(T, rows, -1)[:, same]
     d = np.abs(a - b)
     rel = (d / np.maximum(np.abs(b), 1e-30))[np.abs(b) > 1e-3]
-    tol = 'atol %.3g + 1e-4 rel' % (2e-5 * px) if k in TL.PIXEL_SUMS else ('99.99%% at 1e-4, all 2e-3' if k == 'canvas' else '1e-4 + 1e-4 rel')
+    tol = 'atol %.3g + 1e-4 rel' % (TL.PIXEL_SUM_ATOL * px) if k in TL.PIXEL_SUMS else ('99.995% at 1e-4, all 1e-3' if k == 'canvas' else '1e-4 + 1e-4 rel')
     print('%-34s %12.3e %12.3e %12.3e   %s' % (k, d.max(), rel.max() if rel.size else 0.0, np.abs(b).max(), tol))
 if k:
     c = np.abs(w32['canvas'].reshape(T, rows, -1)[:, same].astype(np.float64) - w64['canvas'].reshape(T, rows, -1)[:, same])
