@@ -183,6 +183,15 @@ enum { SQAIR_OPT_RMSPROP = 0, SQAIR_OPT_ADAM = 1, SQAIR_OPT_MOMENTUM = 2, SQAIR_
 int sqair_optimizer_update(int32_t kind, float* params, const float* grad, float* slot0, float* slot1, int64_t n, float lr,
                            float hyper_a, float hyper_b, float epsilon, float grad_scale, float l2_weight, void* stream);
 
+/* Data path: renders frames of moving sprites on the device -- `TemplateDataset.create`
+ * (data/template.py:58-104: every object pasted at its rounded position, max blend) followed by the uint8 -> float / 255
+ * of data/data.py:199.  atlas [S][cell][cell] uint8 templates (top-left aligned), atlas_hw [S][2] their (height, width),
+ * pos [T][B][n][2] int32 (y, x) of the top-left corner, sprite [B][n] template index or -1 for "no object",
+ * frames [T][B][H][W] float32 (overwritten). */
+int sqair_render_sprites(const uint8_t* atlas, const int32_t* atlas_hw, const int32_t* pos, const int32_t* sprite,
+                         float* frames, int32_t T, int32_t B, int32_t n, int32_t H, int32_t W, int32_t S, int32_t cell,
+                         void* stream);
+
 /* Weight gradient of one dense layer (the GEMM-shaped part of the backward pass): dW [K,N] (+)= X^T dY for
  * the stashed layer inputs X [M,K] and output gradients dY [M,N], M = rows x frames x slots, all row-major fp32.
  * fp32-faithful on the tensor cores (tf32 hi/lo split of both operands, four products, per-k-step fp32 accumulation).

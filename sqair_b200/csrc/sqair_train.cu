@@ -397,6 +397,32 @@ __global__ void __launch_bounds__(256) optimizer_kernel(float* __restrict__ w, c
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// data path: frames of moving sprites rendered on the device (data/template.py:69-104 `TemplateDataset`: every object
+// is pasted at its rounded position with a max blend; uint8 -> float32 / 255 as data/data.py:199 does)
+// ---------------------------------------------------------------------------------------------
+__global__ void render_sprites_kernel(const uint8_t* __restrict__ atlas, const int32_t* __restrict__ atlas_hw, const int32_t* __restrict__ pos,
+                                      const int32_t* __restrict__ sprite, float* __restrict__ frames, int T, int B, int n, int H, int W,
+                                      int S, int cell) {
+    const int64_t total = (int64_t)T * B * H * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)((i / W) % H);
+        const int64_t tb = i / ((int64_t)H * W);
+        const int b = (int)(tb % B);
+        int v = 0;
+        for (int j = 0; j < n; ++j) {
+            const int sp = sprite[b * n + j];
+            if (sp < 0 || sp >= S) continue;
+            const int y0 = pos[(tb * n + j) * 2], x0 = pos[(tb * n + j) * 2 + 1];
+            const int dy = y - y0, dx = x - x0;
+            if (dy < 0 || dx < 0 || dy >= atlas_hw[sp * 2] || dx >= atlas_hw[sp * 2 + 1]) continue;
+            v = max(v, (int)atlas[((int64_t)sp * cell + dy) * cell + dx]);
+        }
+        frames[i] = (float)v / 255.f;
+    }
+}
+
 static void fill_piece_tab(const Shape& sh, BPieceTab& bt) {
     memset(&bt, 0, sizeof(bt));
     bt.n = (int)sh.pieces.size();
@@ -588,6 +614,17 @@ int sqair_optimizer_update(int32_t kind, float* params, const float* grad, float
         case SQAIR_OPT_SGD: optimizer_kernel<SQAIR_OPT_SGD><<<blocks, 256, 0, st>>>(params, grad, slot0, slot1, n, lr, hyper_a, hyper_b, epsilon, grad_scale, l2_weight); break;
         default: return fail(SQAIR_EINVAL, "unknown optimiser kind");
     }
+    CUDA_TRY(cudaGetLastError());
+    return SQAIR_OK;
+}
+
+int sqair_render_sprites(const uint8_t* atlas, const int32_t* atlas_hw, const int32_t* pos, const int32_t* sprite, float* frames, int32_t T,
+                         int32_t B, int32_t n, int32_t H, int32_t W, int32_t S, int32_t cell, void* stream) {
+    if (!atlas || !atlas_hw || !pos || !sprite || !frames || T < 1 || B < 1 || n < 0 || H < 1 || W < 1 || S < 1 || cell < 1)
+        return fail(SQAIR_EINVAL, "bad argument");
+    const int64_t total = (int64_t)T * B * H * W;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+    render_sprites_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(atlas, atlas_hw, pos, sprite, frames, T, B, n, H, W, S, cell);
     CUDA_TRY(cudaGetLastError());
     return SQAIR_OK;
 }

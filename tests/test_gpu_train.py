@@ -169,3 +169,14 @@ def test_two_ranks_reproduce_one_rank_over_nccl():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert 'DP_CHECK_OK' in r.stdout
+
+
+def test_device_renderer_matches_the_host_generator():
+    """sqair_render_sprites (data path) against the numpy renderer of the same tracks: identical pixels."""
+    from sqair_b200 import data
+    dev = torch.device('cuda:0')
+    T, B, H, W, n = 6, 9, 50, 50, 3
+    imgs, nums, coords, labels = data.moving_sprites(T, B, H, W, n, seed=5, return_tracks=True)
+    got = data.render_on_device(coords, labels, nums, H, W, dev, seed=5).cpu().numpy()
+    np.testing.assert_array_equal(got, imgs)
+    assert imgs.max() > 0.5
