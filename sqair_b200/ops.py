@@ -153,13 +153,17 @@ def objective(log_w_t: torch.Tensor, disc_lp_t: torch.Tensor, B: int, K: int):
     return dict(log_weights=lw, elbo_iwae_per_example=pe, importance_weights=iw, scalars=sc)
 
 
-def objective_grad(log_w_t: torch.Tensor, disc_lp_t: torch.Tensor, B: int, K: int):
+def objective_grad(log_w_t: torch.Tensor, disc_lp_t: torch.Tensor, B: int, K: int, out=None):
     """Gradients of the VIMCO target (model.py:150-158 / targets.py:62-75) w.r.t. the rows' summed log weights and
     discrete log-probs, both [B,K]; every per-frame term of a row receives the row's value."""
     _need_cuda(log_w_t, disc_lp_t)
     T = log_w_t.shape[0]
-    d_lw = torch.empty(B, K, dtype=torch.float32, device=log_w_t.device)
-    d_lp = torch.empty(B, K, dtype=torch.float32, device=log_w_t.device)
+    if out is not None:
+        d_lw, d_lp = out
+        _need_cuda(d_lw, d_lp)
+    else:
+        d_lw = torch.empty(B, K, dtype=torch.float32, device=log_w_t.device)
+        d_lp = torch.empty(B, K, dtype=torch.float32, device=log_w_t.device)
     check(_capi.lib().sqair_objective_grad(_ptr(log_w_t), _ptr(disc_lp_t), T, B, K, _ptr(d_lw), _ptr(d_lp), _stream()))
     return d_lw, d_lp
 

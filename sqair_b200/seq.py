@@ -127,27 +127,61 @@ class SequentialAIR(object):
                 outputs=ops.alloc_outputs(cfg, device))
         return self._train_bufs[key]
 
-    def forward_backward(self, obs, k_particles=1, noise=None, seed=0, row_offset=0, vimco=None):
+    def forward_backward(self, obs, k_particles=1, noise=None, seed=0, row_offset=0, vimco=None, use_graph=True):
         """Forward pass that keeps what the adjoint needs, particle objective, and the gradient of the training target
         (VIMCO / T when K > 1, else -elbo_iwae / T: model.py:150-158) w.r.t. every variable -- the work of
         `opt.compute_gradients(target)` (model.py:160).  Returns (outputs, objective dict, flat gradient in
-        `sqair_param_layout` order).  The returned tensors live in per-shape buffers that the next call overwrites."""
+        `sqair_param_layout` order).  The returned tensors live in per-shape buffers that the next call overwrites.
+        The ~1 450 launches of the backward pass are replayed from a CUDA graph after the first call of a shape (all
+        its operands live in the per-shape buffers, so the graph is static): 14.5 -> 12.2 ms at BASELINE configs[1]."""
         if obs.dim() == 5:
             if obs.shape[-1] != 1:
                 raise NotImplementedError('multi-channel frames')
             obs = obs[..., 0]
-        obs = obs.contiguous()
         T, B, H, W = obs.shape
         cfg = self.make_cfg(T, B, k_particles, H, W)
         store = self.param_store(H, W, obs.device)
         buf = self._train_buffers(cfg, obs.device)
-        if noise is None:
-            noise = ops.fill_noise(cfg, seed, row_offset, noise=buf.noise)
         vimco = k_particles > 1 if vimco is None else vimco
-        out = ops.forward(cfg, store.packed(cfg), obs, noise, buf.outputs, stash=buf.stash)
+        if 'obs' not in buf:
+            buf.obs = torch.empty(T, B, H, W, dtype=torch.float32, device=obs.device)
+            buf.d_lw = torch.empty(B, k_particles, dtype=torch.float32, device=obs.device)
+            buf.d_lp = torch.empty(B, k_particles, dtype=torch.float32, device=obs.device)
+            buf.graphs = {}
+        buf.obs.copy_(obs, non_blocking=True)              # (also the host-to-device copy when `obs` is pinned host memory)
+        if noise is None:
+            ops.fill_noise(cfg, seed, row_offset, noise=buf.noise)
+        else:
+            for k in buf.noise:
+                buf.noise[k].copy_(noise[k], non_blocking=True)
+        out = ops.forward(cfg, store.packed(cfg), buf.obs, buf.noise, buf.outputs, stash=buf.stash)
         lw, lp = out['log_weights_per_timestep'], out['discrete_log_prob']
         obj = ops.objective(lw, lp, B, k_particles)
-        d_lw, d_lp = ops.objective_grad(lw, lp, B, k_particles)
-        d_params, _ = ops.backward(cfg, store.flat, store.backward_params(cfg), obs, noise, buf.stash, d_lw,
-                                   d_lp if vimco else None, workspace=buf.workspace, d_params=buf.d_params)
-        return AttrDict(out), obj, d_params
+        ops.objective_grad(lw, lp, B, k_particles, out=(buf.d_lw, buf.d_lp))
+        bwp = store.backward_params(cfg)
+
+        def run_backward():
+            ops.backward(cfg, store.flat, bwp, buf.obs, buf.noise, buf.stash, buf.d_lw, buf.d_lp if vimco else None,
+                         workspace=buf.workspace, d_params=buf.d_params)
+
+        key = (bool(vimco), bwp.data_ptr(), store.flat.data_ptr())
+        state = buf.graphs.get(key)
+        if not use_graph or torch.cuda.is_current_stream_capturing():
+            run_backward()
+        elif state is None:
+            run_backward()                                  # first call of this shape: eager (also warms every cache)
+            buf.graphs[key] = 'warm'
+        elif state == 'warm':
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream(device=obs.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    run_backward()
+            torch.cuda.current_stream().wait_stream(side)
+            buf.graphs[key] = g
+            g.replay()
+        else:
+            state.replay()
+        return AttrDict(out), obj, buf.d_params

@@ -129,9 +129,13 @@ def test_training_steps_follow_an_oracle_driven_loop():
     got = O.unflatten_params(torch.from_numpy(store.flat.cpu().numpy() - flat0), cfg)
     want = O.unflatten_params(torch.from_numpy(w - flat0), cfg)
     bad = []
-    for k in want:            # 0.5 % of the change + 0.2 % of the variable's largest change + two ulps of the parameter itself
+    # RMSProp turns a gradient g into lr g / sqrt(ms): saturated (~3 lr per step) where |g| is large, ~lr g where it is small.
+    # The gradient parity bar allows an absolute error of 2e-4 max|g| per variable; on an unsaturated entry of a variable
+    # whose largest gradient is ~300 that is ~0.06 lr per step = ~1 % of the variable's largest parameter change.  So:
+    # 0.5 % of the change + 2 % of the variable's largest change + two ulps of the parameter itself.
+    for k in want:
         g_, w_, p_ = got[k].numpy(), want[k].numpy(), params[k].numpy()
-        tol = 5e-3 * np.abs(w_) + 2e-3 * np.abs(w_).max() + 2.4e-7 * np.abs(p_)
+        tol = 5e-3 * np.abs(w_) + 2e-2 * np.abs(w_).max() + 2.4e-7 * np.abs(p_)
         if (np.abs(g_ - w_) > tol).any():
             bad.append('%s: %d entries, worst %.3e of %.3e' % (k, int((np.abs(g_ - w_) > tol).sum()), np.abs(g_ - w_).max(), np.abs(w_).max()))
     assert not bad, '\n'.join(bad)
