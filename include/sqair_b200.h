@@ -158,6 +158,17 @@ int sqair_forward_train(const sqair_cfg* cfg, const float* packed_params, const 
                         const float* eps_where, const float* eps_what, const float* u_pres,
                         const sqair_outputs* out, float* stash, void* stream);
 
+/* Generation (seq.py:46,198-203; sqair_modules.py:157-170,294-302): `SequentialAIR(..., sample_from_prior=True,
+ * generate_after=g)`.  The inference networks still run on every frame; in addition every propagated slot draws
+ * (what, where, presence) from the propagation prior with the second noise set (same shapes as the first; slots
+ * 0 .. n-1 are used), the posterior log-probabilities are evaluated at those draws, and in frames t > g (only when
+ * g > 0) the draws replace the posterior samples while discovery adds no objects -- the model rolls forward from its
+ * prior.  Same outputs as sqair_forward. */
+int sqair_forward_generate(const sqair_cfg* cfg, const float* packed_params, const float* obs,
+                           const float* eps_where, const float* eps_what, const float* u_pres,
+                           const float* eps_where_prior, const float* eps_what_prior, const float* u_pres_prior,
+                           int32_t generate_after, const sqair_outputs* out, void* stream);
+
 /* canonical flat parameters -> backward parameter buffer (once per parameter update, like sqair_pack_params). */
 int sqair_pack_backward(const sqair_cfg* cfg, const float* params, float* bw_params, void* stream);
 

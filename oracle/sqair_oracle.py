@@ -58,6 +58,8 @@ class Cfg:
     min_std: float = 1e-2
     where_mean: tuple = (-2., -2., 0., 0.)   # only used when rec_where_prior is False
     where_std: tuple = (1., 1., 1., 1.)
+    sample_from_prior: bool = False          # seq.py:46,63: evaluate q at prior samples; with generate_after also ...
+    generate_after: int = -1                 # ... replace the latents by prior samples in frames t > generate_after (seq.py:198-203)
 
     @property
     def P(self):
@@ -476,17 +478,28 @@ def sequential_ssm(p, cfg, img, z_tm1, temporal_state, eps_where, eps_what, u_pr
     return ho, ho['presence'][..., 0].sum(-1)
 
 
-def propagate(p, cfg, img, z_tm1, temporal_state, prior_state, eps_where, eps_what, u_pres):
-    """sqair_modules.py:250-329."""
+def propagate(p, cfg, img, z_tm1, temporal_state, prior_state, eps_where, eps_what, u_pres, do_generate=False,
+              prior_noise=None):
+    """sqair_modules.py:250-329.  `prior_noise` = (eps_where, eps_what, u_pres) of the prior draws, each [B', n, ...]
+    (only with cfg.sample_from_prior)."""
     pres_tm1 = z_tm1[2][..., 0]
     prior_stats, prior_state = propagate_prior(p, cfg, z_tm1, prior_state)
     ho, num_steps = sequential_ssm(p, cfg, img, z_tm1, temporal_state, eps_where, eps_what, u_pres)
-    pres = ho['presence'][..., 0]
+    pres = ho['presence'][..., 0]                                   # (:286: taken BEFORE any replacement and used for all masks)
     pw_loc, pw_scale, pa_loc, pa_scale, p_logit = prior_stats
+    s_what, s_where, s_pres = ho['what'], ho['where'], pres         # :292 samples at which q is evaluated
+    if cfg.sample_from_prior:                                       # :294-302
+        ew, ea, up = prior_noise
+        s_what = pa_loc + pa_scale * ea                             # [p.sample() for p in priors] (propagate.py:113-120)
+        s_where = pw_loc + pw_scale * ew
+        s_pres = (up < torch.sigmoid(p_logit[..., 0])).to(pres.dtype)
+        if do_generate:
+            ho = dict(ho)
+            ho['what'], ho['where'], ho['presence'] = s_what, s_where, s_pres[..., None]
     # posteriors (sqair_modules.py:49-60,290,304)
-    q_what = normal_log_prob(ho['what'], ho['what_loc'], ho['what_scale']).sum(-1)
-    q_where = mvn_tril_log_prob(ho['where'], ho['where_loc'], affine_diag_normal_tril(p, ho['where_scale']))
-    q_pres = bernoulli_log_prob(pres, ho['presence_logit'][..., 0])
+    q_what = normal_log_prob(s_what, ho['what_loc'], ho['what_scale']).sum(-1)
+    q_where = mvn_tril_log_prob(s_where, ho['where_loc'], affine_diag_normal_tril(p, ho['where_scale']))
+    q_pres = bernoulli_log_prob(s_pres, ho['presence_logit'][..., 0])
     # priors (propagate.py:113-120; sqair_modules.py:306-307)
     p_what = normal_log_prob(ho['what'], pa_loc, pa_scale).sum(-1)
     p_where = normal_log_prob(ho['where'], pw_loc, pw_scale).sum(-1)
@@ -559,7 +572,22 @@ def recurrent_normal_log_prob(p, cfg, samples, conditioning):
     return torch.stack(lps, 1)
 
 
-def discover(p, cfg, img, conditioning, time_step, prior_conditioning, eps_where, eps_what, u_pres):
+def recurrent_normal_sample(p, cfg, conditioning, eps):
+    """modules.py:621-630 `RecurrentNormal.sample`: like the log-prob loop, but each step feeds its own draw."""
+    Bp, n, _ = eps.shape
+    state = p[_RN + 'discovery/discover/recurrent_normal_impl/vanilla_rnn_initial_state_0/w'].expand(Bp, -1)
+    state = F.elu(linear(p, _RN + 'linear_1', torch.cat((state, conditioning), -1)))
+    prev = p[_RN + 'init_sample'].expand(Bp, -1)
+    out = []
+    for i in range(n):
+        stats = linear(p, _RN + 'linear', vanilla_rnn(p, _RN + 'vanilla_rnn', prev, state))
+        prev = stats[:, :4] + (F.softplus(stats[:, 4:]) + 1e-2) * eps[:, i]
+        out.append(prev)
+    return torch.stack(out, 1)
+
+
+def discover(p, cfg, img, conditioning, time_step, prior_conditioning, eps_where, eps_what, u_pres, do_generate=False,
+             prior_noise=None):
     """sqair_modules.py:94-229."""
     Bp = img.shape[0]
     n = cfg.n
@@ -571,8 +599,17 @@ def discover(p, cfg, img, conditioning, time_step, prior_conditioning, eps_where
                                        eps_where[:, k], eps_what[:, k], u_pres[:, k])
         outs.append(o)
     ho = _stack(outs)
+    num_steps = ho['presence'][..., 0].sum(-1)                                        # :145 (before any replacement)
+    if cfg.sample_from_prior and do_generate:                                         # :157-170
+        ew, ea, _ = prior_noise
+        ho = dict(ho)
+        ho['what'] = ea                                                               # N(0, 1) prior (:79)
+        if cfg.rec_where_prior:
+            ho['where'] = recurrent_normal_sample(p, cfg, torch.cat((conditioning, prior_conditioning), -1), ew)
+        else:
+            ho['where'] = torch.tensor(cfg.where_mean, dtype=ew.dtype) + torch.tensor(cfg.where_std, dtype=ew.dtype) * ew
+        ho['presence'] = torch.zeros_like(ho['presence'])                             # pres_sample * 0. (:164): nothing is discovered
     pres = ho['presence'][..., 0]
-    num_steps = pres.sum(-1)                                                          # :145
     # posteriors (:177-179)
     q_what = normal_log_prob(ho['what'], ho['what_loc'], ho['what_scale']).sum(-1) * pres
     q_where = normal_log_prob(ho['where'], ho['where_loc'], ho['where_scale']).sum(-1) * pres
@@ -675,15 +712,20 @@ def air_decoder(p, cfg, what, where, presence):
     return canvas, out_std, g.reshape(Bp, n, cfg.G, cfg.G)
 
 
-def sqair_timestep(p, cfg, img, z_tm1, temporal_state, prior_state, last_used_id, prev_ids, t, noise_t):
+def sqair_timestep(p, cfg, img, z_tm1, temporal_state, prior_state, last_used_id, prev_ids, t, noise_t, prior_noise_t=None):
     """sqair_modules.py:446-512."""
     n = cfg.n
     ew, ea, up = noise_t
-    prop = propagate(p, cfg, img, z_tm1, temporal_state, prior_state, ew[:, :n], ea[:, :n], up[:, :n])
+    dg = cfg.sample_from_prior and cfg.generate_after > 0 and t > cfg.generate_after   # seq.py:198-203
+    pn_prop = pn_disc = None
+    if cfg.sample_from_prior:
+        pn_prop = tuple(x[:, :n] for x in prior_noise_t)
+        pn_disc = tuple(x[:, n:] for x in prior_noise_t)
+    prop = propagate(p, cfg, img, z_tm1, temporal_state, prior_state, ew[:, :n], ea[:, :n], up[:, :n], dg, pn_prop)
     conditioning = encode_latents(p, prop['what'], prop['where'], prop['presence'])     # :501
     prior_logit = prop['prior_stats'][-1][..., 0]
     expected = ((torch.sigmoid(prior_logit) - .5) / n).sum(-1, keepdim=True)             # :505-507
-    disc = discover(p, cfg, img, conditioning, t, expected, ew[:, n:], ea[:, n:], up[:, n:])
+    disc = discover(p, cfg, img, conditioning, t, expected, ew[:, n:], ea[:, n:], up[:, n:], dg, pn_disc)
     ho, ids, prior_state, temporal_state, last_used_id = choose_latents(p, cfg, prop, disc, last_used_id, prev_ids)
     return prop, disc, ho, ids, prior_state, temporal_state, last_used_id
 
@@ -712,8 +754,11 @@ def sequential_air(p, cfg, obs, noise):
     for t in range(T):
         img = obs[t]
         noise_t = (noise['eps_where'][t], noise['eps_what'][t], noise['u_pres'][t])
+        pn_t = None
+        if cfg.sample_from_prior:          # the prior draws (samples of `p.sample()`): a second set of the same shapes
+            pn_t = (noise['eps_where_prior'][t], noise['eps_what_prior'][t], noise['u_pres_prior'][t])
         prop, disc, ho, ids, prior, temporal, last_id = sqair_timestep(
-            p, cfg, img, z, temporal, prior, last_id, prev_ids, t, noise_t)
+            p, cfg, img, z, temporal, prior, last_id, prev_ids, t, noise_t, pn_t)
         z = (ho['what'], ho['where'], ho['presence'], ho['presence_logit'])
         prev_ids = ids
         canvas, std, glimpse = air_decoder(p, cfg, ho['what'], ho['where'], ho['presence'])

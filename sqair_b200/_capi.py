@@ -118,6 +118,7 @@ def bind(lib):
     lib.sqair_pack_params.argtypes = [C.POINTER(SqairCfg), vp, vp, vp]
     lib.sqair_fill_noise.argtypes = [C.POINTER(SqairCfg), C.c_uint64, i32, vp, vp, vp, vp]
     lib.sqair_forward.argtypes = [C.POINTER(SqairCfg), vp, vp, vp, vp, vp, C.POINTER(SqairOutputs), vp]
+    lib.sqair_forward_generate.argtypes = [C.POINTER(SqairCfg), vp, vp, vp, vp, vp, vp, vp, vp, i32, C.POINTER(SqairOutputs), vp]
     lib.sqair_forward_train.argtypes = [C.POINTER(SqairCfg), vp, vp, vp, vp, vp, C.POINTER(SqairOutputs), vp, vp]
     lib.sqair_query_train_sizes.argtypes = [C.POINTER(SqairCfg), C.POINTER(SqairTrainSizes)]
     lib.sqair_pack_backward.argtypes = [C.POINTER(SqairCfg), vp, vp, vp]
@@ -132,14 +133,14 @@ def bind(lib):
     lib.sqair_stn_glimpse_grad.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.sqair_canvas_ll.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp]
     lib.sqair_canvas_ll_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp]
-    for name in ('sqair_query_sizes sqair_param_layout sqair_pack_params sqair_fill_noise sqair_forward sqair_forward_train '
+    for name in ('sqair_query_sizes sqair_param_layout sqair_pack_params sqair_fill_noise sqair_forward sqair_forward_train sqair_forward_generate '
                  'sqair_query_train_sizes sqair_pack_backward sqair_backward sqair_optimizer_update sqair_render_sprites '
                  'sqair_objective sqair_objective_grad sqair_wgrad sqair_dgrad sqair_stn_glimpse sqair_stn_glimpse_grad sqair_canvas_ll sqair_canvas_ll_grad').split():
         getattr(lib, name).restype = C.c_int
     return lib
 
 
-EXPORTED = ('sqair_last_error sqair_version sqair_query_sizes sqair_param_layout sqair_pack_params sqair_forward_train '
+EXPORTED = ('sqair_last_error sqair_version sqair_query_sizes sqair_param_layout sqair_pack_params sqair_forward_train sqair_forward_generate '
             'sqair_query_train_sizes sqair_pack_backward sqair_backward sqair_optimizer_update sqair_render_sprites '
             'sqair_fill_noise sqair_forward sqair_objective sqair_objective_grad sqair_stn_glimpse sqair_stn_glimpse_grad sqair_canvas_ll sqair_canvas_ll_grad sqair_wgrad sqair_dgrad').split()
 

@@ -37,7 +37,7 @@ int sqi::cuda_fail(cudaError_t e, const char* what) {
 // ---------------------------------------------------------------------------------------------
 // persistent sequence kernel: one cluster of C blocks per R rows, the whole T-frame recursion
 // ---------------------------------------------------------------------------------------------
-template <int R, bool TR>
+template <int R, bool TR, bool GEN>
 __global__ void __launch_bounds__(NT_LAUNCH) sqair_sequence_kernel(const __grid_constant__ Job job) {
     const PlanHdr& plan = c_plan;
     Ctx c;
@@ -54,7 +54,10 @@ __global__ void __launch_bounds__(NT_LAUNCH) sqair_sequence_kernel(const __grid_
         const uint32_t* h = reinterpret_cast<const uint32_t*>(job.prm + plan.phdr_off);
         if (h[0] != PACK_MAGIC || h[1] != (uint32_t)plan.C || h[2] != (uint32_t)plan.NS || h[3] != (uint32_t)plan.PX) __trap();
     }
-    Block<R, TR> blk(c, job, (int)(blockIdx.x / plan.C) * R);
+    // no block writes into a peer's shared memory before every block of the cluster has started (racecheck: "address is
+    // located in a block that might not have entered yet" on the first exchange)
+    if (plan.C > 1) { cluster_arrive(c); cluster_wait(c); }
+    Block<R, TR, GEN> blk(c, job, (int)(blockIdx.x / plan.C) * R);
     blk.run();
     if (plan.C > 1) { cluster_arrive(c); cluster_wait(c); }      // no block exits while peers may still write to it
 #ifdef SQAIR_PROFILE
@@ -142,7 +145,7 @@ static int get_layer_table(const Plan& plan, int device, cudaStream_t st, const 
     return SQAIR_OK;
 }
 
-template <int R, bool TR>
+template <int R, bool TR, bool GEN>
 static int launch_sequence_impl(const Plan& plan, Job job, cudaStream_t st) {
     int device = 0;
     CUDA_TRY(cudaGetDevice(&device));
@@ -154,7 +157,7 @@ static int launch_sequence_impl(const Plan& plan, Job job, cudaStream_t st) {
     rc = upload_plan(plan, st, ds);
     if (rc != SQAIR_OK) return rc;
     const int smem_bytes = plan.sm.total * (int)sizeof(float);
-    CUDA_TRY(cudaFuncSetAttribute(sqair_sequence_kernel<R, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(sqair_sequence_kernel<R, TR, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const int ncl = (plan.rows + R - 1) / R;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -169,7 +172,7 @@ static int launch_sequence_impl(const Plan& plan, Job job, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = plan.C > 1 ? 1 : 0;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, sqair_sequence_kernel<R, TR>, job));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, sqair_sequence_kernel<R, TR, GEN>, job));
     if (!stream_is_capturing(st)) {           // (a captured launch replays with the plan that was resident at capture time)
         cudaEvent_t ev = nullptr;
         for (auto& se : ds.inflight) if (se.first == st) ev = se.second;
@@ -186,10 +189,11 @@ static int launch_sequence_impl(const Plan& plan, Job job, cudaStream_t st) {
     return SQAIR_OK;
 }
 
-// inference (no stash: the stash code is compiled out) or training instantiation
+// inference (no stash: the stash code is compiled out), training, or generation (sample_from_prior) instantiation
 template <int R>
 static int launch_sequence(const Plan& plan, const Job& job, cudaStream_t st) {
-    return job.stash ? launch_sequence_impl<R, true>(plan, job, st) : launch_sequence_impl<R, false>(plan, job, st);
+    if (job.eps_where_prior) return launch_sequence_impl<R, false, true>(plan, job, st);
+    return job.stash ? launch_sequence_impl<R, true, false>(plan, job, st) : launch_sequence_impl<R, false, false>(plan, job, st);
 }
 
 // Launch shape.  R rows per cluster (more rows = fewer re-reads of the weights from L2), C blocks per
@@ -1019,7 +1023,9 @@ int sqair_fill_noise(const sqair_cfg* cfg, uint64_t seed, int32_t row_offset, fl
 }
 
 static int forward_impl(const sqair_cfg* cfg, const float* packed_params, const float* obs, const float* eps_where,
-                        const float* eps_what, const float* u_pres, const sqair_outputs* out, float* stash, void* stream) {
+                        const float* eps_what, const float* u_pres, const sqair_outputs* out, float* stash, void* stream,
+                        const float* eps_where_prior = nullptr, const float* eps_what_prior = nullptr,
+                        const float* u_pres_prior = nullptr, int generate_after = -1) {
     if (!cfg || !packed_params || !obs || !eps_where || !eps_what || !u_pres || !out)
         return fail(SQAIR_EINVAL, "null argument");
     if ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(packed_params)) & 15)
@@ -1037,7 +1043,8 @@ static int forward_impl(const sqair_cfg* cfg, const float* packed_params, const 
                 return fail(SQAIR_EINVAL, "packed_params were packed for a different launch shape (cluster size); "
                                           "call sqair_pack_params with the configuration of this call");
     }
-    Job job{packed_params, obs, eps_where, eps_what, u_pres, *out, env_int("SQAIR_DEBUG_FLAGS"), nullptr, stash};
+    Job job{packed_params, obs, eps_where, eps_what, u_pres, *out, env_int("SQAIR_DEBUG_FLAGS"), nullptr, stash,
+            eps_where_prior, eps_what_prior, u_pres_prior, generate_after};
     cudaStream_t st = (cudaStream_t)stream;
 #ifdef SQAIR_ONLY_R              // tuning builds: one instantiation compiles in seconds
     if (sh.R == SQAIR_ONLY_R) return launch_sequence<SQAIR_ONLY_R>(sh.plan, job, st);
@@ -1063,6 +1070,14 @@ int sqair_forward_train(const sqair_cfg* cfg, const float* packed_params, const 
                         const float* eps_what, const float* u_pres, const sqair_outputs* out, float* stash, void* stream) {
     if (!stash) return fail(SQAIR_EINVAL, "null stash (sqair_query_sizes: stash_floats)");
     return forward_impl(cfg, packed_params, obs, eps_where, eps_what, u_pres, out, stash, stream);
+}
+
+int sqair_forward_generate(const sqair_cfg* cfg, const float* packed_params, const float* obs, const float* eps_where,
+                           const float* eps_what, const float* u_pres, const float* eps_where_prior, const float* eps_what_prior,
+                           const float* u_pres_prior, int32_t generate_after, const sqair_outputs* out, void* stream) {
+    if (!eps_where_prior || !eps_what_prior || !u_pres_prior) return fail(SQAIR_EINVAL, "null prior-noise argument");
+    return forward_impl(cfg, packed_params, obs, eps_where, eps_what, u_pres, out, nullptr, stream, eps_where_prior, eps_what_prior,
+                        u_pres_prior, generate_after);
 }
 
 int sqair_objective(const float* log_w_t, const float* disc_lp_t, int32_t T, int32_t B, int32_t K, float* log_weights,

@@ -271,6 +271,12 @@ struct Job {
     int debug_flags;         // tuning experiments only: 1 = skip the MMA math (garbage results), 4/8/16/32/64 skip other stages
     const float* ltab;       // layer table of this launch shape: L_COUNT x DESC_WORDS words (library-owned device buffer)
     float* stash;            // training stash (build_stash layout) or nullptr (inference)
+    // generation (seq.py:46,198-203 `sample_from_prior` / `generate_after`): a second noise set for the draws from the
+    // priors (same shapes; the propagation slots 0 .. n-1 are used) and the last frame that keeps the posterior samples
+    const float* eps_where_prior;
+    const float* eps_what_prior;
+    const float* u_pres_prior;
+    int generate_after;
 };
 
 SQ_DEV bool layer_has_work(const Layer& L, int rank) { return !L.split || rank < L.npanel; }
@@ -604,8 +610,8 @@ SQ_DEVNI bool dense(Ctx& c, const float* SQ_RESTRICT prm, const float* SQ_RESTRI
 #ifndef SQAIR_HOST_EMU
 #define P c_plan
 #endif
-// TR = false compiles the training stash out (the inference kernel)
-template <int R, bool TR = true>
+// TR = false compiles the training stash out (the inference kernel); GEN = true is the `sample_from_prior` variant
+template <int R, bool TR = true, bool GEN = false>
 struct Block {
     Ctx& c;
 #ifdef SQAIR_HOST_EMU
@@ -906,6 +912,10 @@ struct Block {
             rec(m.PropOut, e, F.pres, r) = pres;
         }
         c.sync();
+        if (GEN) {      // sample_from_prior: q is evaluated at draws from the prior, after all slots ran (prop_generate)
+            for (int r = c.tid(); r < R; r += c.nthreads()) rowacc(RA_NPROP, r) += rec(m.PropOut, e, F.pres, r);
+        } else
+        {
         // log-probs under q and p (sqair_modules.py:290-317): one warp per row, lanes over dims
         for (int r = c.warp(); r < R; r += c.nwarps()) {
             float qw = 0.f, pw = 0.f;
@@ -952,6 +962,7 @@ struct Block {
                 rowacc(RA_NPROP, r) += pres;
             }
         }
+        }
         // commit the slot: temporal state, RNN hidden
         for (int i = c.tid(); i < nh * R; i += c.nthreads()) {
             int f = i / R, r = i % R;
@@ -960,6 +971,85 @@ struct Block {
         }
         c.sync();
         stash_copy(S_PROPREC, t_, e, m.PropOut + e * R, LDE(), F.size);
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // sample_from_prior / generate_after (sqair_modules.py:281-326, after the SSM ran all slots): draws from the
+    // propagation prior; the posterior is evaluated at THOSE draws; in generated frames (do_generate) they replace what /
+    // where / presence of the slot.  Masks and the prior's presence term keep the posterior's presence (:286,:306).
+    // ------------------------------------------------------------------------------------------
+    SQ_DEV void prop_generate(int t, bool do_generate) const {
+        const Smem& m = P.sm;
+        const RecF& F = P.rec;
+        const int nw = P.nw;
+        for (int s = 0; s < P.NS; ++s) {
+            const int e = s + 1;
+            for (int r = c.warp(); r < R; r += c.nwarps()) {
+                const size_t ni = nidx(t, r, s);
+                float qw = 0.f, pw = 0.f;
+                for (int j = c.lane(); j < nw; j += c.nlanes()) {
+                    const float x = pri(5 + j, s, r) + pri(9 + nw + j, s, r) * J.eps_what_prior[ni * nw + j];
+                    qw += normal_lp(x, rec(m.PropOut, e, F.what_loc + j, r), rec(m.PropOut, e, F.what_scale + j, r));
+                    const float xp = do_generate ? x : rec(m.PropOut, e, F.what + j, r);
+                    pw += normal_lp(xp, pri(5 + j, s, r), pri(9 + nw + j, s, r));
+                    if (do_generate) rec(m.PropOut, e, F.what + j, r) = x;
+                }
+                qw = warp_sum(qw);
+                pw = warp_sum(pw);
+                if (c.lane() == 0) {
+                    float x[4], loc[4], sc[4], L[4][4], y[4];
+                    float pwh = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        x[i] = pri(1 + i, s, r) + pri(5 + nw + i, s, r) * J.eps_where_prior[ni * 4 + i];
+                        loc[i] = rec(m.PropOut, e, F.where_loc + i, r);
+                        sc[i] = rec(m.PropOut, e, F.where_scale + i, r);
+                        const float xp = do_generate ? x[i] : rec(m.PropOut, e, F.where + i, r);
+                        pwh += normal_lp(xp, pri(1 + i, s, r), pri(5 + nw + i, s, r));
+                        if (do_generate) rec(m.PropOut, e, F.where + i, r) = x[i];
+                    }
+                    tril_from_scale(sc, L);
+                    float qwh = -2.f * SQ_LOG_2PI, ss = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float a = x[i] - loc[i];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (j < i) a -= L[i][j] * y[j];
+                        y[i] = a / L[i][i];
+                        ss += y[i] * y[i];
+                        qwh -= logf(fabsf(L[i][i]));
+                    }
+                    qwh += -0.5f * ss;
+                    const float ptm1 = Z(nw + 4, s, r), pres = rec(m.PropOut, e, F.pres, r);
+                    const float sp = J.u_pres_prior[ni] < sigmoidf_(pri(0, s, r)) ? 1.f : 0.f;
+                    const float qp = bernoulli_lp(sp, rec(m.PropOut, e, F.logit, r));
+                    const float pp = bernoulli_lp(pres, pri(0, s, r));
+                    const float mk = ptm1 * pres;
+                    lp(LP_PQWHAT, s, r) = qw * mk;
+                    lp(LP_PQWHERE, s, r) = qwh * mk;
+                    lp(LP_PPWHAT, s, r) = pw * mk;
+                    lp(LP_PPWHERE, s, r) = pwh * mk;
+                    lp(LP_PROB, s, r) = expf(qp) * ptm1;
+                    rowacc(RA_QPRES, r) += qp * ptm1;
+                    rowacc(RA_PPRES, r) += pp * ptm1;
+                    if (do_generate) rec(m.PropOut, e, F.pres, r) = sp;
+                }
+            }
+        }
+        c.sync();
+    }
+
+    // Generated frames discover nothing (sqair_modules.py:161-170: presence = pres_sample * 0): the discovery slots keep
+    // their posterior statistics and the count terms (evaluated at the posterior's count, :145), every presence-masked
+    // term vanishes.  The prior draws of what / where would only fill absent slots that never reach z_t.
+    SQ_DEV void disc_generate() const {
+        const Smem& m = P.sm;
+        for (int i = c.tid(); i < LDS(); i += c.nthreads()) {
+            const int s = i / R, r = i % R;
+            rec(m.DiscOut, s + 1, P.rec.pres, r) = 0.f;
+            lp(LP_DQWHAT, s, r) = 0.f; lp(LP_DQWHERE, s, r) = 0.f; lp(LP_DPWHAT, s, r) = 0.f;
+        }
+        c.sync();
     }
 
     // L = fill_triangular(cholesky_scale) * scale[:, None] + diag(scale) (modules.py:535-545).
@@ -1417,6 +1507,8 @@ struct Block {
             stash_copy(S_DISCREC, t, 0, m.DiscOut, LDE(), P.rec.size);
         }
         for (int s = 0; s < NS; ++s) prop_slot(t, s);
+        const bool do_generate = GEN && J.generate_after > 0 && t > J.generate_after;          // seq.py:198-203
+        if (GEN) prop_generate(t, do_generate);
         // latent summary: sum_s pres_s * MLP([what_s, where_s]) (sqair_modules.py:368-385,501)
         for (int s = 0; s < NS; ++s) {
             lin(L_LAT1, s, true); lin(L_LAT2, 0, false, s);
@@ -1436,6 +1528,7 @@ struct Block {
         stash_copy(S_EXP, t, 0, m.Exp, R, 1);
         stash_copy(S_DH, t, 0, m.Hrnn, R, nh);
         for (int s = 0; s < NS; ++s) disc_slot(t, s);
+        if (do_generate) disc_generate();
         disc_priors(t);
         choose_latents(t);
         decode_and_score(t);

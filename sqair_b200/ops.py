@@ -65,7 +65,7 @@ def alloc_outputs(cfg: SqairCfg, device, names=None):
 
 
 def forward(cfg: SqairCfg, packed: torch.Tensor, obs: torch.Tensor, noise: dict, outputs: dict = None, names=None,
-            stash: torch.Tensor = None):
+            stash: torch.Tensor = None, prior_noise: dict = None, generate_after: int = -1):
     """SequentialAIR over a [T,B,H,W] batch (seq.py:69-84); returns {name: [T, B*K, ...] tensor}.  With `stash` (a
     float32 buffer of `query_train_sizes(cfg).stash_floats`) the kernel also records what `backward` needs."""
     _need_cuda(packed, obs, noise['eps_where'], noise['eps_what'], noise['u_pres'])
@@ -82,7 +82,18 @@ def forward(cfg: SqairCfg, packed: torch.Tensor, obs: torch.Tensor, noise: dict,
     for k, v in outputs.items():
         _need_cuda(v)
         setattr(so, k, v.data_ptr())
-    if stash is None:
+    if prior_noise is not None:            # generation: sample_from_prior / generate_after (seq.py:198-203)
+        if stash is not None:
+            raise ValueError('generation is an inference mode: no stash')
+        _need_cuda(prior_noise['eps_where'], prior_noise['eps_what'], prior_noise['u_pres'])
+        for k in ('eps_where', 'eps_what', 'u_pres'):
+            if tuple(prior_noise[k].shape) != tuple(noise[k].shape):
+                raise ValueError('prior noise tensors must have the shapes of the posterior noise tensors')
+        check(_capi.lib().sqair_forward_generate(C.byref(cfg), _ptr(packed), _ptr(obs), _ptr(noise['eps_where']),
+                                                 _ptr(noise['eps_what']), _ptr(noise['u_pres']), _ptr(prior_noise['eps_where']),
+                                                 _ptr(prior_noise['eps_what']), _ptr(prior_noise['u_pres']), int(generate_after),
+                                                 C.byref(so), _stream()))
+    elif stash is None:
         check(_capi.lib().sqair_forward(C.byref(cfg), _ptr(packed), _ptr(obs), _ptr(noise['eps_where']),
                                         _ptr(noise['eps_what']), _ptr(noise['u_pres']), C.byref(so), _stream()))
     else:

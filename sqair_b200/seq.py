@@ -19,9 +19,9 @@ class AttrDict(dict):
 class SequentialAIR(object):
     def __init__(self, max_steps, glimpse_size, discover, propagate, time_cell, decoder,
                  sample_from_prior=False, generate_after=-1):
-        if sample_from_prior or generate_after > 0:
-            raise NotImplementedError('sampling from the prior / conditional generation (seq.py:198-203) is '
-                                      'outside the fused inference path of this build')
+        # seq.py:63-64,198-203: with sample_from_prior the posterior is evaluated at draws from the propagation prior and, in
+        # frames t > generate_after (if > 0), those draws replace the latents (conditional generation)
+        self._sample_from_prior, self._generate_after = bool(sample_from_prior), int(generate_after)
         self._max_steps, self._glimpse_size, self._decoder = max_steps, tuple(glimpse_size), decoder
         self._sqair = SQAIRTimestep(self._max_steps, discover, propagate, time_cell)
         self._discover, self._propagate = discover, propagate
@@ -85,9 +85,8 @@ class SequentialAIR(object):
         """obs: [T,B,H,W] or [T,B,H,W,1] float32 CUDA tensor.  With k_particles = K > 1 the K particles of a
         sequence share its frames (virtual `tile_input_for_iwae`); outputs are [T, B*K, ...] as in the reference.
         `noise` (eps_where / eps_what / u_pres tensors) fixes every random draw; otherwise they are generated
-        on the device from `seed` with rows keyed by `row_offset + row`."""
-        if sample_from_prior:
-            raise NotImplementedError('sample_from_prior')
+        on the device from `seed` with rows keyed by `row_offset + row`.  (The `sample_from_prior` argument of the
+        reference's `_build` is never read there, seq.py:69-84; generation is switched on in the constructor.)"""
         if obs.dim() == 5:
             if obs.shape[-1] != 1:
                 raise NotImplementedError('multi-channel frames')
@@ -106,9 +105,17 @@ class SequentialAIR(object):
             noise = ops.fill_noise(cfg, seed, row_offset, noise=buf['noise'])
         if outputs is None:
             outputs = buf['outputs']
+        prior_noise = None
+        if self._sample_from_prior:                       # second noise set: the draws from the priors
+            if all(k + '_prior' in noise for k in ('eps_where', 'eps_what', 'u_pres')):
+                prior_noise = {k: noise[k + '_prior'] for k in ('eps_where', 'eps_what', 'u_pres')}
+            else:
+                if 'prior_noise' not in buf:
+                    buf['prior_noise'] = ops.alloc_noise(cfg, obs.device)
+                prior_noise = ops.fill_noise(cfg, (seed * 0x9E3779B1 + 0x7F4A7C15) & (2 ** 63 - 1), row_offset, noise=buf['prior_noise'])
         if kernel_events is not None:
             kernel_events[0].record()
-        out = ops.forward(cfg, store.packed(cfg), obs, noise, outputs)
+        out = ops.forward(cfg, store.packed(cfg), obs, noise, outputs, prior_noise=prior_noise, generate_after=self._generate_after)
         if kernel_events is not None:
             kernel_events[1].record()
         return AttrDict(out)

@@ -59,8 +59,13 @@ static void run_clusters(const Plan& plan, const Job& job) {
             c.tid_ = 0; c.nthreads_ = 1; c.lane_ = 0; c.nlanes_ = 1; c.warp_ = 0; c.nwarps_ = 1; c.ncompute_ = 1;
             c.sm = peers[rank]; c.rank_ = rank; c.ncta_ = C;
             c.peers = peers.data(); c.cb = &cb; c.cb_gen = 0; c.plan = &plan;
-            Block<R> blk(c, job, cl * R);
-            blk.run();
+            if (job.eps_where_prior) {                  // generation variant (sample_from_prior)
+                Block<R, true, true> blk(c, job, cl * R);
+                blk.run();
+            } else {
+                Block<R> blk(c, job, cl * R);
+                blk.run();
+            }
         };
         if (C == 1) {
             body(0);
@@ -83,7 +88,8 @@ extern "C" int emu_smem_floats(const sqair_cfg* cfg, int R, int C) {
 
 static int emu_forward_impl(const sqair_cfg* cfg, const float* params, const float* obs,
                             const float* eps_where, const float* eps_what, const float* u_pres,
-                            const sqair_outputs* out, int R, int C, float* stash) {
+                            const sqair_outputs* out, int R, int C, float* stash, const float* const* prior_noise = nullptr,
+                            int generate_after = -1) {
     std::string e = validate_cfg(*cfg);
     if (!e.empty()) { fprintf(stderr, "emu: %s\n", e.c_str()); return -1; }
     auto tab = param_table(*cfg);
@@ -94,7 +100,8 @@ static int emu_forward_impl(const sqair_cfg* cfg, const float* params, const flo
     if (!e.empty()) { fprintf(stderr, "emu: %s\n", e.c_str()); return -1; }
     std::vector<float> packed(total, 0.f);
     pack_host(plan, tab, pieces, params, packed);
-    Job job{packed.data(), obs, eps_where, eps_what, u_pres, *out, 0, nullptr, stash};
+    Job job{packed.data(), obs, eps_where, eps_what, u_pres, *out, 0, nullptr, stash, prior_noise ? prior_noise[0] : nullptr,
+            prior_noise ? prior_noise[1] : nullptr, prior_noise ? prior_noise[2] : nullptr, generate_after};
     switch (R) {
         case 1: run_clusters<1>(plan, job); break;
         case 2: run_clusters<2>(plan, job); break;
@@ -105,6 +112,14 @@ static int emu_forward_impl(const sqair_cfg* cfg, const float* params, const flo
         default: fprintf(stderr, "emu: unsupported R=%d\n", R); return -2;
     }
     return 0;
+}
+
+extern "C" int emu_forward_generate(const sqair_cfg* cfg, const float* params, const float* obs, const float* eps_where,
+                                    const float* eps_what, const float* u_pres, const float* eps_where_prior,
+                                    const float* eps_what_prior, const float* u_pres_prior, int generate_after,
+                                    const sqair_outputs* out, int R, int C) {
+    const float* pn[3] = {eps_where_prior, eps_what_prior, u_pres_prior};
+    return emu_forward_impl(cfg, params, obs, eps_where, eps_what, u_pres, out, R, C, nullptr, pn, generate_after);
 }
 
 extern "C" int emu_forward(const sqair_cfg* cfg, const float* params, const float* obs,

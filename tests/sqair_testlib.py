@@ -116,6 +116,14 @@ def emu_lib():
     return _emu
 
 
+def with_prior_noise(cfg, noise, seed=8):
+    """Adds the second noise set of the generation mode (draws from the priors) to a noise dict."""
+    pn = S.philox_noise(cfg.T, cfg.rows, cfg.n, cfg.nw, seed)
+    out = dict(noise)
+    out.update({k + '_prior': v for k, v in pn.items()})
+    return out
+
+
 def run_emu(cfg: O.Cfg, imgs, params, noise, R, cluster=1):
     ccfg = capi_cfg(cfg)
     flat = np.ascontiguousarray(O.flatten_params(params, cfg).numpy())
@@ -126,8 +134,18 @@ def run_emu(cfg: O.Cfg, imgs, params, noise, R, cluster=1):
         setattr(so, k, outs[k].ctypes.data)
     imgs = np.ascontiguousarray(imgs, dtype=np.float32)
     nz = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in noise.items()}
-    rc = emu_lib().emu_forward(C.byref(ccfg), flat.ctypes.data, imgs.ctypes.data, nz['eps_where'].ctypes.data,
-                               nz['eps_what'].ctypes.data, nz['u_pres'].ctypes.data, C.byref(so), R, cluster)
+    if cfg.sample_from_prior:
+        lib = emu_lib()
+        lib.emu_forward_generate.argtypes = [C.POINTER(_capi.SqairCfg)] + [C.c_void_p] * 8 + [C.c_int, C.POINTER(_capi.SqairOutputs),
+                                                                                             C.c_int, C.c_int]
+        lib.emu_forward_generate.restype = C.c_int
+        rc = lib.emu_forward_generate(C.byref(ccfg), flat.ctypes.data, imgs.ctypes.data, nz['eps_where'].ctypes.data,
+                                      nz['eps_what'].ctypes.data, nz['u_pres'].ctypes.data, nz['eps_where_prior'].ctypes.data,
+                                      nz['eps_what_prior'].ctypes.data, nz['u_pres_prior'].ctypes.data, cfg.generate_after,
+                                      C.byref(so), R, cluster)
+    else:
+        rc = emu_lib().emu_forward(C.byref(ccfg), flat.ctypes.data, imgs.ctypes.data, nz['eps_where'].ctypes.data,
+                                   nz['eps_what'].ctypes.data, nz['u_pres'].ctypes.data, C.byref(so), R, cluster)
     assert rc == 0, rc
     return outs
 

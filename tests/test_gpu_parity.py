@@ -36,7 +36,8 @@ def run_cuda(cfg, imgs, params, noise, rows_per_cta=None, cluster=None):
         flat = O.flatten_params(params, cfg).to(dev)
         packed = ops.pack_params(ccfg, flat)
         nz = {k: torch.from_numpy(v).to(dev) for k, v in noise.items()}
-        out = ops.forward(ccfg, packed, torch.from_numpy(imgs).to(dev), nz)
+        pn = {k: nz[k + '_prior'] for k in ('eps_where', 'eps_what', 'u_pres')} if cfg.sample_from_prior else None
+        out = ops.forward(ccfg, packed, torch.from_numpy(imgs).to(dev), nz, prior_noise=pn, generate_after=cfg.generate_after)
         obj = ops.objective(out['log_weights_per_timestep'], out['discrete_log_prob'], cfg.B, cfg.K)
         torch.cuda.synchronize()
     finally:
@@ -123,6 +124,30 @@ def test_c5_long_rollout_parity():
     got = run_cuda(cfg, imgs, params, noise)
     bad = TL.compare_outputs(got, want) + TL.compare_objective(got['_objective'], obj, cfg)   # ELBO-VAE / IWAE, ESS, targets
     assert not bad, '\n'.join(bad)
+
+
+GENERATION = {
+    'generate_after_1': dict(T=4, B=3, K=2, n=3, sample_from_prior=True, generate_after=1),
+    'prior_draws_only': dict(T=3, B=2, K=2, n=2, sample_from_prior=True),
+    'guided_no_rec': dict(T=4, B=2, K=1, n=2, sample_from_prior=True, generate_after=2, prior_type='guided', rec_where_prior=False),
+    'c2_shaped_rollout': dict(T=10, B=4, K=5, n=4, sample_from_prior=True, generate_after=3),
+}
+
+
+@pytest.mark.parametrize('name', list(GENERATION))
+def test_generation_parity(name):
+    """`SequentialAIR(..., sample_from_prior=True, generate_after=g)` (seq.py:46,198-203; sqair_modules.py:157-170,
+    294-302): posterior evaluated at draws from the propagation prior; frames t > g roll forward from the prior and
+    discover nothing."""
+    cfg = O.Cfg(**GENERATION[name])
+    imgs, params, noise = TL.make_inputs(cfg)
+    noise = TL.with_prior_noise(cfg, noise)
+    want, obj = TL.run_oracle(cfg, imgs, params, noise)
+    got = run_cuda(cfg, imgs, params, noise)
+    bad = TL.compare_outputs(got, want) + TL.compare_objective(got['_objective'], obj, cfg)
+    assert not bad, '\n'.join(bad)
+    if cfg.generate_after > 0:
+        assert (got['disc_pres'][cfg.generate_after + 1:] == 0).all()
 
 
 def test_one_packed_buffer_serves_calls_with_different_rows_per_cluster():
