@@ -267,13 +267,31 @@ def train_section(args, dev, world, rank, B_local, flush, label):
     del model
     if rank != 0:
         return None
-    return dict(step='noise + forward(stash) + objective + backward + all-reduce(flat gradient, NCCL) + RMSProp + re-pack',
+    # roofline of the step (per GPU): algorithmic FLOPs = forward (11.09 M MAC per particle-frame) + backward
+    # (input- and weight-gradient products: 2 x forward); algorithmic HBM bytes = forward traffic + the stash written once
+    # and read once + every layer's output gradient written once and read once (wgrad) + parameters / gradient / slots
+    peaks, which = measured_peaks()
+    pf = B_local * w['K'] * w['T']
+    flops = 3 * 2 * 11092860.0 * pf
+    n_params = int(store.flat.numel())
+    bytes_alg = algorithmic_bytes(w, n_params) + 2 * 4 * ts.stash_floats + 2 * 4 * ts.workspace_floats + 7 * 4 * n_params
+    step_s = total_ms / args.steps * 1e-3
+    tens_peak = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
+    roof = dict(bound='latency (dependent chain of ~1 450 small launches; see DESIGN.md 6b.5)',
+                tensor=dict(achieved=flops / step_s / 1e12, peak=tens_peak, unit='TFLOP/s', frac=flops / step_s / 1e12 / tens_peak,
+                            algorithmic_flops=flops),
+                hbm=dict(achieved=bytes_alg / step_s / 1e9, peak=peaks['hbm_gbs'], unit='GB/s', frac=bytes_alg / step_s / 1e9 / peaks['hbm_gbs'],
+                         algorithmic_bytes=bytes_alg),
+                peak_source=which,
+                kernels='forward+stash 7.9 ms (sqair_sequence_kernel<5,true>), ~850 dgrad_kernel 6-7 ms, 38 wgrad_tc_kernel (tcgen05) + 23 '
+                        'wgrad_addr_kernel 1.3 ms, bwd_stage_kernel 3 ms at B=32 (profiles/r02_train_step_launches.txt)')
+    return dict(step='noise + forward(stash) + objective + backward (CUDA-graph replay) + all-reduce(flat gradient, NCCL) + RMSProp + re-pack',
                 value=frames / (total_ms * 1e-3), unit='frames/s', ms_per_step=total_ms / args.steps,
                 scaling=label, sequences_per_gpu=B_local, global_batch=n_global,
                 allreduce_ms=ar_ms, allreduce_bytes=int(store.flat.numel() * 4), collective='NCCL all_reduce(sum) fp32' if world > 1 else 'none (1 rank)',
                 e2e=dict(value=frames / (e2e_ms * 1e-3), unit='frames/s', h2d_bytes_per_step=int(obs_host.numel() * 4),
                          d2h_bytes_per_step=int(4 * _capi.OBJ_N)),
-                stash_bytes=int(ts.stash_floats * 4), finite=finite, target='VIMCO / T (model.py:150-158)',
+                stash_bytes=int(ts.stash_floats * 4), finite=finite, target='VIMCO / T (model.py:150-158)', roofline=roof,
                 optimizer='RMSProp(lr 1e-5 piecewise /3, momentum .9)')
 
 

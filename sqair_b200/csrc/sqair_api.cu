@@ -233,11 +233,34 @@ std::string sqi::choose_shape(const sqair_cfg& c, const std::vector<ParamEntry>&
     return "";
 }
 
-// Blocks of a cluster of size C that can be resident at once (GPCs hold 16-18 SMs; measured on B200 with
-// cudaOccupancyMaxActiveClusters at 220 KB of shared memory per block).
+// Blocks of a cluster of size C that can be resident at once.  Asked of the device the call runs on
+// (cudaOccupancyMaxActiveClusters for the sequence kernel at its largest shared-memory footprint: GPCs hold 16-18 SMs, so
+// odd cluster sizes leave SMs unused); the table is what a 148-SM B200 answers and serves hosts without a device
+// (sqair_query_sizes in CPU-only tooling).
 static int max_resident_blocks(int C) {
     static const int tab[9] = {0, 148, 148, 132, 132, 120, 120, 112, 128};
-    return tab[C];
+    static std::mutex mu;
+    static int cached[64][9];
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 64) { cudaGetLastError(); return tab[C]; }
+    std::lock_guard<std::mutex> lock(mu);
+    if (cached[device][C] == 0) {
+        int n = 0;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.blockDim = dim3(NT_LAUNCH);
+        cfg.dynamicSmemBytes = 220 * 1024;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cfg.gridDim = dim3(C * 64);
+        cudaError_t e = cudaFuncSetAttribute(sqair_sequence_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, sqair_sequence_kernel<1, false, false>, &cfg);
+        if (e != cudaSuccess || n <= 0) { cudaGetLastError(); cached[device][C] = tab[C]; }
+        else cached[device][C] = n * C;
+    }
+    return cached[device][C];
 }
 
 static std::string choose_shape_uncached(const sqair_cfg& c, const std::vector<ParamEntry>& tab, Shape& out) {

@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "sqair_backward.h"
@@ -19,6 +20,28 @@
 using namespace sq;
 using sqi::Shape;
 using sqi::fail;
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  The reverse program is a chain of ~1 450 short kernels; with the stream-serialisation
+// attribute a kernel is scheduled while its predecessor still runs.  Every kernel launched this way releases its
+// successor immediately (pdl_trigger) and blocks at pdl_wait until the predecessor has completed and flushed its
+// writes -- nothing that depends on earlier kernels may be touched before the wait.  What may: kernel arguments and the
+// weight copies (constant during a backward call), which `dgrad_kernel` fetches ahead of the wait.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---------------------------------------------------------------------------------------------
 // row stages
@@ -62,6 +85,8 @@ template <int STAGE>
 __global__ void bwd_stage_kernel(const __grid_constant__ BwdCtx c, int t, int s) {
     extern __shared__ float bw_smem[];
     __shared__ float red[4 * 32];
+    pdl_trigger();
+    pdl_wait();
     DevEx ex;
     ex.tid = threadIdx.x; ex.nt = blockDim.x; ex.scratch = bw_smem; ex.red = red;
     bw_stage<STAGE>(c, ex, t, s, (int)blockIdx.x);
@@ -111,6 +136,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_kernel(const __grid_const
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * DG_BM, kb = blockIdx.x * DG_BK;
     const bool has_k = A.nseg > 0 && kb < A.K;
+    pdl_trigger();
     if (!has_k && blockIdx.x != 0) return;
     const bool store_dy = A.dy.p != nullptr && blockIdx.x == 0;
     const int nq = has_k ? min(DG_BK / 4, (D.ldt - kb) / 4) : 0;          // 16-byte groups of this tile inside the padded row
@@ -133,11 +159,14 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_kernel(const __grid_const
                 wv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (n < np && q < nq) wv[j] = __ldg(reinterpret_cast<const float4*>(D.wt + (size_t)(nb + n) * D.ldt + kb) + q);
             }
+            if (nb == 0) pdl_wait();                             // the weight loads above are in flight across the wait
 #pragma unroll
             for (int j = 0; j < NW; ++j) {
                 const int i = tid + j * DG_THREADS, n = i >> 3, q = i & 7;
                 if (n < np) *reinterpret_cast<float4*>(Ws + n * DG_BK + 4 * q) = wv[j];
             }
+        } else if (nb == 0) {
+            pdl_wait();
         }
         // A tile: warp w owns rows 2w, 2w + 1, lane l the columns l, l + 32, ... (coalesced); one row per iteration
 #pragma unroll 1
@@ -300,6 +329,8 @@ __global__ void __launch_bounds__(128) wgrad_addr_kernel(const __grid_constant__
 // out[n] += sum_m dY[m, n]: 32 columns x 8 row lanes per block, grid.y splits M
 __global__ void __launch_bounds__(256) colsum_kernel(const __grid_constant__ ColsumArgs A, int m_per_block) {
     __shared__ float red[8][33];
+    pdl_trigger();
+    pdl_wait();
     const int col = threadIdx.x & 31, rl = threadIdx.x >> 5, n = blockIdx.x * 32 + col;
     const int m_begin = blockIdx.y * m_per_block, m_end = min(A.M, m_begin + m_per_block);
     float a = 0.f;
@@ -454,7 +485,8 @@ struct CudaBackend {
     template <int STAGE>
     void stage(const BwdCtx& c, int t, int s) {
         const int threads = STAGE == BS_CANVAS ? 256 : 128;
-        bwd_stage_kernel<STAGE><<<rows, threads, scratch_bytes, st>>>(c, t, s);
+        cudaError_t e = launch_pdl(bwd_stage_kernel<STAGE>, dim3(rows), dim3(threads), (size_t)scratch_bytes, st, c, t, s);
+        if (err == cudaSuccess) err = e;
         check();
     }
     void dgrad(const DgradArgs& A) {
@@ -466,13 +498,15 @@ struct CudaBackend {
         int gx = A.nseg > 0 ? (A.K + DG_BK - 1) / DG_BK : 1;
         const dim3 grid(gx, (A.M + DG_BM - 1) / DG_BM);
         const size_t smem = DG_SMEM_FLOATS * sizeof(float);
+        cudaError_t e;
         switch (A.y.p ? A.act : ACT_NONE) {
-            case ACT_ELU: dgrad_kernel<ACT_ELU><<<grid, DG_THREADS, smem, st>>>(D); break;
-            case ACT_TANH: dgrad_kernel<ACT_TANH><<<grid, DG_THREADS, smem, st>>>(D); break;
-            case ACT_SIGMOID: dgrad_kernel<ACT_SIGMOID><<<grid, DG_THREADS, smem, st>>>(D); break;
-            case ACT_SOFTPLUS: dgrad_kernel<ACT_SOFTPLUS><<<grid, DG_THREADS, smem, st>>>(D); break;
-            default: dgrad_kernel<ACT_NONE><<<grid, DG_THREADS, smem, st>>>(D); break;
+            case ACT_ELU: e = launch_pdl(dgrad_kernel<ACT_ELU>, grid, dim3(DG_THREADS), smem, st, D); break;
+            case ACT_TANH: e = launch_pdl(dgrad_kernel<ACT_TANH>, grid, dim3(DG_THREADS), smem, st, D); break;
+            case ACT_SIGMOID: e = launch_pdl(dgrad_kernel<ACT_SIGMOID>, grid, dim3(DG_THREADS), smem, st, D); break;
+            case ACT_SOFTPLUS: e = launch_pdl(dgrad_kernel<ACT_SOFTPLUS>, grid, dim3(DG_THREADS), smem, st, D); break;
+            default: e = launch_pdl(dgrad_kernel<ACT_NONE>, grid, dim3(DG_THREADS), smem, st, D); break;
         }
+        if (err == cudaSuccess) err = e;
         check();
     }
     void wgrad(const WgradArgs& A) {
@@ -501,7 +535,8 @@ struct CudaBackend {
         if (msplit > max_split) msplit = max_split;
         if (msplit < 1) msplit = 1;
         const int m_per_block = (A.M + msplit - 1) / msplit;
-        colsum_kernel<<<dim3(gx, (A.M + m_per_block - 1) / m_per_block), 256, 0, st>>>(A, m_per_block);
+        cudaError_t e = launch_pdl(colsum_kernel, dim3(gx, (A.M + m_per_block - 1) / m_per_block), dim3(256), 0, st, A, m_per_block);
+        if (err == cudaSuccess) err = e;
         check();
     }
     void zero(float* p, int64_t n) {

@@ -60,6 +60,12 @@ def test_full_size_c2_backward_parity():
     _check(O.Cfg(T=10, B=32, K=5, n=4), smooth=False)
 
 
+def test_c4_shaped_backward_parity():
+    """BASELINE configs[3] shape (100x100 canvas, n=6 objects, B=16, K=10) with three frames: the frames are read from
+    global memory (they do not fit the shared-memory staging), 60 glimpses per row in the canvas stage."""
+    _check(O.Cfg(T=3, B=16, K=10, n=6, H=100, W=100), with_floor=False, smooth=False)
+
+
 def test_backward_is_reproducible_and_workspace_independent():
     """Two runs with differently poisoned scratch memory agree to accumulation-order noise (atomics in the weight
     gradient reductions) -- nothing reads uninitialised workspace."""
