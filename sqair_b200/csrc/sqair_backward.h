@@ -867,6 +867,9 @@ struct BwdLayout {
     int64_t gPropRec, gDiscRec, gTnew, gPnew, gPH, gDH, gDIn, gExp, gHrn, gPri, gMask, gGlm, gLoc1, gHwbmk, gEnc, gRH, tA0, tA1;
     int64_t dwv_off;                  // [bw_total] virtual-matrix gradients
     int64_t img_dy_off;               // [T, B, nh] image-encoder dY summed over the particles of a sequence
+    int nframe;                       // the arrays of the per-frame region, each [rows, frame_stride[i]] (cleared per row range
+    int64_t frame_off[16];            //  by the persistent reverse-program kernel: every cluster clears the rows it owns)
+    int frame_stride[16];
     int64_t total;
 };
 
@@ -893,12 +896,13 @@ inline BwdLayout build_bwd_layout(const sqair_cfg& c, const Plan& plan) {
     L.dyz_end = cur;
     for (int i = 0; i < 6; ++i) L.carry_off[i] = take((int64_t)rows * n * (i % 3 == 0 ? zw : nh));
     L.frame_begin = cur;
-    L.gPropRec = take((int64_t)rows * (n + 1) * zw); L.gDiscRec = take((int64_t)rows * (n + 1) * zw);
-    L.gTnew = take((int64_t)rows * n * nh); L.gPnew = take((int64_t)rows * n * nh);
-    L.gPH = take((int64_t)rows * (n + 1) * nh); L.gDH = take((int64_t)rows * (n + 1) * nh);
-    L.gDIn = take((int64_t)rows * 2 * nh); L.gExp = take(rows); L.gHrn = take((int64_t)rows * 128);
-    L.gPri = take((int64_t)rows * n * npri);
-    L.gMask = take((int64_t)rows * n * g);
+    auto frame_take = [&](int stride) { int64_t o = take((int64_t)rows * stride); L.frame_off[L.nframe] = o; L.frame_stride[L.nframe++] = stride; return o; };
+    L.gPropRec = frame_take((n + 1) * zw); L.gDiscRec = frame_take((n + 1) * zw);
+    L.gTnew = frame_take(n * nh); L.gPnew = frame_take(n * nh);
+    L.gPH = frame_take((n + 1) * nh); L.gDH = frame_take((n + 1) * nh);
+    L.gDIn = frame_take(2 * nh); L.gExp = frame_take(1); L.gHrn = frame_take(128);
+    L.gPri = frame_take(n * npri);
+    L.gMask = frame_take(n * g);
     L.frame_end = cur;
     L.gGlm = take((int64_t)rows * n * g);
     L.gLoc1 = take((int64_t)rows * n * nw);

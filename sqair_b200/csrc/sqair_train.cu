@@ -8,7 +8,9 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <math.h>
+#include <stddef.h>
 #include <stdio.h>
+#include <string.h>
 #include <mutex>
 #include <string>
 #include <utility>
@@ -50,7 +52,11 @@ struct DevEx {
     int tid, nt;
     float* scratch;
     float* red;          // [4][32]
-    __device__ __forceinline__ void sync() { __syncthreads(); }
+    int bar_id;          // 0: the row owns the whole thread block; else the named barrier of the row's `nt` threads
+    __device__ __forceinline__ void sync() {
+        if (bar_id == 0) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nt) : "memory");
+    }
     // dst[0..3] += the warp's sums of v[0..3] (all 32 lanes must call; one shared-memory atomic per warp and value)
     __device__ __forceinline__ void warp_add4(float* dst, const float (&v)[4]) {
 #pragma unroll
@@ -70,14 +76,14 @@ struct DevEx {
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
             if (lane == 0) red[q * 32 + warp] = x;
         }
-        __syncthreads();
+        sync();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float x = 0.f;
             for (int w = 0; w < nw; ++w) x += red[q * 32 + w];
             v[q] = x;
         }
-        __syncthreads();
+        sync();
     }
 };
 
@@ -88,7 +94,7 @@ __global__ void bwd_stage_kernel(const __grid_constant__ BwdCtx c, int t, int s)
     pdl_trigger();
     pdl_wait();
     DevEx ex;
-    ex.tid = threadIdx.x; ex.nt = blockDim.x; ex.scratch = bw_smem; ex.red = red;
+    ex.tid = threadIdx.x; ex.nt = blockDim.x; ex.scratch = bw_smem; ex.red = red; ex.bar_id = 0;
     bw_stage<STAGE>(c, ex, t, s, (int)blockIdx.x);
 }
 
@@ -127,18 +133,20 @@ __device__ __forceinline__ float act_deriv_t(float y, float scale, float add) {
     return 1.f;
 }
 
-template <int ACT>
-__global__ void __launch_bounds__(DG_THREADS, 1) dgrad_kernel(const __grid_constant__ DgradDev D) {
+// One 32 x 32 tile (bx = feature tile, by = row tile).  PDL: the stand-alone kernel releases its successor at once and
+// waits for its predecessor after the weight loads are in flight; inside the persistent reverse-program kernel the
+// grid barrier has already ordered everything.
+template <int ACT, bool PDL>
+__device__ __forceinline__ void dgrad_tile(const DgradDev& D, const int bx, const int by, float* dg_smem) {
     const DgradArgs& A = D.a;
-    extern __shared__ __align__(16) float dg_smem[];
     float* As = dg_smem;                                  // [DG_NP][DG_LDA]  (rows of the tile contiguous: 16-byte loads of 4 rows)
     float* Ws = dg_smem + DG_NP * DG_LDA;                 // [DG_NP][DG_BK]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.y * DG_BM, kb = blockIdx.x * DG_BK;
+    const int m0 = by * DG_BM, kb = bx * DG_BK;
     const bool has_k = A.nseg > 0 && kb < A.K;
-    pdl_trigger();
-    if (!has_k && blockIdx.x != 0) return;
-    const bool store_dy = A.dy.p != nullptr && blockIdx.x == 0;
+    if (PDL) pdl_trigger();
+    if (!has_k && bx != 0) return;
+    const bool store_dy = A.dy.p != nullptr && bx == 0;
     const int nq = has_k ? min(DG_BK / 4, (D.ldt - kb) / 4) : 0;          // 16-byte groups of this tile inside the padded row
     const int rg = lane >> 2, fq = lane & 3;                 // compute: rows 4 rg .. 4 rg + 3, features 8 fq .. 8 fq + 7
     float acc[4][8];
@@ -159,13 +167,13 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_kernel(const __grid_const
                 wv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (n < np && q < nq) wv[j] = __ldg(reinterpret_cast<const float4*>(D.wt + (size_t)(nb + n) * D.ldt + kb) + q);
             }
-            if (nb == 0) pdl_wait();                             // the weight loads above are in flight across the wait
+            if (PDL && nb == 0) pdl_wait();                      // the weight loads above are in flight across the wait
 #pragma unroll
             for (int j = 0; j < NW; ++j) {
                 const int i = tid + j * DG_THREADS, n = i >> 3, q = i & 7;
                 if (n < np) *reinterpret_cast<float4*>(Ws + n * DG_BK + 4 * q) = wv[j];
             }
-        } else if (nb == 0) {
+        } else if (PDL && nb == 0) {
             pdl_wait();
         }
         // A tile: warp w owns rows 2w, 2w + 1, lane l the columns l, l + 32, ... (coalesced); one row per iteration
@@ -236,6 +244,12 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_kernel(const __grid_const
         float* d = const_cast<float*>(addr_row(S.d, mo, A.ny)) + (k - S.k0);
         if (S.mode == SEGM_STORE) *d = sum; else *d += sum;
     }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(DG_THREADS, 1) dgrad_kernel(const __grid_constant__ DgradDev D) {
+    extern __shared__ __align__(16) float dg_smem[];
+    dgrad_tile<ACT, true>(D, (int)blockIdx.x, (int)blockIdx.y, dg_smem);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -468,6 +482,402 @@ static void fill_piece_tab(const Shape& sh, BPieceTab& bt) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// The reverse program as ONE persistent cluster kernel.  The frame recursion of the backward pass is a dependent chain
+// of ~1 400 short operations (row stages, dgrad products, buffer clears); as separate launches every link pays a kernel
+// boundary on a cold instruction cache.  Rows (b, k) never interact inside that chain, so -- like the forward kernel -- a
+// cluster of C thread blocks owns R rows for the whole reverse program: the host records the operations into a table
+// (`BwdOp`, built by the same `BwdDriver`), every cluster interprets the table for ITS rows, and a cluster barrier
+// (release / acquire, which also orders the global-memory traffic between the blocks of the cluster) separates
+// dependent operations instead of a kernel boundary.  No grid-wide synchronisation exists.
+//   * row stage: the cluster's rows are dealt to (block, 128-thread group) pairs, each with its own named barrier;
+//   * dgrad: dX = (dY act'(y)) W^T with out-features as the MMA M dimension and the cluster's rows as N (swap-AB, as
+//     in the forward): the block stages A = dY act'(y) of its cluster's rows in shared memory, streams ITS column panel
+//     of W^T -- stored in mma.m16n8k8 A-fragment order, pre-split into tf32 (hi, lo), by sqair_pack_backward -- through
+//     the tensor cores with the forward's 4-product fp32-faithful k-step, and scatters / accumulates its slice of dX
+//     straight into the gradient buffers;
+//   * clear: every cluster clears the rows it owns.
+// ---------------------------------------------------------------------------------------------
+enum { OP_STAGE = 0, OP_DGRAD = 1, OP_ZERO = 2 };
+constexpr int BP_THREADS = 512, BP_WARPS = BP_THREADS / 32;
+constexpr int BP_XLD = 8;                      // staged operand: X[n][8] (rows of the cluster, padded to the MMA N dimension)
+constexpr int BP_RED_FLOATS = 12288;           // k-slice partial sums [ksplit][Nc][8]
+constexpr int BP_XMAX_N = 768;                 // widest layer output the staged operand holds
+constexpr int BP_NTILE_MAX = 3;                // MMA n-tiles (8 operand rows each) per pass
+
+// W^T of one layer as the kernel reads it: panel p (the out-features [p Nc, (p + 1) Nc) of dX) at w_off + p panel_floats,
+// [m-tile][k-step][hi | lo][lane][4] (unsplit fp32 panels with the split in the loop and four k-steps in flight measured
+// 1.5 % slower: the k-step is not bound by the bytes in flight)
+struct TLayer {
+    int ksteps, nmt, Nc, ksplit, kper, panel_floats;
+    long long w_off;         // floats from the start of the backward parameter buffer
+};
+
+struct BwdOp {
+    int kind, stage, t, s;
+    int act;                 // dgrad: activation whose derivative is applied (ACT_NONE when there is none)
+    int zstride;             // zero: floats per row
+    int nobar, pad0;         // 1: the next operation does not depend on this one (a clear followed by a clear)
+    float* carry[6];         // stage: gZc gTc gPc gZo gTo gPo of the frame (the only BwdCtx fields that change)
+    float* zp;               // zero: [rows, zstride]
+    TLayer tl;
+    DgradArgs d;
+};
+struct BwdProgramHdr {
+    BwdCtx ctx;
+    int nops, R, pad[2];
+};
+constexpr int OP_WORDS = (int)(sizeof(BwdOp) / 4);
+static_assert(sizeof(BwdOp) % 8 == 0 && OP_WORDS <= BP_THREADS, "an operation is staged with one thread per word");
+static_assert(sizeof(BwdProgramHdr) % 16 == 0, "operations follow the header 16-byte aligned");
+static_assert(offsetof(BwdCtx, gPo) - offsetof(BwdCtx, gZc) == 5 * sizeof(float*), "the six carried-gradient pointers are patched as an array");
+
+__device__ __forceinline__ void cluster_sync_rel_acq() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ int cluster_rank() { uint32_t r; asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return (int)r; }
+__device__ __forceinline__ int cluster_size() { uint32_t r; asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return (int)r; }
+__device__ __forceinline__ int cluster_id() { uint32_t r; asm("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return (int)r; }
+
+struct AFragB {
+    float4 hi, lo;
+};
+__device__ __forceinline__ AFragB ldg_afrag_b(const float4* p) {
+    AFragB a;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.hi.x), "=f"(a.hi.y), "=f"(a.hi.z), "=f"(a.hi.w) : "l"(p));
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.lo.x), "=f"(a.lo.y), "=f"(a.lo.z), "=f"(a.lo.w) : "l"(p + 32));
+    return a;
+}
+// one k-step, the forward's arithmetic (sqair_device.cuh: mma_kstep): four tf32 partial products summed on the tensor
+// core starting from zero, joined to the running sum with round-to-nearest FADDs
+__device__ __forceinline__ void mma_kstep_b(float (&acc)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], float b0f, float b1f) {
+    uint32_t b0h, b0l, b1h, b1l;
+    split_tf32_(b0f, b0h, b0l); split_tf32_(b1f, b1h, b1l);
+    float d[4], e[4];
+    mma_tf32_zero_(d, al, b0l, b1l);
+    mma_tf32_zero_(e, ah, b0l, b1l);
+    mma_tf32_(d, al, b0h, b1h);
+    mma_tf32_(e, ah, b0h, b1h);
+    acc[0] += d[0] + e[0]; acc[1] += d[1] + e[1]; acc[2] += d[2] + e[2]; acc[3] += d[3] + e[3];
+}
+
+#ifdef SQAIR_PROG_PROFILE
+__device__ long long g_prog_prof[64][3];      // per operation class: cycles in the body, cycles in the barrier, count (block 0)
+#define PROG_TICK(cls) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t_ = clock64(); g_prog_prof[cls][0] += t_ - ptick; g_prog_prof[cls][2] += 1; ptick = t_; } } while (0)
+#else
+#define PROG_TICK(cls) do { } while (0)
+#endif
+
+// dX slice of this block for the cluster's rows [row0, row0 + R).  The operand rows m = (row0 + r) ny + slot of the
+// cluster (R ny of them: the slots of a batched operand ride along as extra MMA columns, so W^T is streamed once) are
+// processed in passes of up to 8 NTILE columns.
+template <int ACT, int NTILE>
+__device__ __forceinline__ void program_dgrad(const BwdOp& op, float* smem, int row0, int R, int rows) {
+    const DgradArgs& A = op.d;
+    const TLayer& TL = op.tl;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int rank = cluster_rank();
+    const int nr = min(R, rows - row0);
+    const int ncol = nr * A.ny, m_base = row0 * A.ny;
+    const int kcol0 = rank * TL.Nc;
+    const bool has_k = A.nseg > 0 && kcol0 < A.K;
+    const float4* panel = reinterpret_cast<const float4*>(A.w + (long long)rank * TL.panel_floats);   // A.w = panel 0 of W^T here
+    const int npad = TL.ksteps * 8, xtile = npad * BP_XLD;
+    float* X = smem;                                   // [NTILE][npad][BP_XLD]
+    float* red = smem + BP_NTILE_MAX * BP_XMAX_N * BP_XLD;   // [ksplit][Nc][8 NTILE]
+    // row offsets of the pass's operand rows, computed once (the (m / ny, m % ny) split costs two integer divisions):
+    // [0] a, [1] y, [2] dy, [3 + segment] destination of the segment
+    long long* rowoff = reinterpret_cast<long long*>(red + BP_RED_FLOATS);     // [3 + BW_MAXSEG][8 NTILE_MAX]
+    constexpr int RO = 8 * BP_NTILE_MAX;
+    constexpr int NCOLP = 8 * NTILE, PF = 2;           // PF k-steps of weights in flight per warp (register budget)
+#ifdef SQAIR_PROG_PROFILE
+    long long ptick = clock64();
+#endif
+    for (int c0 = 0; c0 < ncol; c0 += NCOLP) {
+        const int ncp = min(NCOLP, ncol - c0);
+        if (c0) __syncthreads();
+        const int nunits = has_k ? TL.nmt * TL.ksplit : 0;
+        if (tid < (3 + A.nseg) * RO) {
+            const int which = tid / RO, c = tid - which * RO;
+            if (c < ncp) {
+                const int m = m_base + c0 + c;
+                const Addr& ad = which == 0 ? A.a : which == 1 ? A.y : which == 2 ? A.dy : A.seg[which - 3].d;
+                rowoff[tid] = (long long)(m / A.ny) * ad.outer + (long long)(m % A.ny) * ad.inner;
+            }
+        }
+        __syncthreads();
+        // operand staging: X[c / 8][n][c % 8] = a[m][n] act'(y[m][n]), also stored to dy by the first block.  A thread owns
+        // feature n and walks the columns of one n-tile: up to 16 independent loads, one memory round trip per tile.
+        for (int n = tid; n < npad; n += BP_THREADS) {
+            const bool okn = n < A.N;
+#pragma unroll
+            for (int q = 0; q < NTILE; ++q) {
+                if (q * 8 >= ncp) break;
+                float av[8], yv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = q * 8 + j;
+                    av[j] = 0.f; yv[j] = 0.f;
+                    if (okn && c < ncp) {
+                        av[j] = A.a.p[rowoff[c] + n];
+                        if (ACT != ACT_NONE) yv[j] = A.y.p[rowoff[RO + c] + n];
+                    }
+                }
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = q * 8 + j;
+                    v[j] = av[j];
+                    if (ACT != ACT_NONE) v[j] *= act_deriv_t<ACT>(yv[j], A.act_scale, A.act_add);
+                    if (rank == 0 && A.dy.p != nullptr && okn && c < ncp) A.dy.p[rowoff[2 * RO + c] + n] = v[j];
+                }
+                float4* xd = reinterpret_cast<float4*>(X + q * xtile + n * BP_XLD);
+                xd[0] = make_float4(v[0], v[1], v[2], v[3]);
+                xd[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        }
+        __syncthreads();
+        PROG_TICK(56);
+        for (int u = warp; u < nunits; u += BP_WARPS) {
+            const int sl = u / TL.nmt, mt = u - sl * TL.nmt;
+            const int k0 = sl * TL.kper, k1 = min(k0 + TL.kper, TL.ksteps);
+            const float4* wp = panel + ((size_t)mt * TL.ksteps + k0) * 64 + lane;
+            float acc[NTILE][4];
+#pragma unroll
+            for (int q = 0; q < NTILE; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+            const float* xp = X + (k0 * 8 + t4) * BP_XLD + g;
+            // PF k-steps of weights in flight per warp (named registers: an indexed buffer ends up in local memory)
+            AFragB b0 = ldg_afrag_b(wp), b1, b2, b3;
+            if (k0 + 1 < k1) b1 = ldg_afrag_b(wp + 64);
+            if (PF == 4) {
+                if (k0 + 2 < k1) b2 = ldg_afrag_b(wp + 128);
+                if (k0 + 3 < k1) b3 = ldg_afrag_b(wp + 192);
+            }
+            auto step = [&](AFragB& slot, int ks) {
+                const uint32_t ah[4] = {__float_as_uint(slot.hi.x), __float_as_uint(slot.hi.y), __float_as_uint(slot.hi.z), __float_as_uint(slot.hi.w)};
+                const uint32_t al[4] = {__float_as_uint(slot.lo.x), __float_as_uint(slot.lo.y), __float_as_uint(slot.lo.z), __float_as_uint(slot.lo.w)};
+                if (ks + PF < k1) slot = ldg_afrag_b(wp + PF * 64);
+                wp += 64;
+#pragma unroll
+                for (int q = 0; q < NTILE; ++q)
+                    if (q * 8 < ncp) mma_kstep_b(acc[q], ah, al, xp[q * xtile], xp[q * xtile + 4 * BP_XLD]);
+                xp += 8 * BP_XLD;
+            };
+            for (int kk = k0; kk < k1; kk += PF) {
+                step(b0, kk);
+                if (kk + 1 < k1) step(b1, kk + 1);
+                if (PF == 4) {
+                    if (kk + 2 < k1) step(b2, kk + 2);
+                    if (kk + 3 < k1) step(b3, kk + 3);
+                }
+            }
+            // C fragment: acc[0] = (col g, row 2 t4), acc[1] = (g, 2 t4 + 1), acc[2] = (g + 8, 2 t4), acc[3] = (g + 8, 2 t4 + 1)
+#pragma unroll
+            for (int q = 0; q < NTILE; ++q) {
+                float* rp = red + ((size_t)sl * TL.Nc + mt * 16 + g) * NCOLP + q * 8 + 2 * t4;
+                rp[0] = acc[q][0]; rp[1] = acc[q][1]; rp[8 * NCOLP] = acc[q][2]; rp[8 * NCOLP + 1] = acc[q][3];
+            }
+        }
+        PROG_TICK(57);
+        __syncthreads();
+        PROG_TICK(58);
+        if (has_k) {
+            for (int o = tid; o < TL.Nc * NCOLP; o += BP_THREADS) {
+                const int col = o / NCOLP, c = o - col * NCOLP, k = kcol0 + col;     // NCOLP is a compile-time constant
+                if (c >= ncp || k >= A.K) continue;
+                int si = -1;
+                for (int q = 0; q < A.nseg; ++q)
+                    if (k >= A.seg[q].k0 && k < A.seg[q].k1) si = q;
+                if (si < 0) continue;
+                float sum = 0.f;
+                for (int s2 = 0; s2 < TL.ksplit; ++s2) sum += red[((size_t)s2 * TL.Nc + col) * NCOLP + c];
+                const DgradArgs::Seg& S = A.seg[si];
+                float* d = S.d.p + rowoff[(3 + si) * RO + c] + (k - S.k0);
+                if (S.mode == SEGM_STORE) *d = sum;
+                else atomicAdd(d, sum);                // one writer per element: a fire-and-forget RED instead of a load round trip
+            }
+        }
+        PROG_TICK(59);
+    }
+}
+
+// rows of the cluster -> (block, thread group): the smallest number of groups per block that covers R rows in one round
+template <int STAGE>
+__device__ __forceinline__ void program_stage(const BwdCtx& c, float* smem, float* red, int scratch_floats, int t, int s, int row0,
+                                              int R) {
+    const int C = cluster_size();
+    const int nsub = R <= C ? 1 : R <= 2 * C ? 2 : 4, nts = BP_THREADS / nsub;
+    const int sub = threadIdx.x / nts;
+    DevEx ex;
+    ex.tid = threadIdx.x - sub * nts; ex.nt = nts; ex.scratch = smem + (size_t)sub * scratch_floats; ex.red = red + sub * 128;
+    ex.bar_id = 1 + sub;
+    for (int i = cluster_rank() + sub * C; i < R && row0 + i < c.rows; i += nsub * C) {
+        bw_stage<STAGE>(c, ex, t, s, row0 + i);
+        ex.sync();                                   // the group's scratch is reused by its next row
+    }
+}
+
+__global__ void __launch_bounds__(BP_THREADS, 1) bwd_program_kernel(const BwdProgramHdr* __restrict__ hdr, int scratch_floats) {
+    extern __shared__ __align__(16) float bp_smem[];
+    __shared__ __align__(16) BwdCtx sc;
+    __shared__ __align__(16) BwdOp sop;
+    __shared__ float red[4 * 128];
+    const int tid = threadIdx.x;
+    {
+        const int* src = reinterpret_cast<const int*>(&hdr->ctx);
+        int* dst = reinterpret_cast<int*>(&sc);
+        for (int i = tid; i < (int)(sizeof(BwdCtx) / 4); i += BP_THREADS) dst[i] = __ldg(src + i);
+    }
+    const int nops = hdr->nops, R = hdr->R;
+    const int row0 = cluster_id() * R;
+    const int* ops = reinterpret_cast<const int*>(hdr + 1);
+    int next_word = (tid < OP_WORDS && nops > 0) ? __ldg(ops + tid) : 0;
+    for (int i = 0; i < nops; ++i) {
+        if (tid < OP_WORDS) reinterpret_cast<int*>(&sop)[tid] = next_word;
+        __syncthreads();
+        if (tid < OP_WORDS && i + 1 < nops) next_word = __ldg(ops + (size_t)(i + 1) * OP_WORDS + tid);
+        const int kind = sop.kind;
+#ifdef SQAIR_PROG_PROFILE
+        const long long pt0 = clock64();
+        const int pclass = kind == OP_STAGE ? sop.stage : kind == OP_DGRAD ? 32 + (sop.d.ny > 1 ? 8 : 0) + sop.act : kind == OP_ZERO ? 48 : 49;
+#endif
+        if (kind == OP_STAGE) {
+            if (tid < 6) (&sc.gZc)[tid] = sop.carry[tid];
+            __syncthreads();
+            const int t = sop.t, s = sop.s;
+            switch (sop.stage) {
+#define SQ_STAGE_CASE(ID) case ID: program_stage<ID>(sc, bp_smem, red, scratch_floats, t, s, row0, R); break;
+                SQ_STAGE_CASE(BS_CANVAS) SQ_STAGE_CASE(BS_COMPACT) SQ_STAGE_CASE(BS_DISC_POST) SQ_STAGE_CASE(BS_DISC_A)
+                SQ_STAGE_CASE(BS_DISC_B) SQ_STAGE_CASE(BS_DISC_C) SQ_STAGE_CASE(BS_LAT_PRE) SQ_STAGE_CASE(BS_PROP_A)
+                SQ_STAGE_CASE(BS_PROP_B) SQ_STAGE_CASE(BS_PROP_C) SQ_STAGE_CASE(BS_PROP_D) SQ_STAGE_CASE(BS_PROP_E)
+                SQ_STAGE_CASE(BS_PROP_F) SQ_STAGE_CASE(BS_STN1) SQ_STAGE_CASE(BS_PRIOR_PRE) SQ_STAGE_CASE(BS_PGRU_A)
+                SQ_STAGE_CASE(BS_PGRU_B) SQ_STAGE_CASE(BS_FINAL_STATES)
+#undef SQ_STAGE_CASE
+                default: break;
+            }
+        } else if (kind == OP_DGRAD) {
+            if (sop.d.ny == 1) {                    // at most 8 operand rows per cluster: one MMA n-tile
+                switch (sop.act) {
+                    case ACT_ELU: program_dgrad<ACT_ELU, 1>(sop, bp_smem, row0, R, sc.rows); break;
+                    case ACT_TANH: program_dgrad<ACT_TANH, 1>(sop, bp_smem, row0, R, sc.rows); break;
+                    case ACT_SIGMOID: program_dgrad<ACT_SIGMOID, 1>(sop, bp_smem, row0, R, sc.rows); break;
+                    default: program_dgrad<ACT_NONE, 1>(sop, bp_smem, row0, R, sc.rows); break;
+                }
+            } else {                                // operand batched over slots
+                switch (sop.act) {
+                    case ACT_ELU: program_dgrad<ACT_ELU, BP_NTILE_MAX>(sop, bp_smem, row0, R, sc.rows); break;
+                    case ACT_SIGMOID: program_dgrad<ACT_SIGMOID, BP_NTILE_MAX>(sop, bp_smem, row0, R, sc.rows); break;
+                    default: program_dgrad<ACT_NONE, BP_NTILE_MAX>(sop, bp_smem, row0, R, sc.rows); break;
+                }
+            }
+        } else {
+            const int nr = min(R, sc.rows - row0);
+            float* p = sop.zp + (size_t)row0 * sop.zstride;
+            const long long n = (long long)nr * sop.zstride;
+            const int ctid = cluster_rank() * BP_THREADS + tid, cn = cluster_size() * BP_THREADS;
+            for (long long j = ctid; j < n; j += cn) p[j] = 0.f;
+        }
+#ifdef SQAIR_PROG_PROFILE
+        __syncthreads();
+        const long long pt1 = clock64();
+#endif
+        if (sop.nobar) __syncthreads(); else cluster_sync_rel_acq();
+#ifdef SQAIR_PROG_PROFILE
+        if (blockIdx.x == 0 && tid == 0) {
+            g_prog_prof[pclass][0] += pt1 - pt0; g_prog_prof[pclass][1] += clock64() - pt1; g_prog_prof[pclass][2] += 1;
+        }
+#endif
+    }
+}
+
+// W^T panels in fragment order from the row-major virtual matrix [KU + 1][NU] of the backward parameter buffer
+struct TPackTab {
+    int n;
+    struct E { long long src, dst; int KU, NU, Nc, ksteps, panel_floats; } e[L_COUNT];
+};
+__global__ void pack_tfrag_kernel(const __grid_constant__ TPackTab tab, float* __restrict__ bw) {
+    const TPackTab::E& E = tab.e[blockIdx.y];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < E.KU * E.NU; i += gridDim.x * blockDim.x) {
+        const int k = i / E.NU, n = i - k * E.NU;
+        const int panel = k / E.Nc, cc = k - panel * E.Nc;
+        const int fo = frag_off(E.ksteps, cc >> 4, n >> 3, cc & 15, n & 7);
+        float hi, lo;
+        split_weight(bw[E.src + i], hi, lo);
+        float* d = bw + E.dst + (long long)panel * E.panel_floats + (long long)(fo >> 7) * 256 + (fo & 127);
+        d[0] = hi; d[128] = lo;
+    }
+}
+
+// layers that have a dgrad product in the reverse program get W^T panels for a cluster of C blocks
+static void build_tlayers(const Plan& plan, int C, TLayer* tl, int64_t* total, int ncolp = 8 * BP_NTILE_MAX) {
+    int64_t cur = (plan.bw_total + plan.bwt_total + 31) / 32 * 32;
+    for (int l = 0; l < L_COUNT; ++l) {
+        TLayer& T = tl[l];
+        memset(&T, 0, sizeof(T));
+        if (plan.L[l].nhead == 0) continue;
+        const LayerB& LB = plan.LB[l];
+        T.ksteps = (LB.NU + 7) / 8;
+        T.Nc = ((LB.KU + C - 1) / C + 15) / 16 * 16;
+        T.nmt = T.Nc / 16;
+        T.panel_floats = T.nmt * T.ksteps * 256;
+        T.w_off = cur;
+        cur += (int64_t)C * T.panel_floats;
+        int best = 1;
+        double best_cost = 1e30;
+        for (int ks = 1; ks <= BP_WARPS; ++ks) {
+            const int kper = (T.ksteps + ks - 1) / ks;
+            if (ks > 1 && (kper < 2 || (ks - 1) * kper >= T.ksteps)) continue;
+            if ((int64_t)ks * T.Nc * ncolp > BP_RED_FLOATS) continue;
+            const int rounds = (T.nmt * ks + BP_WARPS - 1) / BP_WARPS;
+            const double cost = (double)rounds * (kper + 3.0) + 0.5 * ks;
+            if (cost < best_cost) { best_cost = cost; best = ks; }
+        }
+        T.ksplit = best;
+        T.kper = (T.ksteps + best - 1) / best;
+    }
+    if (total) *total = cur;
+}
+
+// device copies of recorded programs, keyed by content (a backward call of the same shape on the same buffers records
+// the same bytes: the upload happens once; a CUDA graph of the call keeps pointing at the cached copy)
+struct ProgramEntry {
+    int device;
+    std::vector<char> host;
+    void* dev;
+};
+static std::mutex g_prog_mutex;
+static std::vector<ProgramEntry*> g_programs;
+
+static cudaError_t get_program(const std::vector<char>& bytes, cudaStream_t st, const void** out) {
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(g_prog_mutex);
+    for (ProgramEntry* pe : g_programs)
+        if (pe->device == device && pe->host.size() == bytes.size() && memcmp(pe->host.data(), bytes.data(), bytes.size()) == 0) {
+            *out = pe->dev;
+            return cudaSuccess;
+        }
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+    if (cs != cudaStreamCaptureStatusNone) return cudaErrorStreamCaptureUnsupported;   // run the shape eagerly once before capturing it
+    if (g_programs.size() >= 64) {              // rare: many distinct (shape, buffer) combinations; drop the oldest once idle
+        cudaDeviceSynchronize();
+        cudaFree(g_programs.front()->dev);
+        delete g_programs.front();
+        g_programs.erase(g_programs.begin());
+    }
+    ProgramEntry* pe = new ProgramEntry{device, bytes, nullptr};
+    e = cudaMalloc(&pe->dev, bytes.size());
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pe->dev, pe->host.data(), bytes.size(), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // once per program: every later call finds the table resident
+    if (e != cudaSuccess) { if (pe->dev) cudaFree(pe->dev); delete pe; return e; }
+    g_programs.push_back(pe);
+    *out = pe->dev;
+    return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------
 // backend
 // ---------------------------------------------------------------------------------------------
 struct CudaBackend {
@@ -477,6 +887,7 @@ struct CudaBackend {
     int scratch_bytes;
     cudaError_t err = cudaSuccess;
     long launches = 0, tc_launches = 0;
+    bool verbose = false;
 
     void check() {
         if (err == cudaSuccess) err = cudaGetLastError();
@@ -518,6 +929,10 @@ struct CudaBackend {
                 return;
             }
         }
+        if (verbose)
+            fprintf(stderr, "  wgrad on the mma.sync kernel: M %d K %d N %d ny %d  x base%%4 %d outer %d inner %d | dy base%%4 %d outer %d inner %d\n", A.M,
+                    A.K, A.N, A.ny, (int)((reinterpret_cast<uintptr_t>(A.x.p) / 4) % 4), A.x.outer, A.x.inner,
+                    (int)((reinterpret_cast<uintptr_t>(A.dy.p) / 4) % 4), A.dy.outer, A.dy.inner);
         const int tiles = ((A.N + WG_T - 1) / WG_T) * ((A.K + WG_T - 1) / WG_T);
         int msplit = (4 * 148 + tiles - 1) / tiles;
         const int max_split = (A.M + 4 * WG_MC - 1) / (4 * WG_MC);
@@ -561,6 +976,123 @@ struct CudaBackend {
     }
 };
 
+// Records the frame recursion (row stages, dgrad products, clears) into a BwdOp table and runs it as one persistent
+// cluster kernel as soon as an operation arrives that is not part of it (the weight-gradient GEMMs at the end, which
+// stay separate launches on the same stream).
+struct ProgramBackend {
+    CudaBackend& cb;
+    const BwdLayout& BL;
+    float* ws;
+    const float* bw;             // backward parameter buffer (the W^T panels follow the matrices)
+    int R, C, rows, scratch_floats;
+    TLayer tl[L_COUNT];
+    BwdProgramHdr hdr;
+    bool have_ctx = false, bad = false;
+    std::vector<BwdOp> ops;
+    long program_launches = 0;
+
+    ProgramBackend(CudaBackend& c, const BwdLayout& bl, float* workspace, const float* bwp, int r, int cl, int nrows, int scratch)
+        : cb(c), BL(bl), ws(workspace), bw(bwp), R(r), C(cl), rows(nrows), scratch_floats(scratch) {
+        memset((void*)&hdr, 0, sizeof(hdr));
+        build_tlayers(cb.sh->plan, C, tl, nullptr);
+    }
+    BwdOp& push(int kind) {
+        BwdOp op;
+        memset((void*)&op, 0, sizeof(op));
+        op.kind = kind;
+        ops.push_back(op);
+        return ops.back();
+    }
+    bool recording() const { return have_ctx; }      // the program starts with the first row stage
+    template <int STAGE>
+    void stage(const BwdCtx& c, int t, int s) {
+        if (!have_ctx) { hdr.ctx = c; have_ctx = true; }
+        BwdOp& op = push(OP_STAGE);
+        op.stage = STAGE; op.t = t; op.s = s;
+        float* const cy[6] = {c.gZc, c.gTc, c.gPc, c.gZo, c.gTo, c.gPo};
+        for (int i = 0; i < 6; ++i) op.carry[i] = cy[i];
+    }
+    void dgrad(const DgradArgs& A) {
+        if (!recording()) { bad = true; return; }
+        if (A.N > BP_XMAX_N) { bad = true; return; }
+        const int act = A.y.p ? A.act : ACT_NONE;
+        if (act == ACT_SOFTPLUS || (A.ny > 1 && act == ACT_TANH)) { bad = true; return; }       // not instantiated (no such product in the reverse program)
+        BwdOp& op = push(OP_DGRAD);
+        op.d = A;
+        op.tl = tl[A.layer];
+        op.d.w = bw + op.tl.w_off;                 // panel 0 of W^T (the row-major matrix is not used by this kernel)
+        op.act = A.y.p ? A.act : ACT_NONE;
+    }
+    void zero_rows(float* p, int stride) {
+        if (!ops.empty() && ops.back().kind == OP_ZERO) ops.back().nobar = 1;
+        BwdOp& op = push(OP_ZERO);
+        op.zp = p; op.zstride = stride;
+    }
+    void zero(float* p, int64_t n) {
+        if (n <= 0) return;
+        if (!recording()) { cb.zero(p, n); return; }            // clears ahead of the program: plain memsets, in stream order
+        if (p == ws + BL.frame_begin && n == BL.frame_end - BL.frame_begin) {
+            for (int i = 0; i < BL.nframe; ++i) zero_rows(ws + BL.frame_off[i], BL.frame_stride[i]);
+        } else if (n % rows == 0) {
+            zero_rows(p, (int)(n / rows));                       // a carried state-gradient set: [rows, n * width]
+        } else {
+            bad = true;
+        }
+    }
+    void flush() {
+        if (ops.empty() || cb.err != cudaSuccess) { ops.clear(); return; }
+        if (bad) { cb.err = cudaErrorInvalidValue; ops.clear(); return; }
+        // the carry fields of the header are patched per operation; keep the recorded bytes independent of the last frame
+        hdr.ctx.gZc = hdr.ctx.gTc = hdr.ctx.gPc = hdr.ctx.gZo = hdr.ctx.gTo = hdr.ctx.gPo = nullptr;
+        hdr.nops = (int)ops.size();
+        hdr.R = R;
+        std::vector<char> bytes(sizeof(hdr) + ops.size() * sizeof(BwdOp));
+        memcpy(bytes.data(), &hdr, sizeof(hdr));
+        memcpy(bytes.data() + sizeof(hdr), ops.data(), ops.size() * sizeof(BwdOp));
+        ops.clear();
+        have_ctx = false;
+        const void* dev = nullptr;
+        cudaError_t e = get_program(bytes, cb.st, &dev);
+        const int smem_floats = std::max(BP_NTILE_MAX * BP_XMAX_N * BP_XLD + BP_RED_FLOATS + 2 * (3 + BW_MAXSEG) * 8 * BP_NTILE_MAX, 4 * scratch_floats);
+        const int smem_bytes = smem_floats * (int)sizeof(float);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bwd_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e == cudaSuccess) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            const int ncl = (rows + R - 1) / R;
+            cfg.gridDim = dim3(ncl * C); cfg.blockDim = dim3(BP_THREADS); cfg.dynamicSmemBytes = (size_t)smem_bytes; cfg.stream = cb.st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = C > 1 ? 1 : 0;
+            e = cudaLaunchKernelEx(&cfg, bwd_program_kernel, (const BwdProgramHdr*)dev, scratch_floats);
+        }
+        if (cb.err == cudaSuccess) cb.err = e;
+        ++cb.launches; ++program_launches;
+#ifdef SQAIR_PROG_PROFILE
+        if (sqi::env_int("SQAIR_PROG_PRINT")) {
+            long long h[64][3];
+            cudaStreamSynchronize(cb.st);
+            cudaMemcpyFromSymbol(h, g_prog_prof, sizeof(h));
+            long long tb = 0, tw = 0;
+            for (int i = 0; i < 64; ++i) { tb += h[i][0]; tw += h[i][1]; }
+            fprintf(stderr, "reverse program, block 0 (classes: 0-17 stage id, 32+act dgrad over rows, 40+act dgrad over rows x slots, 48 clear)\n");
+            for (int i = 0; i < 64; ++i)
+                if (h[i][2]) fprintf(stderr, "  class %2d: n %6lld  body %8.0f cyc/op  barrier %8.0f cyc/op  share %.3f\n", i, h[i][2], (double)h[i][0] / h[i][2],
+                                     (double)h[i][1] / h[i][2], (double)(h[i][0] + h[i][1]) / (double)(tb + tw));
+            fprintf(stderr, "  total body %.3f Mcyc, barrier %.3f Mcyc\n", tb * 1e-6, tw * 1e-6);
+            memset(h, 0, sizeof(h));
+            cudaMemcpyToSymbol(g_prog_prof, h, sizeof(h));
+        }
+#endif
+    }
+    void wgrad(const WgradArgs& A) { flush(); cb.wgrad(A); }
+    void colsum(const ColsumArgs& A) { flush(); cb.colsum(A); }
+    void img_reduce(const float* dy, float* out, int TB, int K, int nh) { flush(); cb.img_reduce(dy, out, TB, K, nh); }
+    void unpack(const float* dwv, float* d_params) { flush(); cb.unpack(dwv, d_params); }
+    void small_to_params(const float* small, float* d_params, const POff& po) { flush(); cb.small_to_params(small, d_params, po); }
+};
+
 static std::string prepare(const sqair_cfg* cfg, Shape& sh, std::vector<ParamEntry>& tab) {
     std::string e = validate_cfg(*cfg);
     if (!e.empty()) return e;
@@ -581,7 +1113,12 @@ int sqair_query_train_sizes(const sqair_cfg* cfg, sqair_train_sizes* out) {
     const BwdLayout BL = build_bwd_layout(*cfg, sh.plan);
     out->stash_floats = SL.total;
     out->workspace_floats = BL.total;
-    out->backward_param_floats = sh.plan.bw_total + sh.plan.bwt_total;
+    {
+        TLayer tl[L_COUNT];
+        int64_t total = 0;
+        build_tlayers(sh.plan, sh.C, tl, &total);
+        out->backward_param_floats = total;             // matrices, transposed copies, W^T fragment panels
+    }
     return SQAIR_OK;
 }
 
@@ -595,8 +1132,24 @@ int sqair_pack_backward(const sqair_cfg* cfg, const float* params, float* bw_par
     cudaStream_t st = (cudaStream_t)stream;
     BPieceTab bt;
     fill_piece_tab(sh, bt);
-    CUDA_TRY(cudaMemsetAsync(bw_params, 0, (size_t)(sh.plan.bw_total + sh.plan.bwt_total) * sizeof(float), st));
+    TPackTab tt;
+    memset(&tt, 0, sizeof(tt));
+    int64_t bw_floats = 0;
+    {
+        TLayer tl[L_COUNT];
+        build_tlayers(sh.plan, sh.C, tl, &bw_floats);
+        for (int l = 0; l < L_COUNT; ++l) {
+            if (sh.plan.L[l].nhead == 0) continue;
+            const LayerB& LB = sh.plan.LB[l];
+            TPackTab::E& E = tt.e[tt.n++];
+            E.src = LB.bw_off; E.dst = tl[l].w_off; E.KU = LB.KU; E.NU = LB.NU; E.Nc = tl[l].Nc; E.ksteps = tl[l].ksteps;
+            E.panel_floats = tl[l].panel_floats;
+        }
+    }
+    CUDA_TRY(cudaMemsetAsync(bw_params, 0, (size_t)bw_floats * sizeof(float), st));
     pack_backward_kernel<<<dim3(32, bt.n), 256, 0, st>>>(bt, params, bw_params);
+    CUDA_TRY(cudaGetLastError());
+    pack_tfrag_kernel<<<dim3(32, tt.n), 256, 0, st>>>(tt, bw_params);       // from the matrices the kernel above assembled
     CUDA_TRY(cudaGetLastError());
     return SQAIR_OK;
 }
@@ -622,12 +1175,25 @@ int sqair_backward(const sqair_cfg* cfg, const float* params, const float* bw_pa
     CUDA_TRY(cudaFuncSetAttribute(dgrad_kernel<ACT_SOFTPLUS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_smem_bytes));
     CudaBackend be;
     be.st = (cudaStream_t)stream; be.sh = &sh; be.rows = cfg->B * cfg->K;
+    be.verbose = sqi::env_int("SQAIR_VERBOSE") > 1;
     be.scratch_bytes = bw_stage_scratch_floats(*cfg) * (int)sizeof(float);
     if (be.scratch_bytes > 48 * 1024) return fail(SQAIR_EUNSUPPORTED, "glimpses do not fit the shared memory of the canvas stage");
     static_assert(sizeof(BwdCtx) <= 4000, "BwdCtx must fit the kernel parameter space");
-    BwdDriver<CudaBackend> drv(be, *cfg, sh.plan, sh.plan.poc, BL, in);
-    drv.param_count_ = tab.back().offset + tab.back().count;
-    drv.run(d_params);
+    const int64_t n_params = tab.back().offset + tab.back().count;
+    if (sqi::env_int("SQAIR_BWD_LAUNCHES")) {           // one launch per operation (the round-2 path; kept for A/B timing and tests)
+        BwdDriver<CudaBackend> drv(be, *cfg, sh.plan, sh.plan.poc, BL, in);
+        drv.param_count_ = n_params;
+        drv.run(d_params);
+    } else {
+        const int scratch_floats = bw_stage_scratch_floats(*cfg);
+        if ((int64_t)std::max(BP_NTILE_MAX * BP_XMAX_N * BP_XLD + BP_RED_FLOATS + 2 * (3 + BW_MAXSEG) * 8 * BP_NTILE_MAX, 4 * scratch_floats) * 4 > 200 * 1024)
+            return fail(SQAIR_EUNSUPPORTED, "glimpses do not fit the shared memory of the reverse-program kernel");
+        ProgramBackend pb(be, BL, workspace, bw_params, sh.R, sh.C, cfg->B * cfg->K, scratch_floats);
+        BwdDriver<ProgramBackend> drv(pb, *cfg, sh.plan, sh.plan.poc, BL, in);
+        drv.param_count_ = n_params;
+        drv.run(d_params);
+        pb.flush();
+    }
     if (be.err != cudaSuccess) return sqi::cuda_fail(be.err, "sqair_backward");
     if (n_launches) *n_launches = (int32_t)be.launches;
     if (sqi::env_int("SQAIR_VERBOSE")) fprintf(stderr, "sqair_backward: %ld launches, %ld of them tcgen05 weight-gradient GEMMs\n", be.launches, be.tc_launches);

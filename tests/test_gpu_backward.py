@@ -75,3 +75,19 @@ def test_backward_is_reproducible_and_workspace_independent():
     b = TL.run_cuda_backward(cfg, imgs, params, noise)
     for k in a:
         np.testing.assert_allclose(a[k], b[k], rtol=1e-4, atol=1e-5 * max(np.abs(a[k]).max(), 1e-30), err_msg=k)
+
+
+@pytest.mark.parametrize('name', ['small_c2_T4_B3_K5_n4', 'no_rec_no_mask', 'max_slots_n8'])
+def test_program_kernel_matches_launch_per_operation(name, monkeypatch):
+    """The reverse program as one persistent cluster kernel (default; dgrad products on the tensor cores with the forward's
+    fp32-faithful tf32 split) against the same program issued as one launch per operation (SQAIR_BWD_LAUNCHES=1; fp32
+    FFMA dgrad): the two paths share the stage code and the weight-gradient GEMMs, not the product kernels."""
+    cfg = O.Cfg(**CASES[name])
+    imgs, params, noise = TL.make_inputs(cfg)
+    monkeypatch.delenv('SQAIR_BWD_LAUNCHES', raising=False)
+    a, _, la = TL.run_cuda_backward(cfg, imgs, params, noise, return_outputs=True)
+    monkeypatch.setenv('SQAIR_BWD_LAUNCHES', '1')
+    b, _, lb = TL.run_cuda_backward(cfg, imgs, params, noise, return_outputs=True)
+    assert la < lb / 2, (la, lb)                  # at BASELINE configs[1]: ~120 launches (program + weight-gradient GEMMs) instead of ~1 450
+    for k in a:
+        np.testing.assert_allclose(a[k], b[k], rtol=2e-4, atol=2e-5 * max(np.abs(b[k]).max(), 1e-30), err_msg=k)

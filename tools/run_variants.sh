@@ -3,5 +3,5 @@
 SHAPE=${SHAPE:-5:4}
 for so in sqair_b200/csrc/exp_*.so; do
   n=$(basename $so .so)
-  echo -n "$n: "; SQAIR_LIB=$PWD/$so SWEEP=$SHAPE python tools/sweep_rows.py 2>&1 | grep 'ms/step\|profile tid 0' | tail -2
+  echo -n "$n: "; SQAIR_LIB=$PWD/$so SWEEP=$SHAPE python tools/sweep_rows.py 2>&1 | grep "ms/step\|profile tid 0\|Error\|error" | tail -3
 done

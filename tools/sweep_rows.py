@@ -37,7 +37,8 @@ def main():
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         res['%d:%d' % (R, C)] = ms
-        print('R=%d C=%d ctas=%d smem=%d B: %.3f ms/step  %.0f frames/s' % (s.rows_per_cta, s.cluster_size, s.n_ctas, s.smem_bytes, ms, B * T / ms * 1e3), flush=True)
+        chk = ' '.join('%s %.6f' % (k, outs[k].double().sum().item()) for k in ('log_weights_per_timestep', 'canvas', 'presence', 'what'))
+        print('R=%d C=%d ctas=%d smem=%d B: %.3f ms/step  %.0f frames/s | %s' % (s.rows_per_cta, s.cluster_size, s.n_ctas, s.smem_bytes, ms, B * T / ms * 1e3, chk), flush=True)
     os.environ.pop('SQAIR_ROWS_PER_CTA', None); os.environ.pop('SQAIR_CLUSTER', None)
     print(json.dumps(res))
 
