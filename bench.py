@@ -277,14 +277,15 @@ def train_section(args, dev, world, rank, B_local, flush, label):
     bytes_alg = algorithmic_bytes(w, n_params) + 2 * 4 * ts.stash_floats + 2 * 4 * ts.workspace_floats + 7 * 4 * n_params
     step_s = total_ms / args.steps * 1e-3
     tens_peak = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
-    roof = dict(bound='latency (dependent chain of ~1 450 small launches; see DESIGN.md 6b.5)',
+    roof = dict(bound='latency (dependent chain of ~1 400 operations inside one persistent cluster kernel per pass; see DESIGN.md 6b.5)',
                 tensor=dict(achieved=flops / step_s / 1e12, peak=tens_peak, unit='TFLOP/s', frac=flops / step_s / 1e12 / tens_peak,
                             algorithmic_flops=flops),
                 hbm=dict(achieved=bytes_alg / step_s / 1e9, peak=peaks['hbm_gbs'], unit='GB/s', frac=bytes_alg / step_s / 1e9 / peaks['hbm_gbs'],
                          algorithmic_bytes=bytes_alg),
                 peak_source=which,
-                kernels='forward+stash 7.9 ms (sqair_sequence_kernel<5,true>), ~850 dgrad_kernel 6-7 ms, 38 wgrad_tc_kernel (tcgen05) + 23 '
-                        'wgrad_addr_kernel 1.3 ms, bwd_stage_kernel 3 ms at B=32 (profiles/r02_train_step_launches.txt)')
+                kernels='forward+stash 7.9 ms (sqair_sequence_kernel<5,true>), reverse program 9.7 ms (bwd_program_kernel: 850 dgrad products '
+                        '+ 440 row stages + clears, cluster barriers in between), 38 wgrad_tc_kernel (tcgen05) + 23 wgrad_addr_kernel 1.4 ms at B=32 '
+                        '(profiles/r02b_train_step_launches.txt)')
     return dict(step='noise + forward(stash) + objective + backward (CUDA-graph replay) + all-reduce(flat gradient, NCCL) + RMSProp + re-pack',
                 value=frames / (total_ms * 1e-3), unit='frames/s', ms_per_step=total_ms / args.steps,
                 scaling=label, sequences_per_gpu=B_local, global_batch=n_global,

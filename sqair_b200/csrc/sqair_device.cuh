@@ -268,7 +268,7 @@ struct Job {
     const float* eps_what;   // [T][rows][2n][nw]
     const float* u_pres;     // [T][rows][2n]
     sqair_outputs out;
-    int debug_flags;         // tuning experiments only: 1 = skip the MMA math (garbage results), 4/8/16/32/64 skip other stages
+    int debug_flags;         // tuning experiments only: 1 = skip the MMA math (garbage results), 4/8/16/32/64 skip other stages, 128 / 256 skip the stash copies of the element-wise stages / of the dense epilogue
     const float* ltab;       // layer table of this launch shape: L_COUNT x DESC_WORDS words (library-owned device buffer)
     float* stash;            // training stash (build_stash layout) or nullptr (inference)
     // generation (seq.py:46,198-203 `sample_from_prior` / `generate_after`): a second noise set for the draws from the
@@ -578,7 +578,7 @@ SQ_DEVNI bool dense(Ctx& c, const float* SQ_RESTRICT prm, const float* SQ_RESTRI
             } else {
                 SQ_SM[off] = v;
             }
-            if (TR && stash != nullptr && H.st_off >= 0 && row0 + r < P.rows && (L.split || c.rank() == 0))
+            if (TR && stash != nullptr && !(dbg & 256) && H.st_off >= 0 && row0 + r < P.rows && (L.split || c.rank() == 0))
                 stash[(size_t)H.st_off + ((size_t)(st_t * P.rows + row0 + r) * H.st_entries + st_entry) * H.st_width + j] = v;
         }
     }
@@ -684,7 +684,7 @@ struct Block {
     // shared memory at smem_off + f * fstride + r.  The (replicated) state is split by features across the cluster's
     // blocks; consecutive threads write consecutive features of one row.
     SQ_DEV void stash_copy(int sig, int t, int entry, int smem_off, int fstride, int nfeat, int col0 = 0) const {
-        if (!TR || stash_ == nullptr) return;
+        if (!TR || stash_ == nullptr || (dbg_ & 128)) return;
         const Sig g = P.st[sig];
         const int per = (nfeat + c.ncta() - 1) / c.ncta(), f0 = c.rank() * per;
         const int cnt = (f0 + per < nfeat ? f0 + per : nfeat) - f0;

@@ -756,7 +756,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) bwd_program_kernel(const BwdPro
                 default: break;
             }
         } else if (kind == OP_DGRAD) {
-            if (sop.d.ny == 1) {                    // at most 8 operand rows per cluster: one MMA n-tile
+            if (sop.d.ny * R <= 8) {                // at most 8 operand rows per cluster: one MMA n-tile
                 switch (sop.act) {
                     case ACT_ELU: program_dgrad<ACT_ELU, 1>(sop, bp_smem, row0, R, sc.rows); break;
                     case ACT_TANH: program_dgrad<ACT_TANH, 1>(sop, bp_smem, row0, R, sc.rows); break;
@@ -766,6 +766,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) bwd_program_kernel(const BwdPro
             } else {                                // operand batched over slots
                 switch (sop.act) {
                     case ACT_ELU: program_dgrad<ACT_ELU, BP_NTILE_MAX>(sop, bp_smem, row0, R, sc.rows); break;
+                    case ACT_TANH: program_dgrad<ACT_TANH, BP_NTILE_MAX>(sop, bp_smem, row0, R, sc.rows); break;
                     case ACT_SIGMOID: program_dgrad<ACT_SIGMOID, BP_NTILE_MAX>(sop, bp_smem, row0, R, sc.rows); break;
                     default: program_dgrad<ACT_NONE, BP_NTILE_MAX>(sop, bp_smem, row0, R, sc.rows); break;
                 }
@@ -1016,7 +1017,7 @@ struct ProgramBackend {
         if (!recording()) { bad = true; return; }
         if (A.N > BP_XMAX_N) { bad = true; return; }
         const int act = A.y.p ? A.act : ACT_NONE;
-        if (act == ACT_SOFTPLUS || (A.ny > 1 && act == ACT_TANH)) { bad = true; return; }       // not instantiated (no such product in the reverse program)
+        if (act == ACT_SOFTPLUS) { bad = true; return; }       // not instantiated (no such product in the reverse program)
         BwdOp& op = push(OP_DGRAD);
         op.d = A;
         op.tl = tl[A.layer];
@@ -1093,6 +1094,15 @@ struct ProgramBackend {
     void small_to_params(const float* small, float* d_params, const POff& po) { flush(); cb.small_to_params(small, d_params, po); }
 };
 
+// Launch shape of the reverse-program kernel: rows per cluster and cluster size.  Default: the forward's (R, C); its own
+// shared memory does not depend on the rows, so SQAIR_BWD_ROWS / SQAIR_BWD_CLUSTER may choose differently (tuning).
+static void program_shape(const Shape& sh, int& R, int& C) {
+    R = sh.R; C = sh.C;
+    const int er = sqi::env_int("SQAIR_BWD_ROWS"), ec = sqi::env_int("SQAIR_BWD_CLUSTER");
+    if (er >= 1 && er <= 24) R = er;
+    if (ec >= 1 && ec <= 8) C = ec;
+}
+
 static std::string prepare(const sqair_cfg* cfg, Shape& sh, std::vector<ParamEntry>& tab) {
     std::string e = validate_cfg(*cfg);
     if (!e.empty()) return e;
@@ -1116,7 +1126,9 @@ int sqair_query_train_sizes(const sqair_cfg* cfg, sqair_train_sizes* out) {
     {
         TLayer tl[L_COUNT];
         int64_t total = 0;
-        build_tlayers(sh.plan, sh.C, tl, &total);
+        int pr, pc;
+        program_shape(sh, pr, pc);
+        build_tlayers(sh.plan, pc, tl, &total);
         out->backward_param_floats = total;             // matrices, transposed copies, W^T fragment panels
     }
     return SQAIR_OK;
@@ -1137,7 +1149,9 @@ int sqair_pack_backward(const sqair_cfg* cfg, const float* params, float* bw_par
     int64_t bw_floats = 0;
     {
         TLayer tl[L_COUNT];
-        build_tlayers(sh.plan, sh.C, tl, &bw_floats);
+        int pr, pc;
+        program_shape(sh, pr, pc);
+        build_tlayers(sh.plan, pc, tl, &bw_floats);
         for (int l = 0; l < L_COUNT; ++l) {
             if (sh.plan.L[l].nhead == 0) continue;
             const LayerB& LB = sh.plan.LB[l];
@@ -1188,7 +1202,9 @@ int sqair_backward(const sqair_cfg* cfg, const float* params, const float* bw_pa
         const int scratch_floats = bw_stage_scratch_floats(*cfg);
         if ((int64_t)std::max(BP_NTILE_MAX * BP_XMAX_N * BP_XLD + BP_RED_FLOATS + 2 * (3 + BW_MAXSEG) * 8 * BP_NTILE_MAX, 4 * scratch_floats) * 4 > 200 * 1024)
             return fail(SQAIR_EUNSUPPORTED, "glimpses do not fit the shared memory of the reverse-program kernel");
-        ProgramBackend pb(be, BL, workspace, bw_params, sh.R, sh.C, cfg->B * cfg->K, scratch_floats);
+        int pr, pc;
+        program_shape(sh, pr, pc);
+        ProgramBackend pb(be, BL, workspace, bw_params, pr, pc, cfg->B * cfg->K, scratch_floats);
         BwdDriver<ProgramBackend> drv(pb, *cfg, sh.plan, sh.plan.poc, BL, in);
         drv.param_count_ = n_params;
         drv.run(d_params);
