@@ -881,6 +881,30 @@ static cudaError_t get_program(const std::vector<char>& bytes, cudaStream_t st, 
 // ---------------------------------------------------------------------------------------------
 // backend
 // ---------------------------------------------------------------------------------------------
+// The weight-gradient phase is ~60 independent GEMMs and column sums, a third of them small (K or N below 32): issued
+// round-robin on a few side streams (fork / join with events, which a stream capture follows) they overlap instead of
+// queueing behind each other.
+constexpr int WG_STREAMS = 4;
+static cudaError_t side_streams(cudaStream_t (&out)[WG_STREAMS]) {
+    static std::mutex mu;
+    static cudaStream_t cache[64][WG_STREAMS];
+    static bool have[64];
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return e;
+    if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!have[device]) {
+        for (int i = 0; i < WG_STREAMS; ++i) {
+            e = cudaStreamCreateWithFlags(&cache[device][i], cudaStreamNonBlocking);
+            if (e != cudaSuccess) return e;
+        }
+        have[device] = true;
+    }
+    for (int i = 0; i < WG_STREAMS; ++i) out[i] = cache[device][i];
+    return cudaSuccess;
+}
+
 struct CudaBackend {
     cudaStream_t st;
     const Shape* sh;
@@ -889,10 +913,43 @@ struct CudaBackend {
     cudaError_t err = cudaSuccess;
     long launches = 0, tc_launches = 0;
     bool verbose = false;
+    // fork / join of the weight-gradient phase
+    bool use_side = true, forked = false;
+    cudaStream_t side[WG_STREAMS];
+    cudaStream_t cur = nullptr;
+    int rr = 0, sticky = 0;
 
     void check() {
         if (err == cudaSuccess) err = cudaGetLastError();
         ++launches;
+    }
+    void note(cudaError_t e) { if (err == cudaSuccess) err = e; }
+    // stream of the next independent operation of the weight-gradient phase (`chain` more operations follow on the same one)
+    cudaStream_t pick(int chain = 0) {
+        if (!use_side) return st;
+        if (!forked) {
+            cudaEvent_t ev = nullptr;
+            note(side_streams(side));
+            note(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            if (err != cudaSuccess) { use_side = false; return st; }
+            note(cudaEventRecord(ev, st));
+            for (int i = 0; i < WG_STREAMS; ++i) note(cudaStreamWaitEvent(side[i], ev, 0));
+            note(cudaEventDestroy(ev));
+            forked = true;
+        }
+        if (sticky > 0) { --sticky; return cur; }
+        cur = side[rr++ % WG_STREAMS];
+        sticky = chain;
+        return cur;
+    }
+    void join() {
+        if (!forked) return;
+        for (int i = 0; i < WG_STREAMS; ++i) {
+            cudaEvent_t ev = nullptr;
+            note(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            if (ev) { note(cudaEventRecord(ev, side[i])); note(cudaStreamWaitEvent(st, ev, 0)); note(cudaEventDestroy(ev)); }
+        }
+        forked = false; sticky = 0;
     }
     template <int STAGE>
     void stage(const BwdCtx& c, int t, int s) {
@@ -922,10 +979,11 @@ struct CudaBackend {
         check();
     }
     void wgrad(const WgradArgs& A) {
+        const cudaStream_t ws_ = pick();
         {   // Blackwell path (sqair_wgrad_tc.cu): TMA + tcgen05.mma + TMEM, whenever TMA can describe both operands
             const sqi::TcOperand ox{A.x.p, A.x.outer, A.x.inner, A.ny}, oy{A.dy.p, A.dy.outer, A.dy.inner, A.ny};
             if (sqi::wgrad_tc_supported(ox, oy, A.M, A.K, A.N)) {
-                if (sqi::wgrad_tc(ox, oy, A.dw, A.ldw, A.M, A.K, A.N, st) != SQAIR_OK && err == cudaSuccess) err = cudaErrorInvalidValue;
+                if (sqi::wgrad_tc(ox, oy, A.dw, A.ldw, A.M, A.K, A.N, ws_) != SQAIR_OK && err == cudaSuccess) err = cudaErrorInvalidValue;
                 ++launches; ++tc_launches;
                 return;
             }
@@ -941,7 +999,7 @@ struct CudaBackend {
         if (msplit < 1) msplit = 1;
         const int m_per_block = ((A.M + msplit - 1) / msplit + WG_MC - 1) / WG_MC * WG_MC;
         msplit = (A.M + m_per_block - 1) / m_per_block;
-        wgrad_addr_kernel<<<dim3((A.N + WG_T - 1) / WG_T, (A.K + WG_T - 1) / WG_T, msplit), 128, 0, st>>>(A, m_per_block);
+        wgrad_addr_kernel<<<dim3((A.N + WG_T - 1) / WG_T, (A.K + WG_T - 1) / WG_T, msplit), 128, 0, ws_>>>(A, m_per_block);
         check();
     }
     void colsum(const ColsumArgs& A) {
@@ -951,7 +1009,7 @@ struct CudaBackend {
         if (msplit > max_split) msplit = max_split;
         if (msplit < 1) msplit = 1;
         const int m_per_block = (A.M + msplit - 1) / msplit;
-        cudaError_t e = launch_pdl(colsum_kernel, dim3(gx, (A.M + m_per_block - 1) / m_per_block), dim3(256), 0, st, A, m_per_block);
+        cudaError_t e = launch_pdl(colsum_kernel, dim3(gx, (A.M + m_per_block - 1) / m_per_block), dim3(256), 0, pick(), A, m_per_block);
         if (err == cudaSuccess) err = e;
         check();
     }
@@ -962,16 +1020,18 @@ struct CudaBackend {
         ++launches;
     }
     void img_reduce(const float* dy, float* out, int TB, int K, int nh) {
-        img_reduce_kernel<<<(TB * nh + 255) / 256, 256, 0, st>>>(dy, out, TB, K, nh);
+        img_reduce_kernel<<<(TB * nh + 255) / 256, 256, 0, pick(2)>>>(dy, out, TB, K, nh);      // its consumers (GEMM, column sum) follow on the same stream
         check();
     }
     void unpack(const float* dwv, float* d_params) {
         BPieceTab bt;
         fill_piece_tab(*sh, bt);
+        join();                                      // every virtual-matrix gradient is complete
         unpack_backward_kernel<<<dim3(32, bt.n), 256, 0, st>>>(bt, dwv, d_params);
         check();
     }
     void small_to_params(const float* small, float* d_params, const POff& po) {
+        join();
         small_to_params_kernel<<<1, 32, 0, st>>>(small, d_params, po);
         check();
     }
@@ -1190,6 +1250,7 @@ int sqair_backward(const sqair_cfg* cfg, const float* params, const float* bw_pa
     CudaBackend be;
     be.st = (cudaStream_t)stream; be.sh = &sh; be.rows = cfg->B * cfg->K;
     be.verbose = sqi::env_int("SQAIR_VERBOSE") > 1;
+    be.use_side = !sqi::env_int("SQAIR_WGRAD_ONE_STREAM");
     be.scratch_bytes = bw_stage_scratch_floats(*cfg) * (int)sizeof(float);
     if (be.scratch_bytes > 48 * 1024) return fail(SQAIR_EUNSUPPORTED, "glimpses do not fit the shared memory of the canvas stage");
     static_assert(sizeof(BwdCtx) <= 4000, "BwdCtx must fit the kernel parameter space");
@@ -1210,6 +1271,7 @@ int sqair_backward(const sqair_cfg* cfg, const float* params, const float* bw_pa
         drv.run(d_params);
         pb.flush();
     }
+    be.join();
     if (be.err != cudaSuccess) return sqi::cuda_fail(be.err, "sqair_backward");
     if (n_launches) *n_launches = (int32_t)be.launches;
     if (sqi::env_int("SQAIR_VERBOSE")) fprintf(stderr, "sqair_backward: %ld launches, %ld of them tcgen05 weight-gradient GEMMs\n", be.launches, be.tc_launches);
