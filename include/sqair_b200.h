@@ -169,14 +169,20 @@ int sqair_forward_generate(const sqair_cfg* cfg, const float* packed_params, con
                            const float* eps_where_prior, const float* eps_what_prior, const float* u_pres_prior,
                            int32_t generate_after, const sqair_outputs* out, void* stream);
 
-/* canonical flat parameters -> backward parameter buffer (once per parameter update, like sqair_pack_params). */
+/* canonical flat parameters -> backward parameter buffer (once per parameter update, like sqair_pack_params): every layer's
+ * virtual matrix row-major and transposed (launch-per-operation path, weight-gradient scatter) and W^T as tensor-core
+ * fragment panels for the reverse-program kernel; sqair_query_train_sizes gives the size. */
 int sqair_pack_backward(const sqair_cfg* cfg, const float* params, float* bw_params, void* stream);
 
 /* Gradient of the training target w.r.t. every variable of sqair_param_layout (canonical flat layout, overwritten).
  * d_log_weights / d_discrete_log_prob: [B*K] from sqair_objective_grad (d_discrete_log_prob may be NULL = zeros: the
  * `-elbo_iwae` target of model.py:156).  `params` is the canonical flat buffer the packed copies were made from; obs and
  * the noise tensors are the ones the forward call consumed.  *n_launches (nullable) receives the number of kernels and
- * memsets enqueued.  Asynchronous on `stream`; capturable in a CUDA graph after one warm-up call. */
+ * memsets enqueued.  The frame recursion runs as ONE persistent cluster kernel interpreting an operation table that the
+ * library records and caches per (configuration, buffer addresses); the first call with new buffers uploads the table and
+ * synchronises `stream` once.  Otherwise asynchronous on `stream` (the weight-gradient GEMMs fork onto library-owned side
+ * streams and join back before the call returns control of `stream`); capturable in a CUDA graph after one eager call with
+ * the same buffers.  SQAIR_BWD_LAUNCHES=1 selects the launch-per-operation path instead. */
 int sqair_backward(const sqair_cfg* cfg, const float* params, const float* bw_params, const float* obs,
                    const float* eps_where, const float* eps_what, const float* stash,
                    const float* d_log_weights, const float* d_discrete_log_prob,

@@ -139,8 +139,9 @@ class SequentialAIR(object):
         (VIMCO / T when K > 1, else -elbo_iwae / T: model.py:150-158) w.r.t. every variable -- the work of
         `opt.compute_gradients(target)` (model.py:160).  Returns (outputs, objective dict, flat gradient in
         `sqair_param_layout` order).  The returned tensors live in per-shape buffers that the next call overwrites.
-        The ~1 450 launches of the backward pass are replayed from a CUDA graph after the first call of a shape (all
-        its operands live in the per-shape buffers, so the graph is static): 14.5 -> 12.2 ms at BASELINE configs[1]."""
+        The backward pass (one persistent reverse-program kernel + ~120 weight-gradient launches on four streams) is
+        replayed from a CUDA graph after the first call of a shape (all its operands live in the per-shape buffers, so
+        the graph is static; the first, eager call also uploads the program table the graph then refers to)."""
         if obs.dim() == 5:
             if obs.shape[-1] != 1:
                 raise NotImplementedError('multi-channel frames')
