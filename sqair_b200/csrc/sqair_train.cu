@@ -854,11 +854,14 @@ static cudaError_t get_program(const std::vector<char>& bytes, cudaStream_t st, 
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess) return e;
     std::lock_guard<std::mutex> lock(g_prog_mutex);
-    for (ProgramEntry* pe : g_programs)
+    for (size_t i = g_programs.size(); i-- > 0;) {          // most recently used last: the common case is one comparison
+        ProgramEntry* pe = g_programs[i];
         if (pe->device == device && pe->host.size() == bytes.size() && memcmp(pe->host.data(), bytes.data(), bytes.size()) == 0) {
+            if (i + 1 != g_programs.size()) { g_programs.erase(g_programs.begin() + i); g_programs.push_back(pe); }
             *out = pe->dev;
             return cudaSuccess;
         }
+    }
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
     if (cs != cudaStreamCaptureStatusNone) return cudaErrorStreamCaptureUnsupported;   // run the shape eagerly once before capturing it
@@ -884,7 +887,7 @@ static cudaError_t get_program(const std::vector<char>& bytes, cudaStream_t st, 
 // The weight-gradient phase is ~60 independent GEMMs and column sums, a third of them small (K or N below 32): issued
 // round-robin on a few side streams (fork / join with events, which a stream capture follows) they overlap instead of
 // queueing behind each other.
-constexpr int WG_STREAMS = 4;
+constexpr int WG_STREAMS = 8;          // upper bound; SQAIR_WGRAD_STREAMS picks how many are used (measured: 2 -> 11.00, 4 -> 10.71, 6 -> 10.53, 8 -> 10.53 ms per backward)
 static cudaError_t side_streams(cudaStream_t (&out)[WG_STREAMS]) {
     static std::mutex mu;
     static cudaStream_t cache[64][WG_STREAMS];
@@ -915,6 +918,7 @@ struct CudaBackend {
     bool verbose = false;
     // fork / join of the weight-gradient phase
     bool use_side = true, forked = false;
+    int nside = 8;
     cudaStream_t side[WG_STREAMS];
     cudaStream_t cur = nullptr;
     int rr = 0, sticky = 0;
@@ -933,18 +937,18 @@ struct CudaBackend {
             note(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             if (err != cudaSuccess) { use_side = false; return st; }
             note(cudaEventRecord(ev, st));
-            for (int i = 0; i < WG_STREAMS; ++i) note(cudaStreamWaitEvent(side[i], ev, 0));
+            for (int i = 0; i < nside; ++i) note(cudaStreamWaitEvent(side[i], ev, 0));
             note(cudaEventDestroy(ev));
             forked = true;
         }
         if (sticky > 0) { --sticky; return cur; }
-        cur = side[rr++ % WG_STREAMS];
+        cur = side[rr++ % nside];
         sticky = chain;
         return cur;
     }
     void join() {
         if (!forked) return;
-        for (int i = 0; i < WG_STREAMS; ++i) {
+        for (int i = 0; i < nside; ++i) {
             cudaEvent_t ev = nullptr;
             note(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             if (ev) { note(cudaEventRecord(ev, side[i])); note(cudaStreamWaitEvent(st, ev, 0)); note(cudaEventDestroy(ev)); }
@@ -1251,6 +1255,7 @@ int sqair_backward(const sqair_cfg* cfg, const float* params, const float* bw_pa
     be.st = (cudaStream_t)stream; be.sh = &sh; be.rows = cfg->B * cfg->K;
     be.verbose = sqi::env_int("SQAIR_VERBOSE") > 1;
     be.use_side = !sqi::env_int("SQAIR_WGRAD_ONE_STREAM");
+    if (sqi::env_int("SQAIR_WGRAD_STREAMS") >= 1 && sqi::env_int("SQAIR_WGRAD_STREAMS") <= WG_STREAMS) be.nside = sqi::env_int("SQAIR_WGRAD_STREAMS");
     be.scratch_bytes = bw_stage_scratch_floats(*cfg) * (int)sizeof(float);
     if (be.scratch_bytes > 48 * 1024) return fail(SQAIR_EUNSUPPORTED, "glimpses do not fit the shared memory of the canvas stage");
     static_assert(sizeof(BwdCtx) <= 4000, "BwdCtx must fit the kernel parameter space");
