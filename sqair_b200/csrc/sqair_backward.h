@@ -867,6 +867,7 @@ struct BwdLayout {
     int64_t gPropRec, gDiscRec, gTnew, gPnew, gPH, gDH, gDIn, gExp, gHrn, gPri, gMask, gGlm, gLoc1, gHwbmk, gEnc, gRH, tA0, tA1;
     int64_t dwv_off;                  // [bw_total] virtual-matrix gradients
     int64_t img_dy_off;               // [T, B, nh] image-encoder dY summed over the particles of a sequence
+    int64_t bcast_dy_off;             // [T, rows, nh] dY summed over the slots (weight gradient against an operand shared by the slots)
     int nframe;                       // the arrays of the per-frame region, each [rows, frame_stride[i]] (cleared per row range
     int64_t frame_off[16];            //  by the persistent reverse-program kernel: every cluster clears the rows it owns)
     int frame_stride[16];
@@ -912,6 +913,7 @@ inline BwdLayout build_bwd_layout(const sqair_cfg& c, const Plan& plan) {
     L.tA0 = take((int64_t)rows * n * nh); L.tA1 = take((int64_t)rows * n * nh);
     L.dwv_off = take(plan.bw_total);
     L.img_dy_off = take((int64_t)T * c.B * nh);
+    L.bcast_dy_off = take((int64_t)T * rows * nh);
     L.total = cur;
     return L;
 }
@@ -1176,6 +1178,16 @@ struct BwdDriver {
         A.M = T * rows * ny; A.K = L.seg[segi].K; A.N = LB.NU; A.ny = ny;
         A.x = mk_addr(x.p + (size_t)frame0 * rows * x.outer, x.outer, x.inner);
         A.dy = mk_addr(c.dy[l] + (size_t)dy_e0 * c.dy_w[l], c.dy_e[l] * c.dy_w[l], c.dy_w[l]);
+        if (!bcast_used_ && ny > 1 && x.inner == 0 && x.outer > 0 && dy_e0 == 0 && c.dy_e[l] == ny && c.dy_w[l] <= nh && A.K >= 32 && LB.NU >= 32) {
+            bcast_used_ = true;                    // one scratch buffer: one user per backward call
+            // the operand is shared by the slots of a row (the discovery RNN's image / conditioning input): sum dY over the
+            // slots first -- a fifth of the reduction length, and rows TMA can address
+            float* red = ws + BL.bcast_dy_off;
+            be.img_reduce(c.dy[l], red, T * rows, ny, c.dy_w[l]);
+            A.M = T * rows; A.ny = 1;
+            A.x = mk_addr(x.p + (size_t)frame0 * rows * x.outer, x.outer, 0);
+            A.dy = mk_addr(red, c.dy_w[l], 0);
+        }
         A.dw = ws + BL.dwv_off + LB.bw_off + (size_t)LB.u0[segi] * LB.NU;
         A.ldw = LB.NU;
         be.wgrad(A);
@@ -1294,6 +1306,7 @@ struct BwdDriver {
         weight_grads(d_params);
     }
     int64_t param_count_ = 0;
+    bool bcast_used_ = false;
     int64_t plan_param_count() const { return param_count_; }
 };
 

@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(128) wgrad_addr_kernel(const __grid_constant__
             for (int q = 0; q < 4; ++q) acc[a][b][q] = 0.f;
     for (int m0 = m_begin; m0 < m_end; m0 += WG_MC) {
         __syncthreads();
-#pragma unroll 4
+#pragma unroll
         for (int mm = mm0; mm < WG_MC; mm += 2) {
             const int m = m0 + mm;
             float xv = 0.f, yv = 0.f;
@@ -998,7 +998,10 @@ struct CudaBackend {
                     (int)((reinterpret_cast<uintptr_t>(A.dy.p) / 4) % 4), A.dy.outer, A.dy.inner);
         const int tiles = ((A.N + WG_T - 1) / WG_T) * ((A.K + WG_T - 1) / WG_T);
         int msplit = (4 * 148 + tiles - 1) / tiles;
-        const int max_split = (A.M + 4 * WG_MC - 1) / (4 * WG_MC);
+        // layers with few output tiles are bound by the latency of a block's row loop, not by the reductions: one 32-row
+        // step per block (measured: 4 steps per block cost 50 us per launch whatever the layer)
+        const int steps_min = tiles <= 8 ? 1 : 4;
+        const int max_split = (A.M + steps_min * WG_MC - 1) / (steps_min * WG_MC);
         if (msplit > max_split) msplit = max_split;
         if (msplit < 1) msplit = 1;
         const int m_per_block = ((A.M + msplit - 1) / msplit + WG_MC - 1) / WG_MC * WG_MC;
@@ -1024,7 +1027,8 @@ struct CudaBackend {
         ++launches;
     }
     void img_reduce(const float* dy, float* out, int TB, int K, int nh) {
-        img_reduce_kernel<<<(TB * nh + 255) / 256, 256, 0, pick(2)>>>(dy, out, TB, K, nh);      // its consumers (GEMM, column sum) follow on the same stream
+        // its consumers follow on the same stream: the image encoder's GEMM and column sum, or the GEMM of a slot-shared operand
+        img_reduce_kernel<<<(TB * nh + 255) / 256, 256, 0, pick(2)>>>(dy, out, TB, K, nh);
         check();
     }
     void unpack(const float* dwv, float* d_params) {
