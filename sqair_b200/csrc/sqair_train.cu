@@ -1162,10 +1162,44 @@ struct ProgramBackend {
     void small_to_params(const float* small, float* d_params, const POff& po) { flush(); cb.small_to_params(small, d_params, po); }
 };
 
-// Launch shape of the reverse-program kernel: rows per cluster and cluster size.  Default: the forward's (R, C); its own
-// shared memory does not depend on the rows, so SQAIR_BWD_ROWS / SQAIR_BWD_CLUSTER may choose differently (tuning).
-static void program_shape(const Shape& sh, int& R, int& C) {
+// Launch shape of the reverse-program kernel: rows per cluster and cluster size.  Default: the forward's (R, C) -- except
+// that the forward's shared-memory budget sometimes forces clusters of fewer than 4 blocks (BASELINE configs[3]: R=4, C=3),
+// while this kernel's shared memory does not depend on the rows: then C = 4 with as many rows per cluster as one wave of
+// resident clusters needs (configs[3]: 17.1 -> 15.6 ms per backward).  SQAIR_BWD_ROWS / SQAIR_BWD_CLUSTER override (tuning).
+static int program_max_clusters(int C, int smem_bytes) {
+    static std::mutex mu;
+    static int cached[64][9];
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 64 || C < 1 || C > 8) { cudaGetLastError(); return 32; }
+    std::lock_guard<std::mutex> lock(mu);
+    if (cached[device][C] == 0) {
+        int n = 0;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.blockDim = dim3(BP_THREADS); cfg.gridDim = dim3(C * 64); cfg.dynamicSmemBytes = (size_t)smem_bytes;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaFuncSetAttribute(bwd_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, bwd_program_kernel, &cfg);
+        if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = 128 / C; }      // what a 148-SM B200 answers for C = 4: 33
+        cached[device][C] = n;
+    }
+    return cached[device][C];
+}
+static int program_smem_bytes(const sqair_cfg& cfg) {
+    return std::max(BP_NTILE_MAX * BP_XMAX_N * BP_XLD + BP_RED_FLOATS + 2 * (3 + BW_MAXSEG) * 8 * BP_NTILE_MAX, 4 * bw_stage_scratch_floats(cfg)) *
+           (int)sizeof(float);
+}
+static void program_shape(const sqair_cfg& cfg, const Shape& sh, int& R, int& C) {
     R = sh.R; C = sh.C;
+    const int rows = cfg.B * cfg.K;
+    if (C < 4 && rows > 4 * R) {
+        C = 4;
+        const int maxcl = program_max_clusters(4, program_smem_bytes(cfg));
+        R = std::max(R, (rows + maxcl - 1) / maxcl);
+    }
     const int er = sqi::env_int("SQAIR_BWD_ROWS"), ec = sqi::env_int("SQAIR_BWD_CLUSTER");
     if (er >= 1 && er <= 24) R = er;
     if (ec >= 1 && ec <= 8) C = ec;
@@ -1195,7 +1229,7 @@ int sqair_query_train_sizes(const sqair_cfg* cfg, sqair_train_sizes* out) {
         TLayer tl[L_COUNT];
         int64_t total = 0;
         int pr, pc;
-        program_shape(sh, pr, pc);
+        program_shape(*cfg, sh, pr, pc);
         build_tlayers(sh.plan, pc, tl, &total);
         out->backward_param_floats = total;             // matrices, transposed copies, W^T fragment panels
     }
@@ -1218,7 +1252,7 @@ int sqair_pack_backward(const sqair_cfg* cfg, const float* params, float* bw_par
     {
         TLayer tl[L_COUNT];
         int pr, pc;
-        program_shape(sh, pr, pc);
+        program_shape(*cfg, sh, pr, pc);
         build_tlayers(sh.plan, pc, tl, &bw_floats);
         for (int l = 0; l < L_COUNT; ++l) {
             if (sh.plan.L[l].nhead == 0) continue;
@@ -1273,7 +1307,7 @@ int sqair_backward(const sqair_cfg* cfg, const float* params, const float* bw_pa
         if ((int64_t)std::max(BP_NTILE_MAX * BP_XMAX_N * BP_XLD + BP_RED_FLOATS + 2 * (3 + BW_MAXSEG) * 8 * BP_NTILE_MAX, 4 * scratch_floats) * 4 > 200 * 1024)
             return fail(SQAIR_EUNSUPPORTED, "glimpses do not fit the shared memory of the reverse-program kernel");
         int pr, pc;
-        program_shape(sh, pr, pc);
+        program_shape(*cfg, sh, pr, pc);
         ProgramBackend pb(be, BL, workspace, bw_params, pr, pc, cfg->B * cfg->K, scratch_floats);
         BwdDriver<ProgramBackend> drv(pb, *cfg, sh.plan, sh.plan.poc, BL, in);
         drv.param_count_ = n_params;
