@@ -275,8 +275,9 @@ def compare_gradients(got: dict, want: dict, rtol=1e-3, atol_rel=2e-4, floor: di
     return bad
 
 
-def run_cuda_backward(cfg: O.Cfg, imgs, params, noise, vimco=None, return_outputs=False):
-    """The product path: sqair_forward_train -> sqair_objective_grad -> sqair_backward, through the C ABI."""
+def run_cuda_backward(cfg: O.Cfg, imgs, params, noise, vimco=None, return_outputs=False, keep_alive=None):
+    """The product path: sqair_forward_train -> sqair_objective_grad -> sqair_backward, through the C ABI.  `keep_alive`: a
+    list that receives the device buffers of the call (so that a later call cannot get the same addresses)."""
     from sqair_b200 import ops
     dev = torch.device('cuda:0')
     ccfg = capi_cfg(cfg)
@@ -293,6 +294,8 @@ def run_cuda_backward(cfg: O.Cfg, imgs, params, noise, vimco=None, return_output
     ws = torch.full((ts.workspace_floats,), float('nan'), dtype=torch.float32, device=dev)
     d_params, launches = ops.backward(ccfg, flat, bw, obs, nz, stash, d_lw, d_lp if vimco else None, workspace=ws)
     torch.cuda.synchronize()
+    if keep_alive is not None:
+        keep_alive.append((flat, packed, bw, stash, nz, obs, out, d_lw, d_lp, ws, d_params))
     grads = {k: v.numpy() for k, v in O.unflatten_params(d_params.cpu(), cfg).items()}
     if return_outputs:
         return grads, {k: v.cpu().numpy() for k, v in out.items()}, launches

@@ -91,3 +91,35 @@ def test_program_kernel_matches_launch_per_operation(name, monkeypatch):
     assert la < lb / 2, (la, lb)                  # at BASELINE configs[1]: ~120 launches (program + weight-gradient GEMMs) instead of ~1 450
     for k in a:
         np.testing.assert_allclose(a[k], b[k], rtol=2e-4, atol=2e-5 * max(np.abs(b[k]).max(), 1e-30), err_msg=k)
+
+
+@pytest.mark.parametrize('shape', ['1:1', '3:2', '7:4', '12:8'])
+def test_program_kernel_launch_shapes(shape, monkeypatch):
+    """Rows per cluster / cluster size of the reverse-program kernel are free parameters (SQAIR_BWD_ROWS / SQAIR_BWD_CLUSTER):
+    a single block, a ragged last cluster (15 rows), operands wider than one pass of three MMA n-tiles (12 rows x 3 slots)."""
+    cfg = O.Cfg(T=2, B=5, K=3, n=3)
+    imgs, params, noise = TL.make_inputs(cfg)
+    monkeypatch.setenv('SQAIR_BWD_LAUNCHES', '1')
+    want = TL.run_cuda_backward(cfg, imgs, params, noise)
+    monkeypatch.delenv('SQAIR_BWD_LAUNCHES')
+    r, c = shape.split(':')
+    monkeypatch.setenv('SQAIR_BWD_ROWS', r)
+    monkeypatch.setenv('SQAIR_BWD_CLUSTER', c)
+    got = TL.run_cuda_backward(cfg, imgs, params, noise)
+    for k in want:
+        np.testing.assert_allclose(got[k], want[k], rtol=2e-4, atol=2e-5 * max(np.abs(want[k]).max(), 1e-30), err_msg=k)
+
+
+def test_program_tables_are_cached_and_evicted():
+    """Every (configuration, buffer set) records its own operation table; the library keeps 64 of them.  More than 64 distinct
+    buffer sets (all kept alive, so the addresses differ) exercise the eviction path; results stay identical."""
+    cfg = O.Cfg(T=1, B=1, K=2, n=1)
+    imgs, params, noise = TL.make_inputs(cfg)
+    keep, first = [], None
+    for i in range(70):
+        g, outs, _ = TL.run_cuda_backward(cfg, imgs, params, noise, return_outputs=True, keep_alive=keep)
+        if first is None:
+            first = g
+        elif i % 23 == 0 or i == 69:
+            for k in first:
+                np.testing.assert_allclose(g[k], first[k], rtol=1e-4, atol=1e-5 * max(np.abs(first[k]).max(), 1e-30), err_msg=k)
