@@ -193,6 +193,7 @@ static int launch_sequence_impl(const Plan& plan, Job job, cudaStream_t st) {
 template <int R>
 static int launch_sequence(const Plan& plan, const Job& job, cudaStream_t st) {
     if (job.eps_where_prior) return launch_sequence_impl<R, false, true>(plan, job, st);
+    if (env_int("SQAIR_FORCE_TRAIN_KERNEL")) return launch_sequence_impl<R, true, false>(plan, job, st);      // tuning: the training instantiation without a stash
     return job.stash ? launch_sequence_impl<R, true, false>(plan, job, st) : launch_sequence_impl<R, false, false>(plan, job, st);
 }
 
