@@ -123,3 +123,16 @@ def test_program_tables_are_cached_and_evicted():
         elif i % 23 == 0 or i == 69:
             for k in first:
                 np.testing.assert_allclose(g[k], first[k], rtol=1e-4, atol=1e-5 * max(np.abs(first[k]).max(), 1e-30), err_msg=k)
+
+
+def test_long_sequence_program_matches_launches(monkeypatch):
+    """T = 100 (the roll-out length of BASELINE configs[4]): ~14 000 recorded operations in one table."""
+    cfg = O.Cfg(T=100, B=2, K=2, n=2)
+    imgs, params, noise = TL.make_inputs(cfg)
+    monkeypatch.delenv('SQAIR_BWD_LAUNCHES', raising=False)
+    a = TL.run_cuda_backward(cfg, imgs, params, noise)
+    monkeypatch.setenv('SQAIR_BWD_LAUNCHES', '1')
+    b = TL.run_cuda_backward(cfg, imgs, params, noise)
+    for k in a:
+        assert np.isfinite(a[k]).all(), k
+        np.testing.assert_allclose(a[k], b[k], rtol=2e-4, atol=2e-5 * max(np.abs(b[k]).max(), 1e-30), err_msg=k)
