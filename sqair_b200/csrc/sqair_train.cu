@@ -59,6 +59,8 @@ struct DevEx {
     }
     // dst[0..3] += the warp's sums of v[0..3] (all 32 lanes must call; one shared-memory atomic per warp and value)
     __device__ __forceinline__ void warp_add4(float* dst, const float (&v)[4]) {
+        // most warps of the canvas stage lie outside a glimpse: nothing to add (exact zeros), skip the 20 shuffles
+        if (!__any_sync(0xffffffffu, v[0] != 0.f || v[1] != 0.f || v[2] != 0.f || v[3] != 0.f)) return;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float x = v[q];
