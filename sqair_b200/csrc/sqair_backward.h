@@ -696,17 +696,24 @@ SQB_HD void bw_prop_f(const BwdCtx& c, EX& ex, int t, int s, int row) {
     if (ex.tid == 0) {
         const float* Z = sgp(c, S_Z, t, row, s);
         const float* pri = sgp(c, S_PRI, t, row, s);
-        const float mk = Z[nw + 4] * rec[F.pres];
-        const float cq = -c.gw[row] * mk, cp = c.gw[row] * mk;
         const float* gr = c.gPropRec + ((size_t)row * (n + 1) + e) * c.zw;
         const float* eps = c.eps_where + (((size_t)t * c.rows + row) * (2 * n) + s) * 4;
         float* gpri = c.gPri + ((size_t)row * n + s) * c.npri;
         float* gzo = c.gZo + ((size_t)row * n + s) * c.zw;
-        float x[4], loc[4], sd[4], L[4][4], y[4], w[4], gx[4], cs[4][4];
-        for (int i = 0; i < 4; ++i) { x[i] = rec[F.where + i]; loc[i] = rec[F.where_loc + i]; sd[i] = rec[F.where_scale + i]; }
+        // every input first (independent loads, one memory round trip), then the arithmetic, then the stores: interleaved
+        // read-modify-writes would serialise a dozen L2 round trips in this single-thread section
+        float x[4], loc[4], sd[4], L[4][4], y[4], w[4], gx[4], cs[4][4], pmu[4], psd[4], grv[4], ev[4], gpm[4], gps[4], gz[4], chol[10];
+        const float mk = Z[nw + 4] * rec[F.pres], up = c.gw[row];
+        for (int i = 0; i < 4; ++i) {
+            x[i] = rec[F.where + i]; loc[i] = rec[F.where_loc + i]; sd[i] = rec[F.where_scale + i];
+            pmu[i] = pri[1 + i]; psd[i] = pri[5 + nw + i]; grv[i] = gr[nw + i]; ev[i] = eps[i];
+            gpm[i] = gpri[1 + i]; gps[i] = gpri[5 + nw + i]; gz[i] = gzo[nw + i];
+        }
+        for (int i = 0; i < 10; ++i) chol[i] = c.prm[c.po.cholesky + i];
+        const float cq = -up * mk, cp = up * mk;
         for (int i = 0; i < 4; ++i)
             for (int j = 0; j < 4; ++j) {
-                cs[i][j] = j <= i ? c.prm[c.po.cholesky + chol_idx(i, j)] : 0.f;
+                cs[i][j] = j <= i ? chol[chol_idx(i, j)] : 0.f;
                 L[i][j] = j <= i ? cs[i][j] * sd[i] + (i == j ? sd[i] : 0.f) : 0.f;
             }
         for (int i = 0; i < 4; ++i) {                       // L y = x - loc
@@ -719,26 +726,29 @@ SQB_HD void bw_prop_f(const BwdCtx& c, EX& ex, int t, int s, int row) {
             for (int j = i + 1; j < 4; ++j) a -= L[j][i] * w[j];
             w[i] = a / L[i][i];
         }
-        float d3[8], dso = 0.f;
+        float d3[8], dso = 0.f, dchol[10];
+        for (int i = 0; i < 10; ++i) dchol[i] = 0.f;
         for (int i = 0; i < 4; ++i) {
-            const NormG p = normal_lp_grad(x[i], pri[1 + i], pri[5 + nw + i]);
-            gx[i] = gr[nw + i] + stn[i] + cp * p.dx + cq * (-w[i]);
-            gpri[1 + i] += cp * p.dmu;
-            gpri[5 + nw + i] += cp * p.dsd;
+            const NormG p = normal_lp_grad(x[i], pmu[i], psd[i]);
+            gx[i] = grv[i] + stn[i] + cp * p.dx + cq * (-w[i]);
+            gpm[i] += cp * p.dmu;
+            gps[i] += cp * p.dsd;
         }
         for (int i = 0; i < 4; ++i) {
             const float dloc = gx[i] + cq * w[i];
-            gzo[nw + i] += dloc;
+            gz[i] += dloc;
             d3[i] = c.cfg.where_update_scale * dloc;
             float dsd = 0.f;
             for (int j = 0; j <= i; ++j) {
-                const float dL = gx[i] * eps[j] + cq * (w[i] * y[j] - (i == j ? 1.f / L[i][i] : 0.f));
+                const float dL = gx[i] * ev[j] + cq * (w[i] * y[j] - (i == j ? 1.f / L[i][i] : 0.f));
                 dsd += dL * (cs[i][j] + (i == j ? 1.f : 0.f));
-                SQB_AADD(c.small + SM_CHOL + chol_idx(i, j), dL * sd[i]);
+                dchol[chol_idx(i, j)] += dL * sd[i];
             }
             d3[4 + i] = dsd * -expm1f(-(sd[i] - 1e-2f));
             dso += d3[4 + i];
         }
+        for (int i = 0; i < 4; ++i) { gpri[1 + i] = gpm[i]; gpri[5 + nw + i] = gps[i]; gzo[nw + i] = gz[i]; }
+        for (int i = 0; i < 10; ++i) SQB_AADD(c.small + SM_CHOL + i, dchol[i]);
         SQB_AADD(c.small + SM_PSO, dso);
         float* dy3 = dyp(c, L_PT3, t, row, s);
         for (int i = 0; i < 8; ++i) dy3[i] = tp[i] = d3[i];
