@@ -283,8 +283,8 @@ def train_section(args, dev, world, rank, B_local, flush, label):
                 hbm=dict(achieved=bytes_alg / step_s / 1e9, peak=peaks['hbm_gbs'], unit='GB/s', frac=bytes_alg / step_s / 1e9 / peaks['hbm_gbs'],
                          algorithmic_bytes=bytes_alg),
                 peak_source=which,
-                kernels='forward+stash 7.9 ms (sqair_sequence_kernel<5,true>), reverse program 9.7 ms (bwd_program_kernel: 850 dgrad products '
-                        '+ 440 row stages + clears, cluster barriers in between), 38 wgrad_tc_kernel (tcgen05) + 23 wgrad_addr_kernel 1.4 ms at B=32 '
+                kernels='forward+stash 7.9 ms (sqair_sequence_kernel<5,true>), reverse program 9.3 ms (bwd_program_kernel: 850 dgrad products '
+                        '+ 440 row stages + clears, cluster barriers in between), 34 wgrad_tc_kernel (tcgen05) + 20 wgrad_addr_kernel + column sums 0.8 ms on eight streams at B=32 '
                         '(profiles/r02b_train_step_launches.txt)')
     return dict(step='noise + forward(stash) + objective + backward (CUDA-graph replay) + all-reduce(flat gradient, NCCL) + RMSProp + re-pack',
                 value=frames / (total_ms * 1e-3), unit='frames/s', ms_per_step=total_ms / args.steps,
