@@ -20,11 +20,13 @@
 #define SQ_DEV inline
 #define SQ_DEVNI inline
 #define SQ_LDG(p) (*(p))
+#define SQ_STCS(p, v) (*(p) = (v))
 #define SQ_RESTRICT
 #else
 #define SQ_DEV __device__ __forceinline__
 #define SQ_DEVNI __device__ __noinline__
 #define SQ_LDG(p) __ldg(p)
+#define SQ_STCS(p, v) __stcs((p), (v))      // streaming store (evict first): the stash is written once, read a pass later, and larger than L2
 #define SQ_RESTRICT __restrict__
 #endif
 
@@ -579,7 +581,7 @@ SQ_DEVNI bool dense(Ctx& c, const float* SQ_RESTRICT prm, const float* SQ_RESTRI
                 SQ_SM[off] = v;
             }
             if (TR && stash != nullptr && !(dbg & 256) && H.st_off >= 0 && row0 + r < P.rows && (L.split || c.rank() == 0))
-                stash[(size_t)H.st_off + ((size_t)(st_t * P.rows + row0 + r) * H.st_entries + st_entry) * H.st_width + j] = v;
+                SQ_STCS(&stash[(size_t)H.st_off + ((size_t)(st_t * P.rows + row0 + r) * H.st_entries + st_entry) * H.st_width + j], v);
         }
     }
     SQ_TICK(c, 3);
@@ -691,8 +693,8 @@ struct Block {
         for (int i = c.tid(); i < cnt * R; i += c.nthreads()) {
             const int r = i / cnt, f = f0 + i - r * cnt;
             if (valid_row(r))
-                stash_[(size_t)g.off + ((size_t)(t * P.rows + row0 + r) * g.entries + entry) * g.width + col0 + f] =
-                    SQ_SM[smem_off + f * fstride + r];
+                SQ_STCS(&stash_[(size_t)g.off + ((size_t)(t * P.rows + row0 + r) * g.entries + entry) * g.width + col0 + f],
+                        SQ_SM[smem_off + f * fstride + r]);
         }
     }
     enum { RA_QPRES = 0, RA_PPRES = 1, RA_NPROP = 2, RA_NDISC = 3, RA_QNUM = 4, RA_PNUM = 5, RA_LL = 6 };
