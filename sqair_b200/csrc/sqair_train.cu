@@ -1,10 +1,14 @@
 // sqair_train.cu -- CUDA backend of the backward pass (sqair_backward.h) and its C ABI.
 //
-// Kernels: `bwd_stage_kernel<STAGE>` (one thread block per row: the hand-written adjoints of the element-wise stages),
-// `dgrad_kernel` (dX = dY . W^T for M = rows or rows x slots, fp32 FFMA, activation derivative fused into the operand
-// load, input-segment scatter / accumulate fused into the epilogue), `wgrad_kernel` (dW += X^T . dY over M = T x rows x
-// slots on the tensor cores, fp32-faithful tf32 split), column sums, and the packing / unpacking between the reference's
-// variables and the per-layer virtual matrices.
+// The frame recursion of the reverse program runs as ONE persistent cluster kernel (`bwd_program_kernel`): the host records
+// the operations the driver issues (row stages = the hand-written adjoints of the element-wise stages, dgrad products
+// dX = dY . W^T on the tensor cores, clears) into a table, every cluster of thread blocks interprets it for the rows it owns,
+// cluster barriers separate dependent operations.  The weight gradients follow as GEMMs over M = T x rows x slots: tcgen05
+// (sqair_wgrad_tc.cu) where TMA can describe the operands, `wgrad_addr_kernel` (mma.sync, fp32-faithful tf32 split) otherwise,
+// column sums for the biases, all on a few side streams; then the scatter back to the reference's variables.
+// Kept for A/B measurements and tests (SQAIR_BWD_LAUNCHES=1): the same program as one launch per operation
+// (`bwd_stage_kernel<STAGE>`, `dgrad_kernel`: fp32 FFMA, programmatic dependent launch).  Also here: the fused optimiser
+// update and the sprite renderer of the data path.
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <math.h>
